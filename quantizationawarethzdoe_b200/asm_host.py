@@ -1,0 +1,180 @@
+"""Host-side preparation for the fused ASM kernels: geometry, separable transfer-function vectors,
+cached transfer-function tables and descriptor assembly.
+
+Everything here is O(Hp + Wp) per wavelength (or a one-off table build) and runs once per
+(shape, spacing, wavelengths, z); results are cached by the modules.  The fp32 operation order of
+the reference's create_kernel (Props/ASM_Prop.py:212-311) is kept so that the band-limit mask the
+kernel evaluates is bit-identical to the reference's.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def normalise_padding_scale(padding_scale, do_padding=True):
+    """ASM_prop.__init__ normalisation (Props/ASM_Prop.py:75-98) -> 2-element tensor or None."""
+    if not do_padding:
+        return None
+    err = False
+    if not torch.is_tensor(padding_scale):
+        if padding_scale is None:
+            padding_scale = torch.tensor([1, 1])
+        elif np.isscalar(padding_scale):
+            padding_scale = torch.tensor([padding_scale, padding_scale])
+        else:
+            padding_scale = torch.tensor(padding_scale)
+            if padding_scale.numel() != 2:
+                err = True
+    elif padding_scale.numel() == 1:
+        v = padding_scale.reshape(-1)[0]
+        padding_scale = torch.stack([v, v])
+    elif padding_scale.numel() == 2:
+        padding_scale = padding_scale.squeeze()
+    else:
+        err = True
+    if err:
+        raise Exception("Invalid value for argument 'padding_scale'.  Should be a real-valued non-negative scalar "
+                        "number or a two-element tuple/tensor containing real-valued non-negative scalar numbers.")
+    return padding_scale
+
+
+def compute_padding(H, W, padding_scale, do_padding):
+    """Props/ASM_Prop.py:119-136 -> (padH, padW, Hp, Wp)."""
+    if not do_padding:
+        return 0, 0, int(H), int(W)
+    pad_h = int(np.floor((float(padding_scale[0]) * H) / 2))
+    pad_w = int(np.floor((float(padding_scale[1]) * W) / 2))
+    return pad_h, pad_w, H + 2 * pad_h, W + 2 * pad_w
+
+
+def _as_f32_cpu(v):
+    return torch.as_tensor(v).detach().to(device="cpu", dtype=torch.float32)
+
+
+def _spacing2(spacing):
+    s = _as_f32_cpu(spacing).reshape(-1)
+    if s.numel() == 1:
+        s = s.repeat(2)
+    if s.numel() != 2:
+        raise ValueError("Spacing must be a 2-element tensor.")
+    return s
+
+
+def tf_vectors(Hp, Wp, spacing, wavelengths, z, bandlimit=True, bandlimit_type="exact"):
+    """Separable pieces of the band-limited transfer function in FFT-bin order (CPU fp32 tensors).
+
+    rowvec [C,Hp,4] = {Kx^2, Kx^2/(2 pi u_lim)^2, Kx^2/klam^2, 0}
+    colvec [C,Wp,4] = {Ky^2, Ky^2/klam^2,        Ky^2/(2 pi v_lim)^2, 0}
+    scal   [C,2]    = {klam^2, z}
+    The kernel keeps a bin iff rowvec.y+colvec.y <= 1 and rowvec.z+colvec.z <= 1 and klam^2-(Kx^2+Ky^2) >= 0
+    (Props/ASM_Prop.py:262, 297-301); for 'approx' (:303-306) the two flags are folded into .y."""
+    spacing = _spacing2(spacing)
+    lam = _as_f32_cpu(wavelengths).reshape(-1)
+    z = _as_f32_cpu(z).reshape(())
+    dx, dy = spacing[0:1], spacing[1:2]
+    C = lam.numel()
+    kx = (torch.linspace(0, Hp - 1, Hp) - (Hp // 2)) / Hp            # ASM_Prop.py:142
+    ky = (torch.linspace(0, Wp - 1, Wp) - (Wp // 2)) / Wp            # :143
+    Kx = 2 * torch.pi * kx / dx                                      # :245
+    Ky = 2 * torch.pi * ky / dy                                      # :246
+    Kx2, Ky2 = Kx ** 2, Ky ** 2                                      # :249
+    k_lam = 2 * torch.tensor(np.pi) / lam[:, None]                   # :253  [C,1]
+    k_lam2 = k_lam ** 2                                              # :254
+    rowvec = torch.zeros(C, Hp, 4)
+    colvec = torch.zeros(C, Wp, 4)
+    rowvec[:, :, 0] = Kx2[None, :]
+    colvec[:, :, 0] = Ky2[None, :]
+    if bandlimit:
+        if bandlimit_type == "exact":
+            du = ((2 * np.pi / dx) / (2 * Hp)) / (2 * np.pi)         # :290
+            dv = ((2 * np.pi / dy) / (2 * Hp)) / (2 * np.pi)         # :291 (Hp for both axes: reference quirk)
+            u_lim = 1 / torch.sqrt(((2 * du * z) ** 2) + 1) / lam[:, None]     # :293
+            v_lim = 1 / torch.sqrt(((2 * dv * z) ** 2) + 1) / lam[:, None]     # :294
+            rowvec[:, :, 1] = (Kx2[None, :]) / ((2 * np.pi * u_lim) ** 2)      # :297 first term
+            colvec[:, :, 1] = (Ky2[None, :]) / (k_lam ** 2)                    # :297 second term
+            rowvec[:, :, 2] = (Kx2[None, :]) / (k_lam ** 2)                    # :298 first term
+            colvec[:, :, 2] = (Ky2[None, :]) / ((2 * np.pi * v_lim) ** 2)      # :298 second term
+        elif bandlimit_type == "approx":
+            len_x = Hp * dx                                          # :274
+            len_y = Hp * dy                                          # :275
+            kx_max = 2 * np.pi / torch.sqrt(((2 * (1 / len_x) * z) ** 2) + 1) / lam[:, None]   # :303
+            ky_max = 2 * np.pi / torch.sqrt(((2 * (1 / len_y) * z) ** 2) + 1) / lam[:, None]   # :304
+            rowvec[:, :, 1] = (torch.abs(Kx)[None, :] > kx_max).float() * 2.0   # :306
+            colvec[:, :, 1] = (torch.abs(Ky)[None, :] > ky_max).float() * 2.0
+        else:
+            raise Exception("Should not be in this state.")
+    rowvec = torch.fft.ifftshift(rowvec, dim=1).contiguous()
+    colvec = torch.fft.ifftshift(colvec, dim=1).contiguous()
+    scal = torch.stack([k_lam2[:, 0], z.expand(C)], dim=1).contiguous()
+    return rowvec, colvec, scal
+
+
+def tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, bandlimit=True, bandlimit_type="exact"):
+    """Full centred transfer function [C,Hp,Wp] complex64 assembled on the host from the separable
+    vectors with the same torch CPU ops the reference uses per pixel (sqrt, exp(1j .)), so that the
+    cached-table mode reproduces the reference kernel bit for bit (incl. torch's CPU sqrt/exp)."""
+    rowvec, colvec, scal = tf_vectors(Hp, Wp, spacing, wavelengths, z, bandlimit, bandlimit_type)
+    rv = torch.fft.fftshift(rowvec, dim=1)
+    cv = torch.fft.fftshift(colvec, dim=1)
+    K2 = rv[:, :, None, 0] + cv[:, None, :, 0]
+    d = scal[:, 0, None, None] - K2
+    ang = scal[:, 1, None, None] * torch.sqrt(d)
+    out = torch.exp(1j * ang)
+    out[d < 0] = 0
+    keep = ((rv[:, :, None, 1] + cv[:, None, :, 1]) <= 1) & ((rv[:, :, None, 2] + cv[:, None, :, 2]) <= 1)
+    out[~keep] = 0
+    return out
+
+
+def tf_table_slot_order(Hc, slot_to_bin_fn=None):
+    """Centred kernel [C,Hp,Wp] -> table[c][slot_r][slot_c] = ifftshift(Hc)[c][bin(slot_r)][bin(slot_c)]."""
+    Hn = torch.fft.ifftshift(Hc, dim=(-2, -1))
+    pr = N.slot_to_bin(Hn.shape[-2], slot_to_bin_fn)
+    pc = N.slot_to_bin(Hn.shape[-1], slot_to_bin_fn)
+    return Hn[:, pr][:, :, pc].contiguous()
+
+
+def critical_distance(Hp, spacing, wavelengths):
+    """Zc of Props/ASM_Prop.py:280."""
+    spacing = _spacing2(spacing)
+    lam = _as_f32_cpu(wavelengths).reshape(-1)
+    dx = spacing[0:1]
+    return (Hp * dx ** 2) * torch.sqrt(1 - (torch.max(lam) / (2 * dx)) ** 2) / torch.max(lam)
+
+
+def doe_coefficients(wavelengths, epsilon, tand):
+    """[C,4] = {k_c, tand, sqrt(eps), sqrt(eps)-1} in fp32 (Components/QuantizedDOE.py:67-74)."""
+    lam = _as_f32_cpu(wavelengths).reshape(-1)
+    k = 2 * torch.pi / lam
+    eps = _as_f32_cpu(epsilon).reshape(())
+    td = _as_f32_cpu(tand).reshape(())
+    se = torch.sqrt(eps)
+    return torch.stack([k, td.expand_as(k), se.expand_as(k), (se - 1).expand_as(k)], dim=1).contiguous()
+
+
+def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, out_c0, tf_mode, tf_conj,
+               rowvec, colvec, scal, table, doe_mode, doe_base, hmap, coef, xsaved, gh, tw_h, tw_w, ws,
+               bc_chunk=0, tune_k2_cols=0, tune_lines=0):
+    """Fill a thz_asm_desc from tensors (device or, in the CPU replay tests, host tensors)."""
+    d = N.AsmDesc()
+    d.B, d.C, d.inH, d.inW, d.Hp, d.Wp = B, C, inH, inW, Hp, Wp
+    d.in_r0, d.in_c0, d.outH, d.outW, d.out_r0, d.out_c0 = in_r0, in_c0, outH, outW, out_r0, out_c0
+    d.x, d.y = N.ptr(x), N.ptr(y)
+    d.tf_mode, d.tf_conj = tf_mode, tf_conj
+    d.tf_rowvec, d.tf_colvec, d.tf_scal, d.tf_table = N.ptr(rowvec), N.ptr(colvec), N.ptr(scal), N.ptr(table)
+    d.doe_mode, d.doe_base = doe_mode, doe_base
+    d.doe_hmap, d.doe_coef, d.doe_xsaved, d.doe_gh = N.ptr(hmap), N.ptr(coef), N.ptr(xsaved), N.ptr(gh)
+    d.tw_h, d.tw_w = N.ptr(tw_h), N.ptr(tw_w)
+    d.ws = N.ptr(ws)
+    d.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
+    d.bc_chunk, d.tune_k2_cols, d.tune_lines, d.reserved = bc_chunk, tune_k2_cols, tune_lines, 0
+    return d
+
+
+def workspace_elems(B, C, inH, outH, Wp, bc_chunk=0):
+    nbc = B * C
+    chunk = bc_chunk if 0 < bc_chunk < nbc else nbc
+    return chunk * max(inH, outH) * Wp

@@ -1,0 +1,357 @@
+// Fused band-limited angular-spectrum propagation (+ DOE phase modulation) -- kernel phase bodies.
+//
+// Replaces the reference op chain  pad -> fftshift -> fft2(ortho) -> fftshift -> create_kernel ->
+// multiply -> ifftshift -> ifft2 -> ifftshift -> CenterCrop  (Props/ASM_Prop.py:340-361,
+// utils/Helper_Functions.py:150) and, when a height map is given, DOELayer.modulate
+// (Components/QuantizedDOE.py:92-126) with three kernels:
+//
+//   K1 row pass   : x rows (live rows only) --[* exp(-a h) e^{-i phi h}]--> zero-pad in smem -> row FFT -> T
+//   K2 column pass: T column tile -> zero-pad in smem -> column FFT -> * H(kx,ky,lambda,z) generated
+//                   in registers (or conj(H) for the adjoint) -> column iFFT -> cropped rows -> T (in place)
+//   K3 row pass   : T rows -> row iFFT -> crop -> scale -> y          (forward)
+//                                                 -> gx = g' conj(p), gh += Re(conj(g') x p gamma)   (adjoint)
+//
+// T holds spectra in the plans' digit-reversed order along both axes; nothing ever reorders it.
+#pragma once
+#include "thz_fft.cuh"
+
+struct AsmGeom {
+    int B, C;                 // batch, wavelengths
+    int inH, inW;             // live input region
+    int Hp, Wp;               // transform size
+    int in_r0, in_c0;         // where the input sits inside the Hp x Wp canvas
+    int outH, outW;           // output (crop) region
+    int out_r0, out_c0;
+};
+
+struct TfArgs {
+    int mode;                 // 0: generate H in registers from separable vectors; 1: cached table; 2: H == 1
+    int conj;                 // 1: use conj(H) (adjoint / backward)
+    const float4* rowvec;     // [C][Hp] {Kx^2, Kx^2/lim_u^2, Kx^2/klam^2, 0}  natural bin order
+    const float4* colvec;     // [C][Wp] {Ky^2, Ky^2/klam^2, Ky^2/lim_v^2, 0}  natural bin order
+    const float2* scal;       // [C]     {klam^2, z}
+    const cpx* table;         // [C][Hp][Wp] in (slot_r, slot_c) scrambled layout (mode 1)
+};
+
+struct DoeArgs {
+    const float* hmap;        // [inH][inW] height map, NULL = no DOE
+    const float4* coef;       // [C] {k_c, tand, sqrt(eps), sqrt(eps)-1}
+    float base;               // BASE_PLANE_THICKNESS (Components/QuantizedDOE.py:23)
+};
+
+// DOE transmission p = exp(-0.5 k (h+b) tand sqrt(eps)) * exp(-i k (h+b) (sqrt(eps)-1)), evaluated in the
+// reference's fp32 rounding order (Components/QuantizedDOE.py:73-77).
+THZ_HD cpx thz_doe_phase(float h, float4 cf, float base) {
+    const float hb = thz_add_rn(h, base);
+    const float la = thz_mul_rn(thz_mul_rn(thz_mul_rn(thz_mul_rn(-0.5f, cf.x), hb), cf.y), cf.z);
+    const float ph = thz_mul_rn(thz_mul_rn(-cf.x, hb), cf.w);
+    float sn, cs;
+    thz_sincos(ph, &sn, &cs);
+    const float a = expf(la);
+    return cmake(a * cs, a * sn);
+}
+
+// Transfer function value for (row bin vector entry rv, column entry cv): Props/ASM_Prop.py:249-301.
+THZ_HD cpx thz_tf_value(float4 rv, float4 cv, float2 sc, int conj) {
+    const float K2 = thz_add_rn(rv.x, cv.x);
+    const float d = thz_sub_rn(sc.x, K2);
+    const bool keep = (thz_add_rn(rv.y, cv.y) <= 1.0f) && (thz_add_rn(rv.z, cv.z) <= 1.0f) && !(d < 0.0f);
+    if (!keep) return cmake(0.f, 0.f);
+    const float ang = thz_mul_rn(sc.y, thz_sqrt_rn(d));
+    float sn, cs;
+    thz_sincos(ang, &sn, &cs);
+    return cmake(cs, conj ? -sn : sn);
+}
+
+// =============================================================================== K1: row forward
+struct RowFwdArgs {
+    const cpx* x;             // [nbc][inH][inW] (already offset to the chunk)
+    cpx* T;                   // [nbc][rowsT][Wp]
+    int nbc;                  // fields in this chunk
+    int rowsT;                // row pitch of one field in T (max(inH, outH))
+    int c0, C;                // wavelength index of field i is (c0 + i) % C
+    int inH, inW, Wp, in_c0;
+    int lines;                // rows per CTA
+    FftPlan plan;             // length Wp
+    const cpx* tw;
+    DoeArgs doe;
+    int conj_in;              // conjugate on load (inverse transforms via conj . FFT . conj)
+};
+
+THZ_HD void k1_load(const RowFwdArgs& a, cpx* s, int bx, int tid, int nthreads) {
+    const int pitch = thz_padded_len(a.Wp);
+    const int total_lines = a.nbc * a.inH;
+    for (int l = 0; l < a.lines; ++l) {
+        const int gl = bx * a.lines + l;
+        cpx* sl = s + l * pitch;
+        if (gl >= total_lines) {
+            for (int p = tid; p < a.Wp; p += nthreads) sl[thz_pad(p)] = cmake(0.f, 0.f);
+            continue;
+        }
+        const int f = gl / a.inH, r = gl - f * a.inH;
+        const cpx* xr = a.x + (size_t)gl * a.inW;
+        float4 cf = cmake4(0.f);
+        const float* hr = nullptr;
+        if (a.doe.hmap) {
+            cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
+            hr = a.doe.hmap + (size_t)r * a.inW;
+        }
+        for (int p = tid; p < a.Wp; p += nthreads) {
+            const int c = p - a.in_c0;
+            cpx v = cmake(0.f, 0.f);
+            if (c >= 0 && c < a.inW) {
+                v = xr[c];
+                if (a.conj_in) v.y = -v.y;
+                if (hr) v = cmul(v, thz_doe_phase(thz_ldg(hr + c), cf, a.doe.base));
+            }
+            sl[thz_pad(p)] = v;
+        }
+    }
+}
+
+THZ_HD void k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int nthreads) {
+    const int pitch = thz_padded_len(a.Wp);
+    const int total_lines = a.nbc * a.inH;
+    for (int l = 0; l < a.lines; ++l) {
+        const int gl = bx * a.lines + l;
+        if (gl >= total_lines) break;
+        const cpx* sl = s + l * pitch;
+        const int f = gl / a.inH, r = gl - f * a.inH;
+        cpx* tr = a.T + ((size_t)f * a.rowsT + r) * a.Wp;
+        for (int p = tid; p < a.Wp; p += nthreads) tr[p] = sl[thz_pad(p)];
+    }
+}
+
+// =============================================================================== K2: column pass
+struct ColArgs {
+    cpx* T;                   // [nbc][rowsT][Wp] in place; input rows [0,inH), output rows [0,outH)
+    int nbc, c0, C;
+    int rowsT;                // max(inH, outH): row pitch of one field in T is rowsT*Wp
+    int inH, outH, Hp, Wp;
+    int in_r0, out_r0;
+    int cols;                 // columns per CTA tile
+    FftPlan plan;             // length Hp (column transform)
+    FftPlan planW;            // length Wp (only for slot -> bin of the column index)
+    const cpx* tw;            // length Hp
+    TfArgs tf;
+};
+
+THZ_HD void k2_load(const ColArgs& a, cpx* s, int bx, int by, int tid, int nthreads) {
+    const int col0 = bx * a.cols;
+    const cpx* Tf = a.T + (size_t)by * a.rowsT * a.Wp;
+    const int total = a.Hp * a.cols;
+    for (int w = tid; w < total; w += nthreads) {
+        const int p = w / a.cols, l = w - p * a.cols;
+        const int r = p - a.in_r0, c = col0 + l;
+        cpx v = cmake(0.f, 0.f);
+        if (r >= 0 && r < a.inH && c < a.Wp) v = Tf[(size_t)r * a.Wp + c];
+        s[thz_pad(p) * a.cols + l] = v;
+    }
+}
+
+// Last forward stage + transfer-function multiply + first inverse stage, fused in registers: the DIF
+// forward's final butterfly and the DIT inverse's first butterfly touch the same R slots.
+template <int R>
+THZ_HD void k2_middle_butterfly(const ColArgs& a, cpx* s, int l, int u, int col, int f) {
+    const int st = a.plan.ns - 1;
+    const int p0 = u * R;   // M == 1 in the last stage
+    cpx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = s[thz_pad(p0 + t) * a.cols + l];
+    Dft<R, false>::run(v);
+    if (a.tf.mode != 2 && col < a.Wp) {
+        const int c = (a.c0 + f) % a.C;
+        if (a.tf.mode == 0) {
+            const int binc = thz_pos_to_bin(a.planW, col);
+            const float4 cv = thz_ldg(a.tf.colvec + (size_t)c * a.Wp + binc);
+            const float2 sc = thz_ldg(a.tf.scal + c);
+            const int bin0 = thz_pos_to_bin(a.plan, p0);
+            const float4* rvp = a.tf.rowvec + (size_t)c * a.Hp + bin0;
+            const int wt = a.plan.wt[st];
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[q] = cmul(v[q], thz_tf_value(thz_ldg(rvp + q * wt), cv, sc, a.tf.conj));
+        } else {
+            const cpx* tp = a.tf.table + ((size_t)c * a.Hp + p0) * a.Wp + col;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                cpx h = thz_ldg(tp + (size_t)q * a.Wp);
+                v[q] = a.tf.conj ? cmulc(v[q], h) : cmul(v[q], h);
+            }
+        }
+    }
+    Dft<R, true>::run(v);
+#pragma unroll
+    for (int t = 0; t < R; ++t) s[thz_pad(p0 + t) * a.cols + l] = v[t];
+}
+
+template <bool MIXED>
+THZ_HD void k2_middle(const ColArgs& a, cpx* s, int bx, int by, int tid, int nthreads) {
+    const int R = a.plan.radix[a.plan.ns - 1];
+    const int nb = a.Hp / R;
+    const int total = nb * a.cols;
+    const int col0 = bx * a.cols;
+    for (int w = tid; w < total; w += nthreads) {
+        const int u = w / a.cols, l = w - u * a.cols;
+        const int col = col0 + l;
+        switch (R) {
+        case 16: k2_middle_butterfly<16>(a, s, l, u, col, by); break;
+        case 8: k2_middle_butterfly<8>(a, s, l, u, col, by); break;
+        case 4: k2_middle_butterfly<4>(a, s, l, u, col, by); break;
+        case 2: k2_middle_butterfly<2>(a, s, l, u, col, by); break;
+        default:
+            if (MIXED) {
+                switch (R) {
+                case 25: k2_middle_butterfly<25>(a, s, l, u, col, by); break;
+                case 20: k2_middle_butterfly<20>(a, s, l, u, col, by); break;
+                case 15: k2_middle_butterfly<15>(a, s, l, u, col, by); break;
+                case 14: k2_middle_butterfly<14>(a, s, l, u, col, by); break;
+                case 12: k2_middle_butterfly<12>(a, s, l, u, col, by); break;
+                case 10: k2_middle_butterfly<10>(a, s, l, u, col, by); break;
+                case 9: k2_middle_butterfly<9>(a, s, l, u, col, by); break;
+                case 7: k2_middle_butterfly<7>(a, s, l, u, col, by); break;
+                case 6: k2_middle_butterfly<6>(a, s, l, u, col, by); break;
+                case 5: k2_middle_butterfly<5>(a, s, l, u, col, by); break;
+                case 3: k2_middle_butterfly<3>(a, s, l, u, col, by); break;
+                default: break;
+                }
+            }
+            break;
+        }
+    }
+}
+
+THZ_HD void k2_store(const ColArgs& a, const cpx* s, int bx, int by, int tid, int nthreads) {
+    const int col0 = bx * a.cols;
+    cpx* Tf = a.T + (size_t)by * a.rowsT * a.Wp;
+    const int total = a.outH * a.cols;
+    for (int w = tid; w < total; w += nthreads) {
+        const int r = w / a.cols, l = w - r * a.cols;
+        const int c = col0 + l;
+        if (c < a.Wp) Tf[(size_t)r * a.Wp + c] = s[thz_pad(r + a.out_r0) * a.cols + l];
+    }
+}
+
+// =============================================================================== K3: row inverse + epilogue
+#define THZ_K3_OWN 16  // max output elements a thread owns (register gradient accumulators)
+
+struct RowInvArgs {
+    const cpx* T;             // [nbc][rowsT][Wp]
+    cpx* y;                   // [nbc][outH][outW]   forward output, or grad wrt field (may be NULL in DOE mode)
+    int nbc, c0, C;
+    int rowsT, outH, outW, Wp, out_c0;
+    int lines;                // rows per CTA
+    int bc_per_cta;           // fields a CTA walks through (gridDim.y = ceil(nbc / bc_per_cta))
+    float scale;              // 1 / (Hp Wp)
+    FftPlan plan;             // length Wp
+    const cpx* tw;
+    // DOE adjoint epilogue (mode = hmap != NULL)
+    DoeArgs doe;
+    const cpx* xsaved;        // [nbc][outH][outW] field that entered the DOE
+    float* gh;                // [outH][outW]
+    int gh_atomic;            // 1: several CTAs contribute to one gh element -> atomicAdd
+};
+
+THZ_HD void k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nthreads) {
+    const int pitch = thz_padded_len(a.Wp);
+    for (int l = 0; l < a.lines; ++l) {
+        const int r = bx * a.lines + l;
+        cpx* sl = s + l * pitch;
+        if (r >= a.outH) {
+            for (int p = tid; p < a.Wp; p += nthreads) sl[thz_pad(p)] = cmake(0.f, 0.f);
+            continue;
+        }
+        const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * a.Wp;
+        for (int p = tid; p < a.Wp; p += nthreads) sl[thz_pad(p)] = tr[p];
+    }
+}
+
+// Epilogue for field f.  acc[] are the per-thread partial sums of grad_height for the elements the
+// thread owns (element e = tid + k*nthreads of the CTA's lines*outW block).
+THZ_HD void k3_epilogue(const RowInvArgs& a, const cpx* s, int bx, int f, int tid, int nthreads, float (&acc)[THZ_K3_OWN]) {
+    const int pitch = thz_padded_len(a.Wp);
+    const int block_elems = a.lines * a.outW;
+    float4 cf = cmake4(0.f);
+    cpx gamma = cmake(0.f, 0.f);
+    if (a.doe.hmap) {
+        cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
+        // gamma_c = -k (0.5 tand sqrt(eps) + i (sqrt(eps) - 1))
+        gamma = cmake(-cf.x * (0.5f * cf.y * cf.z), -cf.x * cf.w);
+    }
+    if (!a.doe.hmap) {   // plain forward output: no accumulators, any block size
+        for (int e = tid; e < block_elems; e += nthreads) {
+            const int l = e / a.outW, c = e - l * a.outW;
+            const int r = bx * a.lines + l;
+            if (r >= a.outH) break;
+            a.y[((size_t)f * a.outH + r) * a.outW + c] = cscale(s[l * pitch + thz_pad(c + a.out_c0)], a.scale);
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < THZ_K3_OWN; ++k) {
+        const int e = tid + k * nthreads;
+        if (e >= block_elems) break;
+        const int l = e / a.outW, c = e - l * a.outW;
+        const int r = bx * a.lines + l;
+        if (r >= a.outH) break;
+        const cpx v = cscale(s[l * pitch + thz_pad(c + a.out_c0)], a.scale);
+        const size_t o = ((size_t)f * a.outH + r) * a.outW + c;
+        const cpx p = thz_doe_phase(thz_ldg(a.doe.hmap + (size_t)r * a.outW + c), cf, a.doe.base);
+        if (a.y) a.y[o] = cmulc(v, p);                       // gx = g' conj(p)
+        const cpx xp = cmul(cmul(a.xsaved[o], p), gamma);    // x p gamma
+        acc[k] += v.x * xp.x + v.y * xp.y;                   // Re(conj(g') x p gamma)
+    }
+}
+
+THZ_HD void k3_flush(const RowInvArgs& a, int bx, int tid, int nthreads, const float (&acc)[THZ_K3_OWN]) {
+    if (!a.doe.hmap) return;
+    const int block_elems = a.lines * a.outW;
+#pragma unroll
+    for (int k = 0; k < THZ_K3_OWN; ++k) {
+        const int e = tid + k * nthreads;
+        if (e >= block_elems) break;
+        const int l = e / a.outW, c = e - l * a.outW;
+        const int r = bx * a.lines + l;
+        if (r >= a.outH) break;
+        float* g = a.gh + (size_t)r * a.outW + c;
+        if (a.gh_atomic) thz_atomic_add(g, acc[k]);
+        else *g = acc[k];
+    }
+}
+
+// =============================================================================== stand-alone fft2 column pass
+// Forward column FFT of a tile, then un-scramble both axes on store:  y[bin_r][bin_c] = scale * s[slot_r][slot_c].
+struct ColFftArgs {
+    const cpx* T;             // [batch][H][W] row-transformed, slot order along W
+    cpx* y;                   // [batch][H][W] natural order
+    int H, W, cols;
+    float scale;
+    int conj_out;
+    FftPlan plan;             // length H
+    FftPlan planW;            // length W
+    const cpx* tw;
+};
+
+THZ_HD void k2f_load(const ColFftArgs& a, cpx* s, int bx, int by, int tid, int nthreads) {
+    const int col0 = bx * a.cols;
+    const cpx* Tf = a.T + (size_t)by * a.H * a.W;
+    const int total = a.H * a.cols;
+    for (int w = tid; w < total; w += nthreads) {
+        const int p = w / a.cols, l = w - p * a.cols;
+        const int c = col0 + l;
+        s[thz_pad(p) * a.cols + l] = c < a.W ? Tf[(size_t)p * a.W + c] : cmake(0.f, 0.f);
+    }
+}
+
+THZ_HD void k2f_store(const ColFftArgs& a, const cpx* s, int bx, int by, int tid, int nthreads) {
+    const int col0 = bx * a.cols;
+    cpx* yf = a.y + (size_t)by * a.H * a.W;
+    const int total = a.H * a.cols;
+    for (int w = tid; w < total; w += nthreads) {
+        const int p = w / a.cols, l = w - p * a.cols;
+        const int c = col0 + l;
+        if (c >= a.W) continue;
+        cpx v = cscale(s[thz_pad(p) * a.cols + l], a.scale);
+        if (a.conj_out) v.y = -v.y;
+        yf[(size_t)thz_pos_to_bin(a.plan, p) * a.W + thz_pos_to_bin(a.planW, c)] = v;
+    }
+}

@@ -1,0 +1,174 @@
+// Host-side launch planning for the fused ASM pipeline, shared by the CUDA launcher (thz_asm.cu)
+// and the CPU replay harness (tests/emul).  No CUDA runtime calls in here.
+#pragma once
+#include "thz_asm.cuh"
+
+#define THZ_SMEM_BUDGET (200 * 1024)   // per-CTA dynamic shared memory we allow ourselves (HW max 227 KB)
+
+struct AsmLaunch {
+    RowFwdArgs k1;
+    ColArgs k2;
+    RowInvArgs k3;
+    int k1_grid, k1_threads;
+    size_t k1_smem;
+    int k2_gridx, k2_threads;
+    size_t k2_smem;
+    int k3_gridx, k3_gridy, k3_threads;
+    size_t k3_smem;
+    int mixed_w, mixed_h;
+    int gh_needs_zero;        // 1: gh is accumulated with atomics and must be zeroed first
+};
+
+static inline int thz_imax(int a, int b) { return a > b ? a : b; }
+static inline int thz_imin(int a, int b) { return a < b ? a : b; }
+
+static inline int thz_asm_validate(const thz_asm_desc* d) {
+    if (!d) return THZ_E_NULL;
+    if (!d->x || !d->tw_h || !d->tw_w || !d->ws) return THZ_E_NULL;
+    if (d->B < 1 || d->C < 1 || d->inH < 1 || d->inW < 1 || d->outH < 1 || d->outW < 1) return THZ_E_SHAPE;
+    if (d->in_r0 < 0 || d->in_c0 < 0 || d->out_r0 < 0 || d->out_c0 < 0) return THZ_E_SHAPE;
+    if (d->in_r0 + d->inH > d->Hp || d->in_c0 + d->inW > d->Wp) return THZ_E_SHAPE;
+    if (d->out_r0 + d->outH > d->Hp || d->out_c0 + d->outW > d->Wp) return THZ_E_SHAPE;
+    if (d->tf_mode == 0 && (!d->tf_rowvec || !d->tf_colvec || !d->tf_scal)) return THZ_E_NULL;
+    if (d->tf_mode == 1 && !d->tf_table) return THZ_E_NULL;
+    if (d->tf_mode < 0 || d->tf_mode > 2) return THZ_E_SHAPE;
+    if (d->doe_mode < 0 || d->doe_mode > 2) return THZ_E_SHAPE;
+    if (d->doe_mode != 0 && (!d->doe_hmap || !d->doe_coef)) return THZ_E_NULL;
+    if (d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
+    if (d->doe_mode != 2 && !d->y) return THZ_E_NULL;
+    return THZ_OK;
+}
+
+static inline uint64_t thz_asm_chunk_fields(const thz_asm_desc* d) {
+    uint64_t nbc = (uint64_t)d->B * d->C;
+    if (d->bc_chunk > 0 && (uint64_t)d->bc_chunk < nbc) return (uint64_t)d->bc_chunk;
+    return nbc;
+}
+
+static inline uint64_t thz_asm_ws_bytes(const thz_asm_desc* d) {
+    return thz_asm_chunk_fields(d) * (uint64_t)thz_imax(d->inH, d->outH) * (uint64_t)d->Wp * sizeof(cpx);
+}
+
+// Build the three kernels' arguments for the chunk of fields [f0, f0+nbc).
+static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int sm_count, AsmLaunch* L) {
+    FftPlan pw, ph;
+    if (thz_make_plan(d->Wp, &pw) != 0) return THZ_E_UNSUPPORTED;
+    if (thz_make_plan(d->Hp, &ph) != 0) return THZ_E_UNSUPPORTED;
+    L->mixed_w = pw.mixed;
+    L->mixed_h = ph.mixed;
+    const int rowsT = thz_imax(d->inH, d->outH);
+    const size_t line_bytes_w = (size_t)thz_padded_len(d->Wp) * sizeof(cpx);
+    const size_t line_bytes_h = (size_t)thz_padded_len(d->Hp) * sizeof(cpx);
+    if (line_bytes_w > THZ_SMEM_BUDGET || line_bytes_h > THZ_SMEM_BUDGET) return THZ_E_SMEM;
+
+    // ---- K1
+    RowFwdArgs& a1 = L->k1;
+    a1.x = (const cpx*)d->x + (size_t)f0 * d->inH * d->inW;
+    a1.T = (cpx*)d->ws;
+    a1.nbc = nbc;
+    a1.rowsT = rowsT;
+    a1.c0 = f0 % d->C;
+    a1.C = d->C;
+    a1.inH = d->inH;
+    a1.inW = d->inW;
+    a1.Wp = d->Wp;
+    a1.in_c0 = d->in_c0;
+    a1.plan = pw;
+    a1.tw = (const cpx*)d->tw_w;
+    a1.doe.hmap = d->doe_mode == 1 ? (const float*)d->doe_hmap : nullptr;
+    a1.doe.coef = (const float4*)d->doe_coef;
+    a1.doe.base = d->doe_base;
+    a1.conj_in = 0;
+    {
+        // enough lines per CTA to give 256 threads at least one radix-16 butterfly each
+        int lines = thz_imax(1, 4096 / d->Wp);
+        lines = thz_imin(lines, 16);
+        while (lines > 1 && lines * line_bytes_w > 64 * 1024) --lines;
+        if (d->tune_lines > 0 && d->tune_lines * line_bytes_w <= THZ_SMEM_BUDGET) lines = d->tune_lines;
+        a1.lines = lines;
+        L->k1_threads = 256;
+        L->k1_grid = (nbc * d->inH + lines - 1) / lines;
+        L->k1_smem = lines * line_bytes_w;
+    }
+
+    // ---- K2
+    ColArgs& a2 = L->k2;
+    a2.T = (cpx*)d->ws;
+    a2.nbc = nbc;
+    a2.c0 = f0 % d->C;
+    a2.C = d->C;
+    a2.rowsT = rowsT;
+    a2.inH = d->inH;
+    a2.outH = d->outH;
+    a2.Hp = d->Hp;
+    a2.Wp = d->Wp;
+    a2.in_r0 = d->in_r0;
+    a2.out_r0 = d->out_r0;
+    a2.plan = ph;
+    a2.planW = pw;
+    a2.tw = (const cpx*)d->tw_h;
+    a2.tf.mode = d->tf_mode;
+    a2.tf.conj = d->tf_conj;
+    a2.tf.rowvec = (const float4*)d->tf_rowvec;
+    a2.tf.colvec = (const float4*)d->tf_colvec;
+    a2.tf.scal = (const float2*)d->tf_scal;
+    a2.tf.table = (const cpx*)d->tf_table;
+    {
+        int cols = 16;
+        // shrink the tile until it fits and until there are enough tiles to fill the GPU twice
+        while (cols > 1 && cols * line_bytes_h > 72 * 1024) cols >>= 1;
+        while (cols > 4 && (long)((d->Wp + cols - 1) / cols) * nbc < 2L * sm_count) cols >>= 1;
+        if (d->tune_k2_cols > 0) cols = d->tune_k2_cols;
+        if ((size_t)cols * line_bytes_h > THZ_SMEM_BUDGET) return THZ_E_SMEM;
+        a2.cols = cols;
+        L->k2_gridx = (d->Wp + cols - 1) / cols;
+        L->k2_smem = cols * line_bytes_h;
+        const int work = (d->Hp / 16 + 1) * cols;
+        L->k2_threads = work >= 1024 ? 512 : (work >= 384 ? 256 : 128);
+    }
+
+    // ---- K3
+    RowInvArgs& a3 = L->k3;
+    a3.T = (const cpx*)d->ws;
+    a3.y = d->y ? (cpx*)d->y + (size_t)f0 * d->outH * d->outW : nullptr;
+    a3.nbc = nbc;
+    a3.c0 = f0 % d->C;
+    a3.C = d->C;
+    a3.rowsT = rowsT;
+    a3.outH = d->outH;
+    a3.outW = d->outW;
+    a3.Wp = d->Wp;
+    a3.out_c0 = d->out_c0;
+    a3.scale = 1.0f / ((float)d->Hp * (float)d->Wp);
+    a3.plan = pw;
+    a3.tw = (const cpx*)d->tw_w;
+    a3.doe.hmap = d->doe_mode == 2 ? (const float*)d->doe_hmap : nullptr;
+    a3.doe.coef = (const float4*)d->doe_coef;
+    a3.doe.base = d->doe_base;
+    a3.xsaved = d->doe_mode == 2 ? (const cpx*)d->doe_xsaved + (size_t)f0 * d->outH * d->outW : nullptr;
+    a3.gh = (float*)d->doe_gh;
+    {
+        int lines = thz_imax(1, 4096 / d->Wp);
+        lines = thz_imin(lines, 16);
+        while (lines > 1 && lines * line_bytes_w > 64 * 1024) --lines;
+        int threads = 256;
+        if (d->tune_lines > 0 && d->tune_lines * line_bytes_w <= THZ_SMEM_BUDGET) lines = d->tune_lines;
+        if (d->doe_mode == 2) {
+            // register accumulators: lines*outW <= THZ_K3_OWN * threads
+            while (lines > 1 && (long)lines * d->outW > (long)THZ_K3_OWN * threads) --lines;
+            while (threads < 512 && (long)lines * d->outW > (long)THZ_K3_OWN * threads) threads <<= 1;
+            if ((long)lines * d->outW > (long)THZ_K3_OWN * threads) return THZ_E_UNSUPPORTED;
+        }
+        a3.lines = lines;
+        L->k3_threads = threads;
+        L->k3_gridx = (d->outH + lines - 1) / lines;
+        // split the field axis over gridDim.y until the grid fills the GPU ~4x
+        int gy = 1;
+        while (gy < nbc && (long)L->k3_gridx * gy < 4L * sm_count) gy <<= 1;
+        gy = thz_imin(gy, nbc);
+        a3.bc_per_cta = (nbc + gy - 1) / gy;
+        L->k3_gridy = (nbc + a3.bc_per_cta - 1) / a3.bc_per_cta;
+        L->k3_smem = lines * line_bytes_w;
+    }
+    return THZ_OK;
+}

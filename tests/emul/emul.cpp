@@ -1,0 +1,168 @@
+// CPU replay harness for the CUDA kernel bodies (TEST INFRASTRUCTURE, never loaded by the product).
+//
+// The kernels in quantizationawarethzdoe_b200/csrc are written as __host__ __device__ phase
+// functions separated by block barriers.  This file replays them block by block, thread by thread,
+// on HOST pointers, with the very same launch planning (thz_asm_host.h), so that index arithmetic,
+// digit-reversal bookkeeping, pruning, padding and the epilogues can be checked against the oracle
+// in the GPU-less build container (`pytest -m "not gpu"`).  Built by tests/emul/build.py with g++.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../quantizationawarethzdoe_b200/csrc/thz_asm_host.h"
+
+template <typename F>
+static void for_threads(int nthreads, F f) {
+    for (int t = 0; t < nthreads; ++t) f(t);
+}
+
+template <bool MIXED>
+static void run_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
+    std::vector<unsigned char> buf(smem);
+    cpx* s = (cpx*)buf.data();
+    const int pitch = thz_padded_len(a.Wp);
+    for (int bx = 0; bx < grid; ++bx) {
+        for_threads(nt, [&](int t) { k1_load(a, s, bx, t, nt); });
+        for (int st = 0; st < a.plan.ns; ++st)
+            for_threads(nt, [&](int t) { fft_stage_all<MIXED, false>(a.plan, st, s, a.lines, pitch, false, t, nt, a.tw); });
+        for_threads(nt, [&](int t) { k1_store(a, s, bx, t, nt); });
+    }
+}
+
+template <bool MIXED>
+static void run_k2(const ColArgs& a, int gx, int gy, int nt, size_t smem) {
+    std::vector<unsigned char> buf(smem);
+    cpx* s = (cpx*)buf.data();
+    const int last = a.plan.ns - 1;
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            for_threads(nt, [&](int t) { k2_load(a, s, bx, by, t, nt); });
+            for (int st = 0; st < last; ++st)
+                for_threads(nt, [&](int t) { fft_stage_all<MIXED, false>(a.plan, st, s, a.cols, 0, true, t, nt, a.tw); });
+            for_threads(nt, [&](int t) { k2_middle<MIXED>(a, s, bx, by, t, nt); });
+            for (int st = last - 1; st >= 0; --st)
+                for_threads(nt, [&](int t) { fft_stage_all<MIXED, true>(a.plan, st, s, a.cols, 0, true, t, nt, a.tw); });
+            for_threads(nt, [&](int t) { k2_store(a, s, bx, by, t, nt); });
+        }
+}
+
+template <bool MIXED>
+static void run_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) {
+    std::vector<unsigned char> buf(smem);
+    cpx* s = (cpx*)buf.data();
+    const int pitch = thz_padded_len(a.Wp);
+    typedef float acc_t[THZ_K3_OWN];
+    std::vector<float> accs((size_t)nt * THZ_K3_OWN);
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            std::fill(accs.begin(), accs.end(), 0.f);
+            const int f_lo = by * a.bc_per_cta;
+            const int f_hi = thz_imin(a.nbc, f_lo + a.bc_per_cta);
+            for (int f = f_lo; f < f_hi; ++f) {
+                for_threads(nt, [&](int t) { k3_load(a, s, bx, f, t, nt); });
+                for (int st = a.plan.ns - 1; st >= 0; --st)
+                    for_threads(nt, [&](int t) { fft_stage_all<MIXED, true>(a.plan, st, s, a.lines, pitch, false, t, nt, a.tw); });
+                for_threads(nt, [&](int t) { k3_epilogue(a, s, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * THZ_K3_OWN]); });
+            }
+            for_threads(nt, [&](int t) { k3_flush(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * THZ_K3_OWN]); });
+        }
+}
+
+template <bool MIXED>
+static void run_k2f(const ColFftArgs& a, int gx, int gy, int nt, size_t smem) {
+    std::vector<unsigned char> buf(smem);
+    cpx* s = (cpx*)buf.data();
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            for_threads(nt, [&](int t) { k2f_load(a, s, bx, by, t, nt); });
+            for (int st = 0; st < a.plan.ns; ++st)
+                for_threads(nt, [&](int t) { fft_stage_all<MIXED, false>(a.plan, st, s, a.cols, 0, true, t, nt, a.tw); });
+            for_threads(nt, [&](int t) { k2f_store(a, s, bx, by, t, nt); });
+        }
+}
+
+extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
+    int rc = thz_asm_validate(d);
+    if (rc != THZ_OK) return rc;
+    if (d->ws_bytes < thz_asm_ws_bytes(d)) return THZ_E_WORKSPACE;
+    const int nbc_all = d->B * d->C;
+    const int chunk = (int)thz_asm_chunk_fields(d);
+    const int nchunks = (nbc_all + chunk - 1) / chunk;
+    bool zeroed = false;
+    for (int f0 = 0; f0 < nbc_all; f0 += chunk) {
+        const int nbc = nbc_all - f0 < chunk ? nbc_all - f0 : chunk;
+        AsmLaunch L;
+        rc = thz_asm_plan_chunk(d, f0, nbc, sm_count, &L);
+        if (rc != THZ_OK) return rc;
+        L.k3.gh_atomic = (d->doe_mode == 2 && (nchunks > 1 || L.k3_gridy > 1)) ? 1 : 0;
+        if (L.k3.gh_atomic && !zeroed) {
+            memset(d->doe_gh, 0, (size_t)d->outH * d->outW * sizeof(float));
+            zeroed = true;
+        }
+        if (L.mixed_w) run_k1<true>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
+        else run_k1<false>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
+        if (L.mixed_h) run_k2<true>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
+        else run_k2<false>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
+        if (L.mixed_w) run_k3<true>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
+        else run_k3<false>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
+    }
+    return THZ_OK;
+}
+
+extern "C" int thz_emul_fft2_c2c(const void* x, void* y, int32_t batch, int32_t H, int32_t W, int32_t inverse,
+                                 int32_t ortho, const void* tw_h, const void* tw_w, void* ws) {
+    FftPlan pw, ph;
+    if (thz_make_plan(W, &pw) != 0 || thz_make_plan(H, &ph) != 0) return THZ_E_UNSUPPORTED;
+    const size_t lw = (size_t)thz_padded_len(W) * sizeof(cpx), lh = (size_t)thz_padded_len(H) * sizeof(cpx);
+    RowFwdArgs a1;
+    memset(&a1, 0, sizeof(a1));
+    a1.x = (const cpx*)x;
+    a1.T = (cpx*)ws;
+    a1.nbc = batch;
+    a1.rowsT = H;
+    a1.C = 1;
+    a1.inH = H;
+    a1.inW = W;
+    a1.Wp = W;
+    a1.plan = pw;
+    a1.tw = (const cpx*)tw_w;
+    a1.conj_in = inverse ? 1 : 0;
+    int lines = thz_imax(1, 4096 / W);
+    lines = thz_imin(lines, 16);
+    a1.lines = lines;
+    if (pw.mixed) run_k1<true>(a1, (batch * H + lines - 1) / lines, 256, lines * lw);
+    else run_k1<false>(a1, (batch * H + lines - 1) / lines, 256, lines * lw);
+    ColFftArgs a2;
+    memset(&a2, 0, sizeof(a2));
+    a2.T = (const cpx*)ws;
+    a2.y = (cpx*)y;
+    a2.H = H;
+    a2.W = W;
+    int cols = 16;
+    while (cols > 1 && cols * lh > 72 * 1024) cols >>= 1;
+    a2.cols = cols;
+    a2.scale = (float)(ortho ? 1.0 / sqrt((double)H * (double)W) : (inverse ? 1.0 / ((double)H * (double)W) : 1.0));
+    a2.conj_out = inverse ? 1 : 0;
+    a2.plan = ph;
+    a2.planW = pw;
+    a2.tw = (const cpx*)tw_h;
+    if (ph.mixed) run_k2f<true>(a2, (W + cols - 1) / cols, batch, 128, cols * lh);
+    else run_k2f<false>(a2, (W + cols - 1) / cols, batch, 128, cols * lh);
+    return THZ_OK;
+}
+
+// host-side planning helpers, same as the product exports them (thz_api.cu) but without CUDA
+extern "C" int thz_emul_slot_to_bin(int32_t n, int32_t* out) {
+    FftPlan P;
+    if (thz_make_plan(n, &P) != 0) return THZ_E_UNSUPPORTED;
+    for (int p = 0; p < n; ++p) out[p] = thz_pos_to_bin(P, p);
+    return THZ_OK;
+}
+extern "C" int thz_emul_plan_info(int32_t n, int32_t* radices, int32_t* ns) {
+    FftPlan P;
+    if (thz_make_plan(n, &P) != 0) return THZ_E_UNSUPPORTED;
+    for (int s = 0; s < THZ_MAX_STAGES; ++s) radices[s] = s < P.ns ? P.radix[s] : 0;
+    *ns = P.ns;
+    return THZ_OK;
+}
