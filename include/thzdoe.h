@@ -114,6 +114,65 @@ int thz_asm_propagate(const thz_asm_desc* desc, void* stream);
 int thz_fft2_c2c(const void* x, void* y, int32_t batch, int32_t H, int32_t W, int32_t inverse, int32_t ortho,
                  const void* tw_h, const void* tw_w, void* ws, uint64_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone DOE phase modulation (a DOE that is not directly followed by ASM_prop).
+ * Replaces DOELayer.phase_shift_according_to_height + .modulate (Components/QuantizedDOE.py:46-79,
+ * 92-126) and their autograd:   y = x * p_c(h),   gx = g conj(p),   gh = sum_{b,c} Re(conj(g) x p gamma_c).
+ *   x, y, g, gx: complex64 [B,C,H,W];  hmap, gh: float32 [H,W];  coef: float32 [C,4] as in thz_asm_desc.
+ *   gx or gh may be NULL (not needed); x may be NULL iff gh is NULL.
+ * ------------------------------------------------------------------------------------------- */
+int thz_doe_modulate_fwd(const void* x, void* y, const void* hmap, const void* coef, float base, int32_t B, int32_t C,
+                         int32_t H, int32_t W, void* stream);
+int thz_doe_modulate_bwd(const void* g, const void* x, const void* hmap, const void* coef, float base, void* gx, void* gh,
+                         int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Height-map construction and quantized level selection (all float32 [n] unless noted; idx int32 [n]).
+ *
+ * thz_height_fwd / _bwd: h = hmax * sigmoid(clamp(w, -c, c)) and gw = g * dh/dw
+ *     (FullPrecisionDOELayer.preprocessed_height_map, Components/QuantizedDOE.py:276-283; c = 8).
+ * thz_quant_ste_fwd: STEQuantizationFunction.forward (Components/QuantizedDOE.py:1239-1246):
+ *     idx = argmin_j |h - lut_j| (first minimum), q = lut[idx].  from_weights=1 fuses the sigmoid
+ *     height construction of STEQuantizedDOELayer (:1379-1388) in front; h_pre (optional) gets h.
+ *     Backward is the identity (:1248-1253) followed by thz_height_bwd.
+ * thz_quant_nn_fwd / _bwd: NearestNeighborSearch / PolyGrad / SigmoidGrad
+ *     (Components/quantization.py:59-122, utils/Helper_Functions.py:390-398):
+ *     idx = bucketize(x, mid, right=True) % nmid, q = lut[idx]; kind 0 identity, 1 poly, 2 sigmoid.
+ * thz_quant_psq_fwd: PSQuantizedDOELayer.preprocessed_height_map (Components/QuantizedDOE.py:1193-1207);
+ *     dout_dw (optional) receives d out / d w so that backward is one multiply.
+ * thz_quant_gumbel_v3_fwd: SoftGumbelQuantizedDOELayerv3.preprocessed_height_map
+ *     (Components/QuantizedDOE.py:794-860) for iter_frac > 0.3, Gumbel noise supplied:
+ *     noise float32 [L,n]; beta >= 1 means pure quantized output; dh_dw (optional) = d out / d w;
+ *     phase_input=1: `w` is the phase parameter itself (SoftGumbelQuantizedDOELayer v1, :436-446).
+ * thz_quant_gumbel_naive_fwd: NaiveGumbelQuantizedDOELayer.preprocessed_height_map (:1022-1031):
+ *     logits, noise float32 [n,L]; dq (optional) float32 [n,L] = d q / d logit.
+ * ------------------------------------------------------------------------------------------- */
+int thz_height_fwd(const void* w, float hmax, float clampv, void* h, uint64_t n, void* stream);
+int thz_height_bwd(const void* g, const void* w, float hmax, float clampv, void* gw, uint64_t n, void* stream);
+int thz_quant_ste_fwd(const void* in, int32_t from_weights, float hmax, float clampv, const void* lut, int32_t L, void* q,
+                      void* idx, void* h_pre, uint64_t n, void* stream);
+int thz_quant_nn_fwd(const void* x, const void* lut, int32_t nlut, const void* mid, int32_t nmid, void* q, void* idx,
+                     uint64_t n, void* stream);
+int thz_quant_nn_bwd(const void* g, const void* x, const void* idx, const void* lut, int32_t nlut, float s, int32_t kind,
+                     void* gx, uint64_t n, void* stream);
+int thz_quant_psq_fwd(const void* w, float hmax, int32_t L, float tau, void* out, void* dout_dw, uint64_t n, void* stream);
+int thz_quant_gumbel_v3_fwd(const void* w, const void* lut, int32_t L, const void* noise, float hmax, float kfac, float c_s,
+                            float tau, float tau_max, float s, float beta, float one_minus_beta, int32_t phase_input,
+                            void* h_out, void* idx, void* dh_dw, uint64_t n, void* stream);
+int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise, const void* lut, int32_t L, float tau, void* q,
+                               void* idx, void* dq, uint64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Launch accounting (used by bench.py).  thz_launch_count: kernels launched by this library in this
+ * process so far.  thz_profile_enable(1) makes every launch record a CUDA event pair on its stream
+ * (small overhead, off by default); thz_profile_read sums elapsed milliseconds and launches per
+ * kernel class (0 row-FFT forward, 1 column pass, 2 row-iFFT + epilogue, 3 fft2 column pass, 4 DOE
+ * modulation, 5 quantizers, 6 CZT) after synchronising the recorded events; enable(0) clears them.
+ * ------------------------------------------------------------------------------------------- */
+uint64_t thz_launch_count(void);
+int thz_profile_enable(int32_t on);
+int thz_profile_read(int32_t nclasses, float* ms_sum, int32_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,174 @@
+"""Band-limited angular-spectrum propagation -- drop-in for the reference's Props/ASM_Prop.py.
+
+Same constructor and forward(field) -> ElectricField surface (Props/ASM_Prop.py:17-27, 314-378),
+same attributes (`z` setter :185-195, `padding_scale`, `bandlimit_kernel`, `bandlimit_type`,
+`do_padding`, `do_unpad_after_pad`, `check_Zc`, `shape`, buffers `_Kx/_Ky` :169-183), same
+exceptions (:96, :309) -- but forward and backward run the fused sm_100a kernels behind
+`thz_asm_propagate` (include/thzdoe.h): zero-pad, both FFTs, the transfer function H(kx,ky,lambda,z)
+generated in registers, the crop, and (when the incoming field carries a deferred DOE modulation)
+the DOE phase multiply and its adjoint, all without cuFFT / torch.fft.
+
+`kernel_mode`:
+  'inregister' (default) H is generated inside the column kernel from O(Hp+Wp) host-built vectors;
+                         the band-limit mask is bit-identical to the reference, the phase differs from
+                         the reference's only where torch's CPU sqrt is not correctly rounded.
+  'cached'               H is built once per (shape, spacing, wavelengths, z) on the host with the
+                         reference's own torch CPU ops, uploaded, and streamed by the kernel
+                         (bit-identical H; +8 B per padded sample of HBM traffic per pass).
+"""
+import torch
+import torch.nn as nn
+
+from .. import asm_host as AH
+from .. import functional as Fn
+from ..DataType.ElectricField import ElectricField
+
+
+class ASM_prop(nn.Module):
+
+    def __init__(self,
+                 z_distance=0.0,
+                 do_padding=True,
+                 do_unpad_after_pad=True,
+                 padding_scale=None,
+                 bandlimit_kernel=True,
+                 bandlimit_type='exact',
+                 device=None,
+                 kernel_mode='inregister'):
+        super().__init__()
+        padding_scale = AH.normalise_padding_scale(padding_scale, do_padding)   # raises like ASM_Prop.py:96
+        self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self._z = torch.tensor(z_distance, device=self.device)
+        self.do_padding = do_padding
+        self.do_unpad_after_pad = do_unpad_after_pad
+        self.padding_scale = padding_scale
+        self.bandlimit_kernel = bandlimit_kernel
+        self.bandlimit_type = bandlimit_type
+        if kernel_mode not in ('inregister', 'cached'):
+            raise ValueError("kernel_mode must be 'inregister' or 'cached'")
+        self.kernel_mode = kernel_mode
+        self._shape = None
+        self.Kx = None
+        self.Ky = None
+        self.shape = None
+        self.check_Zc = True
+        self._plan_key = None
+        self._plan = None
+
+    # ---- reference-compatible helpers -------------------------------------------------------
+    def compute_padding(self, H, W, return_size_of_padding=False):
+        pad_h, pad_w, Hp, Wp = AH.compute_padding(int(H), int(W), self.padding_scale, self.do_padding)
+        return (pad_h, pad_w) if return_size_of_padding else (Hp, Wp)
+
+    def create_frequency_grid(self, H, W):
+        with torch.no_grad():
+            kx = (torch.linspace(0, H - 1, H) - (H // 2)) / H
+            ky = (torch.linspace(0, W - 1, W) - (W // 2)) / W
+            self.Kx, self.Ky = torch.meshgrid(kx, ky, indexing="ij")
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @shape.setter
+    def shape(self, shape):
+        if shape is None:
+            self._shape = None
+            return
+        old = self._shape
+        self._shape = shape
+        if old is None or old[-2] != shape[-2] or old[-1] != shape[-1]:
+            self.create_frequency_grid(shape[-2], shape[-1])
+
+    @property
+    def Kx(self):
+        return self._Kx
+
+    @Kx.setter
+    def Kx(self, Kx):
+        self.register_buffer("_Kx", Kx)
+
+    @property
+    def Ky(self):
+        return self._Ky
+
+    @Ky.setter
+    def Ky(self, Ky):
+        self.register_buffer("_Ky", Ky)
+
+    @property
+    def z(self):
+        return self._z
+
+    @z.setter
+    def z(self, z):
+        # The reference stores whatever it is given (tensor, python float or numpy scalar; ASM_Prop.py:190-195).
+        if isinstance(z, torch.Tensor) and z.device != self.device:
+            z = z.to(self.device)
+        self._z = z
+
+    def _z_f32(self):
+        z = self._z
+        if isinstance(z, torch.Tensor):
+            return z.detach().to("cpu", torch.float32).reshape(())
+        return torch.tensor(float(z), dtype=torch.float32)
+
+    def create_kernel(self, field):
+        """Centred transfer function [1,C,Hp,Wp] complex64 exactly as the reference returns it
+        (Props/ASM_Prop.py:212-311); host-built, for inspection / the cached mode."""
+        H, W = field.shape[-2], field.shape[-1]
+        Hp, Wp = self.compute_padding(H, W)
+        self.shape = torch.Size((field.shape[0], field.shape[1], Hp, Wp))
+        Hc = AH.tf_centred_reference_order(Hp, Wp, field.spacing, field.wavelengths, self._z_f32(),
+                                           self.bandlimit_kernel, self.bandlimit_type)
+        return Hc[None].to(self.device)
+
+    # ---- plan cache ------------------------------------------------------------------------
+    def _get_plan(self, B, C, H, W, spacing, wavelengths, device):
+        z = self._z_f32()
+        key = (C, H, W, tuple(spacing.detach().cpu().reshape(-1).tolist()),
+               tuple(wavelengths.detach().cpu().reshape(-1).tolist()), float(z), str(device),
+               self.do_padding, self.do_unpad_after_pad,
+               None if self.padding_scale is None else tuple(self.padding_scale.reshape(-1).tolist()),
+               self.bandlimit_kernel, self.bandlimit_type, self.kernel_mode)
+        if key != self._plan_key:
+            if self.bandlimit_kernel and self.bandlimit_type not in ('exact', 'approx'):
+                raise Exception("Should not be in this state.")                      # ASM_Prop.py:309
+            pad_h, pad_w, Hp, Wp = AH.compute_padding(H, W, self.padding_scale, self.do_padding)
+            self.shape = torch.Size((B, C, Hp, Wp))
+            if self.bandlimit_kernel and self.check_Zc is True:                       # ASM_Prop.py:279-285
+                Zc = AH.critical_distance(Hp, spacing, wavelengths)
+                if float(z) > float(Zc):
+                    print("The propagation distance is greater than critical distance {} m, the TF will be undersampled!".format(Zc.numpy()))
+                else:
+                    print("The critical distance is {} m, the TF will be fine during the sampling !".format(Zc.numpy()))
+                self.check_Zc = False
+            rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
+            table, mode = None, 0
+            if self.kernel_mode == 'cached':
+                Hc = AH.tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
+                table, mode = AH.tf_table_slot_order(Hc), 1
+            unpad = bool(self.do_padding and self.do_unpad_after_pad)
+            self._plan = Fn.AsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, mode)
+            self._plan_key = key
+        self._plan.B = B
+        return self._plan
+
+    # ---- forward ---------------------------------------------------------------------------
+    def forward(self, field):
+        wavelengths = field.wavelengths
+        deferred = getattr(field, "_deferred", None)
+        if deferred is not None and getattr(field, "_data", None) is None:
+            B, C, H, W = deferred.shape
+            dev = deferred.device
+        else:
+            deferred = None
+            data = field.data
+            B, C, H, W = data.shape
+            dev = data.device
+        plan = self._get_plan(B, C, H, W, field.spacing, wavelengths, dev)
+        if deferred is not None:
+            out = Fn.DoeAsmFn.apply(deferred.x, deferred.height_map, plan, deferred.coef)
+        else:
+            out = Fn.AsmPropagateFn.apply(data, plan)
+        return ElectricField(data=out, wavelengths=wavelengths, spacing=field.spacing, device=dev)

@@ -60,6 +60,20 @@ def _declare(l):
     l.thz_asm_workspace_bytes.restype = u64
     l.thz_asm_propagate.argtypes = [ctypes.POINTER(AsmDesc), vp]
     l.thz_fft2_c2c.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, u64, vp]
+    f32 = ctypes.c_float
+    l.thz_doe_modulate_fwd.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
+    l.thz_doe_modulate_bwd.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp]
+    l.thz_height_fwd.argtypes = [vp, f32, f32, vp, u64, vp]
+    l.thz_height_bwd.argtypes = [vp, vp, f32, f32, vp, u64, vp]
+    l.thz_quant_ste_fwd.argtypes = [vp, i32, f32, f32, vp, i32, vp, vp, vp, u64, vp]
+    l.thz_quant_nn_fwd.argtypes = [vp, vp, i32, vp, i32, vp, vp, u64, vp]
+    l.thz_quant_nn_bwd.argtypes = [vp, vp, vp, vp, i32, f32, i32, vp, u64, vp]
+    l.thz_quant_psq_fwd.argtypes = [vp, f32, i32, f32, vp, vp, u64, vp]
+    l.thz_quant_gumbel_v3_fwd.argtypes = [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp, u64, vp]
+    l.thz_quant_gumbel_naive_fwd.argtypes = [vp, vp, vp, i32, f32, vp, vp, vp, u64, vp]
+    l.thz_launch_count.restype = u64
+    l.thz_profile_enable.argtypes = [i32]
+    l.thz_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     for name in EXPORTS:
         getattr(l, name)   # AttributeError here means the .so is stale: rebuild
     return l
@@ -69,6 +83,10 @@ def _declare(l):
 EXPORTS = [
     "thz_version", "thz_last_error", "thz_fft_plan_info", "thz_fft_slot_to_bin", "thz_fft_twiddles",
     "thz_asm_workspace_bytes", "thz_asm_propagate", "thz_fft2_c2c",
+    "thz_doe_modulate_fwd", "thz_doe_modulate_bwd", "thz_height_fwd", "thz_height_bwd",
+    "thz_quant_ste_fwd", "thz_quant_nn_fwd", "thz_quant_nn_bwd", "thz_quant_psq_fwd",
+    "thz_quant_gumbel_v3_fwd", "thz_quant_gumbel_naive_fwd",
+    "thz_launch_count", "thz_profile_enable", "thz_profile_read",
 ]
 
 

@@ -3,6 +3,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "thz_fft.cuh"
 #include "thz_runtime.h"
 
@@ -53,6 +57,78 @@ extern "C" int thz_fft_twiddles(int32_t n, float* tw) {
     for (int m = 0; m < n; ++m) {
         tw[2 * m] = (float)cos(w * m);
         tw[2 * m + 1] = (float)sin(w * m);
+    }
+    return THZ_OK;
+}
+
+// ------------------------------------------------------------------------------- launch accounting
+// The only mutable process-wide state of the library: a launch counter and, when enabled by
+// thz_profile_enable(1), a list of CUDA event pairs bracketing each kernel (bench.py reads them to
+// attribute step time to kernels on the launching stream; never enabled in normal operation).
+struct ProfRec {
+    cudaEvent_t a, b;
+    int cls;
+};
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static thread_local cudaEvent_t g_open_event = nullptr;
+
+void thz_launch_begin(cudaStream_t stream, int) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    cudaEvent_t a;
+    if (cudaEventCreate(&a) != cudaSuccess) return;
+    cudaEventRecord(a, stream);
+    g_open_event = a;
+}
+
+void thz_launch_end(cudaStream_t stream, int kernel_class) {
+    if (!g_prof_on.load(std::memory_order_relaxed) || !g_open_event) return;
+    ProfRec r;
+    r.a = g_open_event;
+    g_open_event = nullptr;
+    r.cls = kernel_class;
+    if (cudaEventCreate(&r.b) != cudaSuccess) {
+        cudaEventDestroy(r.a);
+        return;
+    }
+    cudaEventRecord(r.b, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+}
+
+extern "C" uint64_t thz_launch_count(void) { return g_launches.load(); }
+
+extern "C" int thz_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    g_prof_on.store(on ? 1 : 0);
+    return THZ_OK;
+}
+
+extern "C" int thz_profile_read(int32_t nclasses, float* ms_sum, int32_t* count) {
+    if (!ms_sum || !count) return thz_set_error(THZ_E_NULL, "thz_profile_read: null pointer");
+    for (int i = 0; i < nclasses; ++i) {
+        ms_sum[i] = 0.f;
+        count[i] = 0;
+    }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) {
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e != cudaSuccess) return thz_set_cuda_error("cudaEventSynchronize", e);
+        float ms = 0.f;
+        e = cudaEventElapsedTime(&ms, r.a, r.b);
+        if (e != cudaSuccess) return thz_set_cuda_error("cudaEventElapsedTime", e);
+        if (r.cls >= 0 && r.cls < nclasses) {
+            ms_sum[r.cls] += ms;
+            count[r.cls] += 1;
+        }
     }
     return THZ_OK;
 }

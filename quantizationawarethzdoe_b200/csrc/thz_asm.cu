@@ -89,16 +89,19 @@ static int set_smem(K kernel, size_t bytes) {
     return THZ_OK;
 }
 
-#define THZ_LAUNCH(kern, mixed, grid, block, smem, stream, args)                                \
+#define THZ_LAUNCH(kern, cls, mixed, grid, block, smem, stream, args)                           \
     do {                                                                                        \
         int rc_;                                                                                \
         if (mixed) {                                                                            \
             if ((rc_ = set_smem(kern<true>, smem)) != THZ_OK) return rc_;                       \
+            thz_launch_begin(stream, cls);                                                      \
             kern<true><<<grid, block, smem, stream>>>(args);                                    \
         } else {                                                                                \
             if ((rc_ = set_smem(kern<false>, smem)) != THZ_OK) return rc_;                      \
+            thz_launch_begin(stream, cls);                                                      \
             kern<false><<<grid, block, smem, stream>>>(args);                                   \
         }                                                                                       \
+        thz_launch_end(stream, cls);                                                            \
         cudaError_t e_ = cudaGetLastError();                                                    \
         if (e_ != cudaSuccess) return thz_set_cuda_error(#kern, e_);                            \
     } while (0)
@@ -131,9 +134,9 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
             if (e != cudaSuccess) return thz_set_cuda_error("cudaMemsetAsync(gh)", e);
             zeroed = true;
         }
-        THZ_LAUNCH(thz_k1_row_fwd, L.mixed_w, L.k1_grid, L.k1_threads, L.k1_smem, stream, L.k1);
-        THZ_LAUNCH(thz_k2_col, L.mixed_h, dim3(L.k2_gridx, nbc), L.k2_threads, L.k2_smem, stream, L.k2);
-        THZ_LAUNCH(thz_k3_row_inv, L.mixed_w, dim3(L.k3_gridx, L.k3_gridy), L.k3_threads, L.k3_smem, stream, L.k3);
+        THZ_LAUNCH(thz_k1_row_fwd, THZ_KC_ROW_FWD, L.mixed_w, L.k1_grid, L.k1_threads, L.k1_smem, stream, L.k1);
+        THZ_LAUNCH(thz_k2_col, THZ_KC_COL, L.mixed_h, dim3(L.k2_gridx, nbc), L.k2_threads, L.k2_smem, stream, L.k2);
+        THZ_LAUNCH(thz_k3_row_inv, THZ_KC_ROW_INV, L.mixed_w, dim3(L.k3_gridx, L.k3_gridy), L.k3_threads, L.k3_smem, stream, L.k3);
     }
     return THZ_OK;
 }
@@ -172,7 +175,7 @@ extern "C" int thz_fft2_c2c(const void* x, void* y, int32_t batch, int32_t H, in
     while (lines > 1 && lines * lw > 64 * 1024) --lines;
     a1.lines = lines;
     const int g1 = (batch * H + lines - 1) / lines;
-    THZ_LAUNCH(thz_k1_row_fwd, pw.mixed, g1, 256, lines * lw, stream, a1);
+    THZ_LAUNCH(thz_k1_row_fwd, THZ_KC_ROW_FWD, pw.mixed, g1, 256, lines * lw, stream, a1);
 
     ColFftArgs a2;
     memset(&a2, 0, sizeof(a2));
@@ -191,6 +194,6 @@ extern "C" int thz_fft2_c2c(const void* x, void* y, int32_t batch, int32_t H, in
     a2.tw = (const cpx*)tw_h;
     const int work = (H / 16 + 1) * cols;
     const int threads = work >= 1024 ? 512 : (work >= 384 ? 256 : 128);
-    THZ_LAUNCH(thz_k2f_col_fft, ph.mixed, dim3((W + cols - 1) / cols, batch), threads, cols * lh, stream, a2);
+    THZ_LAUNCH(thz_k2f_col_fft, THZ_KC_FFT2_COL, ph.mixed, dim3((W + cols - 1) / cols, batch), threads, cols * lh, stream, a2);
     return THZ_OK;
 }

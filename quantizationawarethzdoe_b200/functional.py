@@ -1,0 +1,353 @@
+"""torch.autograd.Functions over the C ABI: explicit forward kernels and explicit adjoint kernels.
+
+Nothing in here computes on the CPU or through torch.fft: each Function validates that its inputs
+live on a CUDA device, allocates outputs / workspaces with torch (the caching allocator owns all
+device memory), and calls libthzdoe.so on torch's current stream.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+from . import asm_host as AH
+
+BASE_PLANE_THICKNESS = 2 * 1e-3   # Components/QuantizedDOE.py:23
+
+# tuning knobs (bench.py / tests may override): fields per kernel group, K2 tile width, rows per CTA
+TUNE = {"bc_chunk": 0, "k2_cols": 0, "lines": 0}
+
+_ws_cache = {}
+
+
+def _workspace(numel, device):
+    """One cached complex64 scratch tensor per device, grown on demand (never shrunk)."""
+    key = str(device)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < numel:
+        ws = torch.empty(numel, dtype=torch.complex64, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _c64(t, name):
+    N.require_cuda(t, name)
+    if t.dtype != torch.complex64:
+        if t.dtype in (torch.float32, torch.float16, torch.bfloat16):
+            t = t.to(torch.complex64)
+        else:
+            raise TypeError("%s must be complex64 (got %s): the sm_100a path computes in fp32" % (name, t.dtype))
+    return t.contiguous()
+
+
+class AsmPlan:
+    """Everything static about one ASM_prop call: geometry + device copies of the transfer-function
+    vectors / table and DOE coefficients.  Built once per (shape, spacing, wavelengths, z) by ASM_prop."""
+
+    def __init__(self, B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, tf_mode):
+        self.B, self.C, self.H, self.W = B, C, H, W
+        self.pad_h, self.pad_w, self.Hp, self.Wp = pad_h, pad_w, Hp, Wp
+        self.unpad = unpad
+        if unpad:
+            self.outH, self.outW, self.out_r0, self.out_c0 = H, W, pad_h, pad_w
+        else:
+            self.outH, self.outW, self.out_r0, self.out_c0 = Hp, Wp, 0, 0
+        self.device = device
+        self.rowvec = rowvec.to(device) if rowvec is not None else None
+        self.colvec = colvec.to(device) if colvec is not None else None
+        self.scal = scal.to(device) if scal is not None else None
+        self.table = table.to(device) if table is not None else None
+        self.tf_mode = tf_mode
+        self.tw_h = N.twiddles(Hp, device)
+        self.tw_w = N.twiddles(Wp, device)
+
+    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None):
+        """One thz_asm_propagate call.  Forward: x [B,C,H,W] -> y [B,C,outH,outW].
+        Adjoint (conj=1): x = grad [B,C,outH,outW] -> y [B,C,H,W] (regions swapped)."""
+        B, C = self.B, self.C
+        if not conj:
+            inH, inW, in_r0, in_c0 = self.H, self.W, self.pad_h, self.pad_w
+            outH, outW, out_r0, out_c0 = self.outH, self.outW, self.out_r0, self.out_c0
+        else:
+            inH, inW, in_r0, in_c0 = self.outH, self.outW, self.out_r0, self.out_c0
+            outH, outW, out_r0, out_c0 = self.H, self.W, self.pad_h, self.pad_w
+        nbc = x.shape[0] * x.shape[1]
+        ws = _workspace(AH.workspace_elems(x.shape[0], C, inH, outH, self.Wp, TUNE["bc_chunk"]), x.device)
+        d = AH.build_desc(x, y, x.shape[0], C, inH, inW, self.Hp, self.Wp, in_r0, in_c0, outH, outW, out_r0, out_c0,
+                          self.tf_mode, 1 if conj else 0, self.rowvec, self.colvec, self.scal, self.table,
+                          doe_mode, BASE_PLANE_THICKNESS, hmap, coef, xsaved, gh, self.tw_h, self.tw_w, ws,
+                          bc_chunk=TUNE["bc_chunk"], tune_k2_cols=TUNE["k2_cols"], tune_lines=TUNE["lines"])
+        N.check(N.lib().thz_asm_propagate(ctypes.byref(d), N.current_stream_ptr(x.device)), "thz_asm_propagate")
+        return y
+
+
+class AsmPropagateFn(torch.autograd.Function):
+    """y = ASM(x).  Backward = the adjoint pipeline with conj(H) (explicit kernel, not autograd replay)."""
+
+    @staticmethod
+    def forward(ctx, x, plan):
+        x = _c64(x, "field.data")
+        y = torch.empty(x.shape[0], plan.C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
+        plan.run(x, y, conj=0)
+        ctx.plan = plan
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        plan = ctx.plan
+        g = _c64(g, "grad_output")
+        gx = torch.empty(g.shape[0], plan.C, plan.H, plan.W, dtype=torch.complex64, device=g.device)
+        plan.run(g, gx, conj=1)
+        return gx, None
+
+
+class DoeAsmFn(torch.autograd.Function):
+    """y = ASM(x * p(h)) in one fused pipeline; backward returns grad wrt x (if needed) and wrt h."""
+
+    @staticmethod
+    def forward(ctx, x, hmap, plan, coef):
+        x = _c64(x, "field.data")
+        N.require_cuda(hmap, "height_map")
+        hmap = hmap.to(torch.float32).contiguous()
+        y = torch.empty(x.shape[0], plan.C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
+        plan.run(x, y, conj=0, doe_mode=1, hmap=hmap, coef=coef)
+        ctx.plan, ctx.coef = plan, coef
+        ctx.save_for_backward(x, hmap)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, coef = ctx.plan, ctx.coef
+        x, hmap = ctx.saved_tensors
+        g = _c64(g, "grad_output")
+        need_x, need_h = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx = torch.empty_like(x) if need_x else None
+        if need_h:
+            gh = torch.empty(plan.H, plan.W, dtype=torch.float32, device=g.device)
+            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=gh)
+        else:
+            gh = None
+            # grad wrt x only: adjoint ASM then conj(p) multiply
+            gtmp = torch.empty_like(x)
+            plan.run(g, gtmp, conj=1)
+            N.check(N.lib().thz_doe_modulate_bwd(N.ptr(gtmp), None, N.ptr(hmap), N.ptr(coef), BASE_PLANE_THICKNESS,
+                                                 N.ptr(gx), None, x.shape[0], x.shape[1], x.shape[2], x.shape[3],
+                                                 N.current_stream_ptr(g.device)), "thz_doe_modulate_bwd")
+        return gx, gh, None, None
+
+
+class DoeModulateFn(torch.autograd.Function):
+    """y = x * p(h) (stand-alone; used when a DOE output is consumed by something other than ASM_prop)."""
+
+    @staticmethod
+    def forward(ctx, x, hmap, coef):
+        x = _c64(x, "field.data")
+        N.require_cuda(hmap, "height_map")
+        hmap = hmap.to(torch.float32).contiguous()
+        y = torch.empty_like(x)
+        B, C, H, W = x.shape
+        N.check(N.lib().thz_doe_modulate_fwd(N.ptr(x), N.ptr(y), N.ptr(hmap), N.ptr(coef), BASE_PLANE_THICKNESS,
+                                             B, C, H, W, N.current_stream_ptr(x.device)), "thz_doe_modulate_fwd")
+        ctx.coef = coef
+        ctx.save_for_backward(x, hmap)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, hmap = ctx.saved_tensors
+        g = _c64(g, "grad_output")
+        B, C, H, W = x.shape
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gh = torch.empty(H, W, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
+        N.check(N.lib().thz_doe_modulate_bwd(N.ptr(g), N.ptr(x), N.ptr(hmap), N.ptr(ctx.coef), BASE_PLANE_THICKNESS,
+                                             N.ptr(gx), N.ptr(gh), B, C, H, W, N.current_stream_ptr(g.device)),
+                "thz_doe_modulate_bwd")
+        return gx, gh, None
+
+
+# ----------------------------------------------------------------------------- height map / quantizers
+def _f32(t, name):
+    N.require_cuda(t, name)
+    return t.to(torch.float32).contiguous()
+
+
+class HeightFromWeightFn(torch.autograd.Function):
+    """h = hmax * sigmoid(clamp(w, -c, c))  (Components/QuantizedDOE.py:277)."""
+
+    @staticmethod
+    def forward(ctx, w, hmax, clampv):
+        w = _f32(w, "weight_height_map")
+        h = torch.empty_like(w)
+        N.check(N.lib().thz_height_fwd(N.ptr(w), hmax, clampv, N.ptr(h), w.numel(), N.current_stream_ptr(w.device)), "thz_height_fwd")
+        ctx.hmax, ctx.clampv = hmax, clampv
+        ctx.save_for_backward(w)
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        g = _f32(g, "grad")
+        gw = torch.empty_like(w)
+        N.check(N.lib().thz_height_bwd(N.ptr(g), N.ptr(w), ctx.hmax, ctx.clampv, N.ptr(gw), w.numel(),
+                                       N.current_stream_ptr(w.device)), "thz_height_bwd")
+        return gw, None, None
+
+
+class SteQuantizeFn(torch.autograd.Function):
+    """STEQuantizationFunction (Components/QuantizedDOE.py:1239-1253) on a height map; identity backward.
+    Returns (q, idx)."""
+
+    @staticmethod
+    def forward(ctx, h, lut):
+        h = _f32(h, "height_map")
+        lut = _f32(lut, "lut")
+        q = torch.empty_like(h)
+        idx = torch.empty(h.shape, dtype=torch.int32, device=h.device)
+        N.check(N.lib().thz_quant_ste_fwd(N.ptr(h), 0, 0.0, 0.0, N.ptr(lut), lut.numel(), N.ptr(q), N.ptr(idx), None,
+                                          h.numel(), N.current_stream_ptr(h.device)), "thz_quant_ste_fwd")
+        ctx.mark_non_differentiable(idx)
+        return q, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        return g.clone(), None
+
+
+class SteFromWeightFn(torch.autograd.Function):
+    """Fused sigmoid height construction + STE level selection (STEQuantizedDOELayer.preprocessed_height_map,
+    Components/QuantizedDOE.py:1379-1388).  Returns (q, idx)."""
+
+    @staticmethod
+    def forward(ctx, w, lut, hmax, clampv):
+        w = _f32(w, "weight_height_map")
+        lut = _f32(lut, "lut")
+        q = torch.empty_like(w)
+        idx = torch.empty(w.shape, dtype=torch.int32, device=w.device)
+        N.check(N.lib().thz_quant_ste_fwd(N.ptr(w), 1, hmax, clampv, N.ptr(lut), lut.numel(), N.ptr(q), N.ptr(idx), None,
+                                          w.numel(), N.current_stream_ptr(w.device)), "thz_quant_ste_fwd")
+        ctx.hmax, ctx.clampv = hmax, clampv
+        ctx.save_for_backward(w)
+        ctx.mark_non_differentiable(idx)
+        return q, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        (w,) = ctx.saved_tensors
+        g = _f32(g, "grad")
+        gw = torch.empty_like(w)
+        N.check(N.lib().thz_height_bwd(N.ptr(g), N.ptr(w), ctx.hmax, ctx.clampv, N.ptr(gw), w.numel(),
+                                       N.current_stream_ptr(w.device)), "thz_height_bwd")
+        return gw, None, None, None
+
+
+class NnQuantizeFn(torch.autograd.Function):
+    """NearestNeighborSearch / PolyGrad / SigmoidGrad (Components/quantization.py:59-122). kind: 0/1/2."""
+
+    @staticmethod
+    def forward(ctx, x, lut, mid, s, kind):
+        x = _f32(x, "thickness")
+        lut = _f32(lut, "lut")
+        mid = _f32(mid, "lut_midvals")
+        q = torch.empty_like(x)
+        idx = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+        N.check(N.lib().thz_quant_nn_fwd(N.ptr(x), N.ptr(lut), lut.numel(), N.ptr(mid), mid.numel(), N.ptr(q), N.ptr(idx),
+                                         x.numel(), N.current_stream_ptr(x.device)), "thz_quant_nn_fwd")
+        ctx.s, ctx.kind = float(s), int(kind)
+        ctx.save_for_backward(x, idx, lut)
+        ctx.mark_non_differentiable(idx)
+        return q, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        x, idx, lut = ctx.saved_tensors
+        g = _f32(g, "grad")
+        gx = torch.empty_like(x)
+        N.check(N.lib().thz_quant_nn_bwd(N.ptr(g), N.ptr(x), N.ptr(idx), N.ptr(lut), lut.numel(), ctx.s, ctx.kind, N.ptr(gx),
+                                         x.numel(), N.current_stream_ptr(x.device)), "thz_quant_nn_bwd")
+        return gx, None, None, None, None
+
+
+class PsqFn(torch.autograd.Function):
+    """PSQuantizedDOELayer.preprocessed_height_map (Components/QuantizedDOE.py:1193-1207)."""
+
+    @staticmethod
+    def forward(ctx, w, hmax, levels, tau):
+        w = _f32(w, "weight_height_map")
+        out = torch.empty_like(w)
+        d = torch.empty_like(w)
+        N.check(N.lib().thz_quant_psq_fwd(N.ptr(w), hmax, levels, tau, N.ptr(out), N.ptr(d), w.numel(),
+                                          N.current_stream_ptr(w.device)), "thz_quant_psq_fwd")
+        ctx.save_for_backward(d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return g * d, None, None, None
+
+
+class GumbelV3Fn(torch.autograd.Function):
+    """SoftGumbelQuantizedDOELayerv3 level selection (Components/QuantizedDOE.py:794-860), noise supplied.
+    Returns (height_map, idx)."""
+
+    @staticmethod
+    def forward(ctx, w, lut, noise, hmax, kfac, c_s, tau, tau_max, beta, phase_input=False):
+        w = _f32(w, "weight_init_phase")
+        lut = _f32(lut, "lut")
+        noise = _f32(noise, "gumbel noise")
+        L = lut.numel()
+        assert noise.numel() == L * w.numel(), "noise must be [1,L,H,W]"
+        out = torch.empty_like(w)
+        idx = torch.empty(w.shape, dtype=torch.int32, device=w.device)
+        d = torch.empty_like(w)
+        s = float(tau_max / tau)
+        N.check(N.lib().thz_quant_gumbel_v3_fwd(N.ptr(w), N.ptr(lut), L, N.ptr(noise), hmax, kfac, c_s, tau, tau_max, s,
+                                                float(beta), float(1 - beta), 1 if phase_input else 0, N.ptr(out), N.ptr(idx), N.ptr(d),
+                                                w.numel(),
+                                                N.current_stream_ptr(w.device)), "thz_quant_gumbel_v3_fwd")
+        ctx.save_for_backward(d)
+        ctx.mark_non_differentiable(idx)
+        return out, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        (d,) = ctx.saved_tensors
+        return (g * d,) + (None,) * 9
+
+
+class GumbelNaiveFn(torch.autograd.Function):
+    """NaiveGumbelQuantizedDOELayer level selection (Components/QuantizedDOE.py:1022-1031). logits [H,W,L]."""
+
+    @staticmethod
+    def forward(ctx, logits, lut, noise, tau):
+        logits = _f32(logits, "logits")
+        lut = _f32(lut, "lut")
+        noise = _f32(noise, "gumbel noise")
+        L = lut.numel()
+        n = logits.numel() // L
+        q = torch.empty(logits.shape[:-1], dtype=torch.float32, device=logits.device)
+        idx = torch.empty(logits.shape[:-1], dtype=torch.int32, device=logits.device)
+        dq = torch.empty_like(logits)
+        N.check(N.lib().thz_quant_gumbel_naive_fwd(N.ptr(logits), N.ptr(noise), N.ptr(lut), L, float(tau), N.ptr(q), N.ptr(idx),
+                                                   N.ptr(dq), n, N.current_stream_ptr(logits.device)),
+                "thz_quant_gumbel_naive_fwd")
+        ctx.save_for_backward(dq)
+        ctx.mark_non_differentiable(idx)
+        return q, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        (dq,) = ctx.saved_tensors
+        return g.unsqueeze(-1) * dq, None, None, None
+
+
+def fft2_c2c(x, inverse=False, ortho=False):
+    """Stand-alone natural-order batched 2-D FFT over the last two dims (thz_fft2_c2c)."""
+    x = _c64(x, "input")
+    H, W = x.shape[-2], x.shape[-1]
+    batch = x.numel() // (H * W)
+    y = torch.empty_like(x)
+    ws = _workspace(batch * H * W, x.device)
+    N.check(N.lib().thz_fft2_c2c(N.ptr(x), N.ptr(y), batch, H, W, 1 if inverse else 0, 1 if ortho else 0,
+                                 N.ptr(N.twiddles(H, x.device)), N.ptr(N.twiddles(W, x.device)), N.ptr(ws),
+                                 ws.numel() * 8, N.current_stream_ptr(x.device)), "thz_fft2_c2c")
+    return y

@@ -1,0 +1,133 @@
+"""`not gpu` checks of the C-ABI library (loads, exports everything include/thzdoe.h declares, host-only
+planning helpers) and of the host-side logic mirrored from the reference (padding, validation, errors).
+No compute call is made: there is no GPU here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, golden, rel_l2
+from oracle import asm_oracle as AO
+from quantizationawarethzdoe_b200 import _native as N
+from quantizationawarethzdoe_b200 import asm_host as AH
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from quantizationawarethzdoe_b200 import build
+    build.build()
+    return N.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "thzdoe.h")).read()
+    declared = set(re.findall(r"\b(thz_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("thz_asm_desc")
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libthzdoe.so does not export %s" % name
+    assert declared == set(N.EXPORTS), "python binding list out of sync with include/thzdoe.h"
+    assert lib.thz_version() >= 100
+
+
+def test_descriptor_layout_matches_header():
+    # thz_asm_desc: 12 int32, 2 ptr, 2 int32, 4 ptr, int32+float, 4 ptr, 2 ptr, ptr, u64, 4 int32
+    assert ctypes.sizeof(N.AsmDesc) == 12 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 4 * 4
+
+
+def test_plan_helpers(lib):
+    radices = (ctypes.c_int32 * 16)()
+    ns = ctypes.c_int32()
+    for n, want in ((4096, [16, 16, 16]), (1024, [16, 8, 8]), (2000, [25, 20, 4]), (400, [25, 16]), (3000, [25, 20, 6]), (300, [25, 12])):
+        assert lib.thz_fft_plan_info(n, radices, ctypes.byref(ns)) == 0
+        assert list(radices)[:ns.value] == want and int(np.prod(want)) == n
+    assert lib.thz_fft_plan_info(2 * 13, radices, ctypes.byref(ns)) == -3
+    assert b"prime factor" in lib.thz_last_error()
+    for n in (8, 60, 400, 4096):
+        perm = N.slot_to_bin(n, lib.thz_fft_slot_to_bin)
+        assert sorted(perm.tolist()) == list(range(n))
+    tw = (ctypes.c_float * (2 * 12))()
+    assert lib.thz_fft_twiddles(12, tw) == 0
+    t = torch.tensor(list(tw)).reshape(12, 2)
+    assert rel_l2(torch.view_as_complex(t), N.twiddles_host(12)) < 1e-7
+
+
+def test_null_descriptor_is_rejected_without_touching_cuda(lib):
+    d = N.AsmDesc()
+    assert lib.thz_asm_propagate(ctypes.byref(d), None) == -1      # THZ_E_NULL
+    assert lib.thz_asm_workspace_bytes(ctypes.byref(d)) == 0
+    assert lib.thz_quant_ste_fwd(None, 0, 0.0, 0.0, None, 4, None, None, None, 10, None) == -1
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(N.ThzError, match="no CPU fallback"):
+        N.load_library(str(tmp_path / "nope.so"))
+
+
+# ----------------------------------------------------------------------------- host logic
+def test_padding_rules():
+    assert AH.compute_padding(50, 100, AH.normalise_padding_scale(1), True) == (25, 50, 100, 200)   # ASM_Prop.py:50-54
+    assert AH.compute_padding(50, 100, AH.normalise_padding_scale(torch.tensor([1, 2])), True) == (25, 100, 100, 300)
+    assert AH.compute_padding(100, 100, AH.normalise_padding_scale(2), True) == (100, 100, 300, 300)
+    assert AH.compute_padding(33, 36, AH.normalise_padding_scale([1, 2]), True) == (16, 36, 65, 108)
+    assert AH.compute_padding(7, 9, None, False) == (0, 0, 7, 9)
+    with pytest.raises(Exception, match="padding_scale"):
+        AH.normalise_padding_scale([1, 2, 3])
+    for ps in (None, 2, [1, 2], torch.tensor(3.0), torch.tensor([1.0, 2.0])):
+        a = AH.compute_padding(40, 24, AH.normalise_padding_scale(ps), True)
+        b = AO.compute_padding(40, 24, ps, True)
+        assert a == b
+
+
+@pytest.mark.parametrize("bt", ["exact", "approx"])
+def test_separable_vectors_rebuild_the_reference_kernel(bt):
+    """tf_vectors -> full kernel must equal the reference kernel bit for bit (same CPU ops)."""
+    Hp, Wp, lams, sp, z = 60, 108, [0.9e-3, 1.2e-3], [0.5e-3, 0.4e-3], 0.05
+    Hc = AH.tf_centred_reference_order(Hp, Wp, sp, lams, z, True, bt)
+    ref = AO.centred_transfer_function(Hp, Wp, sp, lams, z, True, bt)[0]
+    assert torch.equal(torch.view_as_real(Hc), torch.view_as_real(ref))
+    g = golden("asm_approx_mixedpad" if bt == "approx" else "asm_pow2")
+    Hp, Wp = g["kernel"].shape[-2:]
+    Hc = AH.tf_centred_reference_order(Hp, Wp, g["spacing"].float(), g["wavelengths"].float(), g["z"], True, g["bandlimit_type"])
+    assert torch.equal(torch.view_as_real(Hc), torch.view_as_real(g["kernel"][0]))
+
+
+def test_electric_field_validation_matches_reference():
+    from quantizationawarethzdoe_b200 import ElectricField
+    cpu = torch.device("cpu")
+    x = torch.zeros(1, 2, 4, 4, dtype=torch.complex64)
+    f = ElectricField(x, wavelengths=[1e-3, 2e-3], spacing=1e-3, device=cpu)
+    assert f.field_type == "scalar" and f.spacing.tolist() == pytest.approx([1e-3, 1e-3]) and f.wavelengths.dtype == torch.float32
+    assert (f.height, f.width, f.num_wavelengths, f.num_batches) == (4, 4, 2, 1)
+    assert ElectricField(torch.zeros(3, 1, 2, 2), 1e-3, 1e-3, device=cpu).field_type == "vectorial"
+    assert ElectricField(torch.zeros(5, 1, 2, 2), 1e-3, 1e-3, device=cpu).field_type == "batch"
+    with pytest.raises(ValueError, match="channels"):
+        ElectricField(x, wavelengths=[1e-3], spacing=1e-3, device=cpu)
+    with pytest.raises(ValueError, match="Spacing"):
+        ElectricField(x, wavelengths=[1e-3, 2e-3], spacing=[1e-3, 1e-3, 1e-3], device=cpu)
+    with pytest.raises(ValueError, match="Wavelengths"):
+        ElectricField(x, wavelengths=None, spacing=1e-3, device=cpu)
+    with pytest.raises(AssertionError):
+        ElectricField(torch.zeros(2, 4, 4), wavelengths=[1e-3, 2e-3], spacing=1e-3, device=cpu)
+
+
+def test_asm_prop_surface_and_loud_failure_without_cuda():
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField
+    cpu = torch.device("cpu")
+    with pytest.raises(Exception, match="padding_scale"):
+        ASM_prop(padding_scale=[1, 2, 3], device=cpu)
+    a = ASM_prop(z_distance=0.1, padding_scale=2, device=cpu)
+    assert a.compute_padding(100, 100) == (300, 300) and a.compute_padding(100, 100, True) == (100, 100)
+    a.z = np.float64(0.2)                      # depth-sweep loops assign python / numpy scalars (ASM_Prop.py:190-195)
+    assert float(a._z_f32()) == pytest.approx(0.2)
+    a.z = torch.tensor(0.3)
+    assert float(a.z) == pytest.approx(0.3)
+    f = ElectricField(torch.zeros(1, 1, 8, 8, dtype=torch.complex64), 1e-3, 1e-3, device=cpu)
+    assert a.create_kernel(f).shape == (1, 1, 24, 24)
+    assert set(a.state_dict().keys()) == {"_Kx", "_Ky"}
+    with pytest.raises(N.ThzError, match="no CPU path"):   # the product never falls back to the CPU
+        a.check_Zc = False
+        a(f)

@@ -1,0 +1,141 @@
+"""CPU replay of the CUDA kernel bodies (tests/emul/emul.cpp) against the oracle.
+
+This is the `not gpu` check of everything that can go wrong in the kernels short of the hardware:
+plan factorisation, digit-reversal bookkeeping, zero-pad / crop pruning, anisotropic and odd paddings,
+chunking over fields, the fused DOE prologue and the DOE adjoint epilogue with its register
+accumulators, and the transfer function in both modes.  The same source compiles for sm_100a."""
+import ctypes
+
+import pytest
+import torch
+
+from helpers import emul_lib, rel_l2
+from oracle import asm_oracle as AO
+from oracle import doe_oracle as DO
+from quantizationawarethzdoe_b200 import _native as N
+from quantizationawarethzdoe_b200 import asm_host as AH
+
+E = emul_lib()
+TOL = 1e-5       # north_star tolerance on complex64 fields and gradients
+TOL_TABLE = 2e-6  # cached-H mode differs from the reference only by FFT round-off
+
+
+def _run(x, desc_kwargs, sm=148):
+    d = AH.build_desc(**desc_kwargs)
+    rc = E.thz_emul_asm_propagate(ctypes.byref(d), sm)
+    assert rc == 0, rc
+
+
+def _setup(B, C, H, W, scale, lams, dxy, z, bt="exact", do_pad=True, unpad=True, mode=0, chunk=0):
+    ps = AH.normalise_padding_scale(scale, do_pad)
+    ph, pw, Hp, Wp = AH.compute_padding(H, W, ps, do_pad)
+    outH, outW, or0, oc0 = (H, W, ph, pw) if (do_pad and unpad) else (Hp, Wp, 0, 0)
+    rv, cv, sc = AH.tf_vectors(Hp, Wp, dxy, lams, z, True, bt)
+    table = None
+    if mode == 1:
+        table = AH.tf_table_slot_order(AH.tf_centred_reference_order(Hp, Wp, dxy, lams, z, True, bt), E.thz_emul_slot_to_bin)
+    base = dict(B=B, C=C, inH=H, inW=W, Hp=Hp, Wp=Wp, in_r0=ph, in_c0=pw, outH=outH, outW=outW, out_r0=or0, out_c0=oc0,
+                tf_mode=mode, tf_conj=0, rowvec=rv, colvec=cv, scal=sc, table=table, doe_mode=0, doe_base=0.0, hmap=None,
+                coef=None, xsaved=None, gh=None, tw_h=N.twiddles_host(Hp), tw_w=N.twiddles_host(Wp),
+                ws=torch.zeros(AH.workspace_elems(B, C, max(H, outH), max(H, outH), Wp, chunk), dtype=torch.complex64), bc_chunk=chunk)
+    return base, (outH, outW)
+
+
+CASES = [
+    # B, C, H, W, scale, wavelengths, spacing, z, kwargs
+    (1, 1, 32, 32, None, [1e-3], 0.5e-3, 0.1, {}),
+    (2, 2, 64, 64, None, [1e-3, 1.01e-3], 0.5e-3, 0.1, {}),
+    (1, 1, 50, 50, 2, [1e-3], [1e-3, 0.7e-3], 0.26, dict(mode=1)),                      # 150 = 25*6
+    (1, 3, 30, 36, [1, 2], [0.9e-3, 1e-3, 1.2e-3], 0.5e-3, 0.05, dict(bt="approx")),     # 60 x 108
+    (1, 1, 100, 100, 2, [1e-3], 1e-3, 0.3, dict(mode=1)),                                # notebook geometry 100 -> 300
+    (3, 2, 40, 24, None, [1e-3, 1.1e-3], 0.5e-3, 0.1, dict(unpad=False, chunk=4)),       # padded output, ragged chunks
+    (1, 1, 48, 48, None, [1e-3], 0.5e-3, 0.1, dict(do_pad=False, mode=1)),
+    (1, 1, 200, 200, None, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                           # 400 = 25*16 (config 4 layer size)
+    (1, 1, 256, 256, None, [1e-3], 0.5e-3, 0.1, {}),
+    (1, 1, 7, 21, 2, [1e-3], 0.5e-3, 0.02, dict(mode=1)),                                # odd sizes: 21 x 63 (radix 7, 3)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_s%s" % (c[2], c[3], c[4]))
+def test_asm_forward_replay_matches_oracle(case):
+    B, C, H, W, scale, lams, dxy, z, kw = case
+    torch.manual_seed(0)
+    x = torch.randn(B, C, H, W, dtype=torch.complex64)
+    base, (outH, outW) = _setup(B, C, H, W, scale, lams, dxy, z, **kw)
+    y = torch.zeros(B, C, outH, outW, dtype=torch.complex64)
+    _run(x, dict(base, x=x, y=y))
+    yo = AO.asm_forward(x, lams, dxy, z, padding_scale=scale, do_padding=kw.get("do_pad", True),
+                        do_unpad_after_pad=kw.get("unpad", True), bandlimit_type=kw.get("bt", "exact"))
+    # in-register H on tiny grids is dominated by the handful of bins where torch's CPU sqrt is 1 ulp off
+    tol = TOL_TABLE if kw.get("mode", 0) == 1 else 2e-5
+    assert rel_l2(y, yo) < tol
+
+
+def test_in_register_mask_is_bit_exact():
+    """Where the kernel zeroes H must be exactly where the reference zeroes it."""
+    H = W = 64
+    lams, dxy, z = [1e-3, 1.3e-3], 0.5e-3, 0.4
+    base, _ = _setup(1, 2, H, W, None, lams, dxy, z)
+    # propagate a delta at the canvas origin region: spectrum is flat, so |fft2(y_padded)| shows the mask
+    Hp = Wp = 128
+    base.update(inH=Hp, inW=Wp, in_r0=0, in_c0=0, outH=Hp, outW=Wp, out_r0=0, out_c0=0,
+                ws=torch.zeros(2 * Hp * Wp, dtype=torch.complex64))
+    x = torch.zeros(1, 2, Hp, Wp, dtype=torch.complex64)
+    x[..., 0, 0] = 1
+    y = torch.zeros_like(x)
+    _run(x, dict(base, x=x, y=y))
+    spec = torch.fft.fft2(y)
+    Hc = AO.centred_transfer_function(Hp, Wp, dxy, lams, z)
+    Hn = torch.fft.ifftshift(Hc, dim=(-2, -1))
+    assert torch.equal(spec.abs() > 0.5, Hn.abs() > 0.5)
+    assert rel_l2(spec, Hn) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,scale,mode,sm,chunk", [
+    (1, 1, 32, 32, None, 1, 148, 0),
+    (2, 3, 48, 40, None, 1, 148, 0),
+    (2, 3, 48, 40, None, 1, 148, 4),      # gh accumulated across chunks (atomic path)
+    (5, 1, 50, 50, 2, 1, 4, 0),           # few SMs: one CTA walks all five fields, register accumulators
+    (1, 2, 64, 64, None, 0, 148, 0),
+])
+def test_doe_fused_forward_and_adjoint_replay(B, C, H, W, scale, mode, sm, chunk):
+    lams = [1e-3, 1.02e-3, 1.05e-3][:C]
+    dxy, z, eps, tand = 0.5e-3, 0.1, 2.66, 0.003
+    torch.manual_seed(0)
+    x = torch.randn(B, C, H, W, dtype=torch.complex64)
+    h = torch.rand(H, W) * 1e-3
+    g = torch.randn(B, C, H, W, dtype=torch.complex64)
+    base, _ = _setup(B, C, H, W, scale, lams, dxy, z, mode=mode, chunk=chunk)
+    coef = AH.doe_coefficients(lams, eps, tand)
+    y = torch.zeros_like(x)
+    _run(x, dict(base, x=x, y=y, doe_mode=1, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef), sm)
+    xr, hr = x.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    yo = AO.asm_forward(DO.modulate(xr, hr, lams, eps, tand), lams, dxy, z, padding_scale=scale)
+    gxo, gho = torch.autograd.grad(yo, (xr, hr), g)
+    gx, gh = torch.zeros_like(x), torch.full((H, W), 7.0)
+    _run(g, dict(base, x=g, y=gx, tf_conj=1, doe_mode=2, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef, xsaved=x, gh=gh), sm)
+    tol = TOL_TABLE if mode == 1 else TOL
+    assert rel_l2(y, yo.detach()) < tol
+    assert rel_l2(gx, gxo) < tol
+    assert rel_l2(gh, gho) < tol
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (64, 48), (60, 100), (8, 250), (35, 27)])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_fft2_replay_matches_torch(H, W, inverse):
+    torch.manual_seed(1)
+    x = torch.randn(3, H, W, dtype=torch.complex64)
+    y = torch.zeros_like(x)
+    ws = torch.zeros_like(x)
+    rc = E.thz_emul_fft2_c2c(N.ptr(x), N.ptr(y), 3, H, W, inverse, 1, N.ptr(N.twiddles_host(H)), N.ptr(N.twiddles_host(W)), N.ptr(ws))
+    assert rc == 0
+    ref = (torch.fft.ifft2 if inverse else torch.fft.fft2)(x, norm="ortho")
+    assert rel_l2(y, ref) < 2e-6
+
+
+def test_unsupported_length_is_reported():
+    radices = (ctypes.c_int32 * 16)()
+    ns = ctypes.c_int32()
+    assert E.thz_emul_plan_info(26, radices, ctypes.byref(ns)) == -3      # 13 is not a supported radix
+    assert E.thz_emul_plan_info(4096, radices, ctypes.byref(ns)) == 0 and list(radices)[:3] == [16, 16, 16]
+    assert E.thz_emul_plan_info(2000, radices, ctypes.byref(ns)) == 0 and list(radices)[:3] == [25, 20, 4]
