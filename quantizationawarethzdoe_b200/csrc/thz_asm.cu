@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "thz_asm_host.h"
+#include "thz_asm_p2_launch.h"
 #include "thz_runtime.h"
 
 // ------------------------------------------------------------------------------- kernels
@@ -134,9 +135,21 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
             if (e != cudaSuccess) return thz_set_cuda_error("cudaMemsetAsync(gh)", e);
             zeroed = true;
         }
-        THZ_LAUNCH(thz_k1_row_fwd, THZ_KC_ROW_FWD, L.mixed_w, L.k1_grid, L.k1_threads, L.k1_smem, stream, L.k1);
-        THZ_LAUNCH(thz_k2_col, THZ_KC_COL, L.mixed_h, dim3(L.k2_gridx, nbc), L.k2_threads, L.k2_smem, stream, L.k2);
-        THZ_LAUNCH(thz_k3_row_inv, THZ_KC_ROW_INV, L.mixed_w, dim3(L.k3_gridx, L.k3_gridy), L.k3_threads, L.k3_smem, stream, L.k3);
+        if (L.p2_w) {
+            if ((rc = thz_p2_launch_k1(L.k1, L.k1_grid, L.k1_threads, L.k1_smem, stream)) != THZ_OK) return rc;
+        } else {
+            THZ_LAUNCH(thz_k1_row_fwd, THZ_KC_ROW_FWD, L.mixed_w, L.k1_grid, L.k1_threads, L.k1_smem, stream, L.k1);
+        }
+        if (L.p2_h) {
+            if ((rc = thz_p2_launch_k2(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem, stream)) != THZ_OK) return rc;
+        } else {
+            THZ_LAUNCH(thz_k2_col, THZ_KC_COL, L.mixed_h, dim3(L.k2_gridx, nbc), L.k2_threads, L.k2_smem, stream, L.k2);
+        }
+        if (L.p2_w) {
+            if ((rc = thz_p2_launch_k3(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem, stream)) != THZ_OK) return rc;
+        } else {
+            THZ_LAUNCH(thz_k3_row_inv, THZ_KC_ROW_INV, L.mixed_w, dim3(L.k3_gridx, L.k3_gridy), L.k3_threads, L.k3_smem, stream, L.k3);
+        }
     }
     return THZ_OK;
 }

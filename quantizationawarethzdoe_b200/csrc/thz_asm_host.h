@@ -1,7 +1,8 @@
 // Host-side launch planning for the fused ASM pipeline, shared by the CUDA launcher (thz_asm.cu)
 // and the CPU replay harness (tests/emul).  No CUDA runtime calls in here.
 #pragma once
-#include "thz_asm.cuh"
+#include <stdlib.h>
+#include "thz_asm_p2.cuh"
 
 #define THZ_SMEM_BUDGET (200 * 1024)   // per-CTA dynamic shared memory we allow ourselves (HW max 227 KB)
 
@@ -16,6 +17,7 @@ struct AsmLaunch {
     int k3_gridx, k3_gridy, k3_threads;
     size_t k3_smem;
     int mixed_w, mixed_h;
+    int p2_w, p2_h;           // 1: the compile-time specialised power-of-two kernels serve this axis
     int gh_needs_zero;        // 1: gh is accumulated with atomics and must be zeroed first
 };
 
@@ -47,6 +49,46 @@ static inline uint64_t thz_asm_chunk_fields(const thz_asm_desc* d) {
 
 static inline uint64_t thz_asm_ws_bytes(const thz_asm_desc* d) {
     return thz_asm_chunk_fields(d) * (uint64_t)thz_imax(d->inH, d->outH) * (uint64_t)d->Wp * sizeof(cpx);
+}
+
+
+static inline bool thz_is_p2_size(int n) { return n >= THZ_P2_MIN && n <= THZ_P2_MAX && (n & (n - 1)) == 0; }
+
+static inline int thz_p2_row_lines_rt(int n) { return p2_row_lines(n); }
+static inline int thz_p2_row_threads_rt(int n) { return p2_row_threads(n); }
+static inline int thz_p2_col_cols_rt(int n) { return p2_col_cols(n); }
+static inline int thz_p2_col_threads_rt(int n) { return p2_col_threads(n); }
+
+// Switch the launch geometry of the axes that the power-of-two fast path serves (THZ_NO_P2=1 disables it).
+static inline void thz_asm_apply_p2(const thz_asm_desc* d, int nbc, int sm_count, AsmLaunch* L) {
+    const char* off = getenv("THZ_NO_P2");
+    const bool enabled = !(off && off[0] == '1');
+    L->p2_w = enabled && thz_is_p2_size(d->Wp);
+    L->p2_h = enabled && thz_is_p2_size(d->Hp);
+    if (L->p2_w) {
+        const int lines = thz_p2_row_lines_rt(d->Wp), threads = thz_p2_row_threads_rt(d->Wp);
+        const size_t smem = (size_t)lines * (d->Wp + (d->Wp >> 4)) * sizeof(cpx);
+        L->k1.lines = lines;
+        L->k1_threads = threads;
+        L->k1_grid = (nbc * d->inH + lines - 1) / lines;
+        L->k1_smem = smem;
+        L->k3.lines = lines;
+        L->k3_threads = threads;
+        L->k3_gridx = (d->outH + lines - 1) / lines;
+        int gy = 1;
+        while (gy < nbc && (long)L->k3_gridx * gy < 4L * sm_count) gy <<= 1;
+        gy = thz_imin(gy, nbc);
+        L->k3.bc_per_cta = (nbc + gy - 1) / gy;
+        L->k3_gridy = (nbc + L->k3.bc_per_cta - 1) / L->k3.bc_per_cta;
+        L->k3_smem = smem;
+    }
+    if (L->p2_h) {
+        const int cols = thz_p2_col_cols_rt(d->Hp);
+        L->k2.cols = cols;
+        L->k2_gridx = (d->Wp + cols - 1) / cols;
+        L->k2_threads = thz_p2_col_threads_rt(d->Hp);
+        L->k2_smem = (size_t)cols * (d->Hp + (d->Hp >> 4)) * sizeof(cpx);
+    }
 }
 
 // Build the three kernels' arguments for the chunk of fields [f0, f0+nbc).
@@ -170,5 +212,6 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k3_gridy = (nbc + a3.bc_per_cta - 1) / a3.bc_per_cta;
         L->k3_smem = lines * line_bytes_w;
     }
+    thz_asm_apply_p2(d, nbc, sm_count, L);
     return THZ_OK;
 }

@@ -1,0 +1,134 @@
+// __global__ wrappers and size dispatch of the power-of-two fast path (bodies: thz_asm_p2.cuh).
+#include "thz_asm_host.h"
+#include "thz_asm_p2_launch.h"
+#include "thz_runtime.h"
+
+// ------------------------------------------------------------------------------- stage recursion with barriers
+template <int N, int S, int S1, int LINES>
+__device__ __forceinline__ void fwd_rows(cpx* s, int tid, int nt, const cpx* tw) {
+    if constexpr (S < S1) {
+        p2_stage_rows<N, S, false, LINES>(s, tid, nt, tw);
+        __syncthreads();
+        fwd_rows<N, S + 1, S1, LINES>(s, tid, nt, tw);
+    }
+}
+template <int N, int S, int S0, int LINES>
+__device__ __forceinline__ void inv_rows(cpx* s, int tid, int nt, const cpx* tw) {   // stages S, S-1, ..., S0
+    if constexpr (S >= S0) {
+        p2_stage_rows<N, S, true, LINES>(s, tid, nt, tw);
+        __syncthreads();
+        inv_rows<N, S - 1, S0, LINES>(s, tid, nt, tw);
+    }
+}
+template <int N, int S, int S1, int COLS>
+__device__ __forceinline__ void fwd_cols(cpx* s, int tid, int nt, const cpx* tw) {
+    if constexpr (S < S1) {
+        p2_stage_cols<N, S, false, COLS>(s, tid, nt, tw);
+        __syncthreads();
+        fwd_cols<N, S + 1, S1, COLS>(s, tid, nt, tw);
+    }
+}
+template <int N, int S, int S0, int COLS>
+__device__ __forceinline__ void inv_cols(cpx* s, int tid, int nt, const cpx* tw) {
+    if constexpr (S >= S0) {
+        p2_stage_cols<N, S, true, COLS>(s, tid, nt, tw);
+        __syncthreads();
+        inv_cols<N, S - 1, S0, COLS>(s, tid, nt, tw);
+    }
+}
+
+// ------------------------------------------------------------------------------- kernels
+template <int N>
+__global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k1(const __grid_constant__ RowFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx* s = reinterpret_cast<cpx*>(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x;
+    p2k1_first<N>(a, s, bx, tid, nt);
+    __syncthreads();
+    fwd_rows<N, 1, p2_stages(N), p2_row_lines(N)>(s, tid, nt, a.tw);
+    p2k1_store<N>(a, s, bx, tid, nt);
+}
+
+template <int N>
+__global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k2(const __grid_constant__ ColArgs a) {
+    constexpr int COLS = p2_col_cols(N), NS = p2_stages(N);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx* s = reinterpret_cast<cpx*>(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x, by = blockIdx.y;
+    p2k2_first<N, COLS>(a, s, bx, by, tid, nt);
+    __syncthreads();
+    fwd_cols<N, 1, NS - 1, COLS>(s, tid, nt, a.tw);
+    p2k2_middle<N, COLS>(a, s, bx, by, tid, nt);
+    __syncthreads();
+    inv_cols<N, NS - 2, 1, COLS>(s, tid, nt, a.tw);
+    p2k2_last<N, COLS>(a, s, bx, by, tid, nt);
+}
+
+template <int N>
+__global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k3(const __grid_constant__ RowInvArgs a) {
+    constexpr int NACC = p2k3_acc<N>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx* s = reinterpret_cast<cpx*>(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    const int f_lo = blockIdx.y * a.bc_per_cta;
+    const int f_hi = min(a.nbc, f_lo + a.bc_per_cta);
+    for (int f = f_lo; f < f_hi; ++f) {
+        p2k3_load<N>(a, s, bx, f, tid, nt);
+        __syncthreads();
+        inv_rows<N, p2_stages(N) - 1, 1, p2_row_lines(N)>(s, tid, nt, a.tw);
+        p2k3_last<N, NACC>(a, s, bx, f, tid, nt, acc);
+        __syncthreads();
+    }
+    p2k3_flush<N, NACC>(a, bx, tid, nt, acc);
+}
+
+// ------------------------------------------------------------------------------- dispatch
+template <typename K>
+static int set_smem_p2(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return THZ_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return thz_set_cuda_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
+    return THZ_OK;
+}
+
+#define THZ_P2_CASE(KERN, NN, cls, grid, block, smem, stream, args)                      \
+    case NN: {                                                                           \
+        int rc_ = set_smem_p2(KERN<NN>, smem);                                           \
+        if (rc_ != THZ_OK) return rc_;                                                   \
+        thz_launch_begin(stream, cls);                                                   \
+        KERN<NN><<<grid, block, smem, stream>>>(args);                                   \
+        thz_launch_end(stream, cls);                                                     \
+        break;                                                                           \
+    }
+#define THZ_P2_SWITCH(KERN, n, cls, grid, block, smem, stream, args)                     \
+    switch (n) {                                                                         \
+        THZ_P2_CASE(KERN, 256, cls, grid, block, smem, stream, args)                     \
+        THZ_P2_CASE(KERN, 512, cls, grid, block, smem, stream, args)                     \
+        THZ_P2_CASE(KERN, 1024, cls, grid, block, smem, stream, args)                    \
+        THZ_P2_CASE(KERN, 2048, cls, grid, block, smem, stream, args)                    \
+        THZ_P2_CASE(KERN, 4096, cls, grid, block, smem, stream, args)                    \
+        THZ_P2_CASE(KERN, 8192, cls, grid, block, smem, stream, args)                    \
+        THZ_P2_CASE(KERN, 16384, cls, grid, block, smem, stream, args)                   \
+    default:                                                                             \
+        return thz_set_error(THZ_E_UNSUPPORTED, "power-of-two fast path: size not instantiated"); \
+    }                                                                                    \
+    {                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                             \
+        if (e_ != cudaSuccess) return thz_set_cuda_error(#KERN, e_);                     \
+    }
+
+int thz_p2_launch_k1(const RowFwdArgs& a, int grid, int threads, size_t smem, cudaStream_t stream) {
+    THZ_P2_SWITCH(thz_p2_k1, a.Wp, THZ_KC_ROW_FWD, grid, threads, smem, stream, a)
+    return THZ_OK;
+}
+int thz_p2_launch_k2(const ColArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream) {
+    THZ_P2_SWITCH(thz_p2_k2, a.Hp, THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a)
+    return THZ_OK;
+}
+int thz_p2_launch_k3(const RowInvArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream) {
+    THZ_P2_SWITCH(thz_p2_k3, a.Wp, THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a)
+    return THZ_OK;
+}

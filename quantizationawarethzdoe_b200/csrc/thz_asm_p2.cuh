@@ -1,0 +1,271 @@
+// Power-of-two fast path of the fused ASM pipeline: the same three kernels as thz_asm.cuh (same
+// argument structs, same T layout, same results), with the transform length a template parameter and
+// the first / last FFT stage of each kernel fused with its global-memory traffic:
+//
+//   K1<N>       x row --[DOE phase]--> registers -> stage 0 -> smem -> stages 1.. -> smem -> T row
+//   K2<N,COLS>  T column tile -> registers -> stage 0 -> smem -> ... -> (last stage . H . last stage^-1)
+//               -> ... -> inverse stage 0 -> registers -> cropped rows of T
+//   K3<N>       T row -> smem -> inverse stages ..1 -> inverse stage 0 -> registers -> crop/scale/epilogue -> y
+//
+// Every phase is a per-thread function; the __global__ wrappers (thz_asm_p2.cu) and the CPU replay
+// (tests/emul) put the barriers between them.
+#pragma once
+#include "thz_asm.cuh"
+#include "thz_fft_p2.cuh"
+
+#define THZ_P2_MIN 256
+#define THZ_P2_MAX 16384
+
+THZ_HD constexpr int p2_row_lines(int N) { return N >= 4096 ? 1 : 4096 / N; }        // lines per CTA, row kernels
+THZ_HD constexpr int p2_row_threads(int N) { return N >= 8192 ? 512 : 256; }
+THZ_HD constexpr int p2_col_cols(int N) { return N >= 16384 ? 1 : (N >= 4096 ? 2 : (N >= 2048 ? 4 : (N >= 1024 ? 8 : 16))); }
+THZ_HD constexpr int p2_col_threads(int N) { return N >= 8192 ? 512 : 256; }
+THZ_HD constexpr int p2_pitch(int N) { return N + (N >> 4); }
+
+// =============================================================================== K1<N>
+struct K1Loader {
+    const cpx* xr;      // row of x (NULL: line beyond the end of the batch)
+    const float* hr;    // row of the height map (NULL: no DOE)
+    float4 cf;
+    float base;
+    int in_c0, inW, conj_in;
+    THZ_HD cpx operator()(int pos) const {
+        const int c = pos - in_c0;
+        if (xr == nullptr || c < 0 || c >= inW) return cmake(0.f, 0.f);
+        cpx v = xr[c];
+        if (conj_in) v.y = -v.y;
+        if (hr) v = cmul(v, thz_doe_phase(thz_ldg(hr + c), cf, base));
+        return v;
+    }
+};
+
+template <int N>
+THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
+    constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N);
+    const int total_lines = a.nbc * a.inH;
+    for (int w = tid; w < LINES * NB; w += nt) {
+        const int line = w / NB, j = w % NB;
+        const int gl = bx * LINES + line;
+        K1Loader ld;
+        ld.xr = nullptr;
+        ld.hr = nullptr;
+        ld.cf = cmake4(0.f);
+        ld.base = a.doe.base;
+        ld.in_c0 = a.in_c0;
+        ld.inW = a.inW;
+        ld.conj_in = a.conj_in;
+        if (gl < total_lines) {
+            const int f = gl / a.inH, r = gl - f * a.inH;
+            ld.xr = a.x + (size_t)gl * a.inW;
+            if (a.doe.hmap) {
+                ld.cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
+                ld.hr = a.doe.hmap + (size_t)r * a.inW;
+            }
+        }
+        p2_first_stage_from<N, 1>(s + line * PITCH, j, a.tw, ld);
+    }
+}
+
+template <int N>
+THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int nt) {
+    constexpr int LINES = p2_row_lines(N), PITCH = p2_pitch(N);
+    const int total_lines = a.nbc * a.inH;
+#pragma unroll
+    for (int l = 0; l < LINES; ++l) {
+        const int gl = bx * LINES + l;
+        if (gl >= total_lines) break;
+        const int f = gl / a.inH, r = gl - f * a.inH;
+        cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
+        const cpx* sl = s + l * PITCH;
+        for (int p = tid; p < N; p += nt) tr[p] = sl[p + (p >> 4)];
+    }
+}
+
+// =============================================================================== K2<N, COLS>
+struct K2Loader {
+    const cpx* col;     // T + field offset + column (NULL if the column is outside the grid)
+    int in_r0, inH, Wp;
+    THZ_HD cpx operator()(int pos) const {
+        const int r = pos - in_r0;
+        if (col == nullptr || r < 0 || r >= inH) return cmake(0.f, 0.f);
+        return col[(size_t)r * Wp];
+    }
+};
+struct K2Storer {
+    cpx* col;
+    int out_r0, outH, Wp;
+    THZ_HD void operator()(int pos, int, cpx v) const {
+        const int r = pos - out_r0;
+        if (col != nullptr && r >= 0 && r < outH) col[(size_t)r * Wp] = v;
+    }
+};
+
+template <int N, int COLS>
+THZ_HD void p2k2_first(const ColArgs& a, cpx* s, int bx, int by, int tid, int nt) {
+    constexpr int NB = P2Stage<N, 0>::NB;
+    for (int w = tid; w < COLS * NB; w += nt) {
+        const int j = w / COLS, l = w % COLS;
+        const int c = bx * COLS + l;
+        K2Loader ld;
+        ld.col = c < a.Wp ? a.T + (size_t)by * a.rowsT * a.Wp + c : nullptr;
+        ld.in_r0 = a.in_r0;
+        ld.inH = a.inH;
+        ld.Wp = a.Wp;
+        p2_first_stage_from<N, COLS>(s + l, j, a.tw, ld);
+    }
+}
+
+// last forward stage . H . first inverse stage, in registers (see thz_asm.cuh k2_middle_butterfly)
+template <int N, int COLS>
+THZ_HD void p2k2_middle(const ColArgs& a, cpx* s, int bx, int by, int tid, int nt) {
+    constexpr int S = p2_stages(N) - 1;
+    typedef P2Stage<N, S> St;
+    constexpr int R = St::R, NB = St::NB;
+    static_assert(St::M == 1, "last stage has unit sub-blocks");
+    // the column (hence its bin and its column-vector entry) is fixed per thread when nt % COLS == 0
+    const int c_chan = (a.c0 + by) % a.C;
+    for (int w = tid; w < COLS * NB; w += nt) {
+        const int u = w / COLS, l = w % COLS;
+        const int col = bx * COLS + l;
+        const int p0 = u * R;
+        cpx* p = s + (p0 + (p0 >> 4)) * COLS + l;
+        cpx v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = p[t * COLS];
+        Dft<R, false>::run(v);
+        if (a.tf.mode != 2 && col < a.Wp) {
+            if (a.tf.mode == 0) {
+                const int binc = thz_pos_to_bin(a.planW, col);
+                const float4 cv = thz_ldg(a.tf.colvec + (size_t)c_chan * a.Wp + binc);
+                const float2 sc = thz_ldg(a.tf.scal + c_chan);
+                const float4* rvp = a.tf.rowvec + (size_t)c_chan * N + p2_bin_of_slot<N>(p0);
+#pragma unroll
+                for (int q = 0; q < R; ++q) v[q] = cmul(v[q], thz_tf_value(thz_ldg(rvp + q * St::WT), cv, sc, a.tf.conj));
+            } else {
+                const cpx* tp = a.tf.table + ((size_t)c_chan * N + p0) * a.Wp + col;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const cpx h = thz_ldg(tp + (size_t)q * a.Wp);
+                    v[q] = a.tf.conj ? cmulc(v[q], h) : cmul(v[q], h);
+                }
+            }
+        }
+        Dft<R, true>::run(v);
+#pragma unroll
+        for (int t = 0; t < R; ++t) p[t * COLS] = v[t];
+    }
+}
+
+template <int N, int COLS>
+THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, int bx, int by, int tid, int nt) {
+    constexpr int NB = P2Stage<N, 0>::NB;
+    for (int w = tid; w < COLS * NB; w += nt) {
+        const int j = w / COLS, l = w % COLS;
+        const int c = bx * COLS + l;
+        K2Storer st;
+        st.col = c < a.Wp ? a.T + (size_t)by * a.rowsT * a.Wp + c : nullptr;
+        st.out_r0 = a.out_r0;
+        st.outH = a.outH;
+        st.Wp = a.Wp;
+        p2_last_inverse_stage_to<N, COLS>(s + l, j, a.tw, st);
+    }
+}
+
+// =============================================================================== K3<N>
+template <int N>
+THZ_HD void p2k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nt) {
+    constexpr int LINES = p2_row_lines(N), PITCH = p2_pitch(N);
+#pragma unroll
+    for (int l = 0; l < LINES; ++l) {
+        const int r = bx * LINES + l;
+        if (r >= a.outH) break;
+        const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
+        cpx* sl = s + l * PITCH;
+        for (int p = tid; p < N; p += nt) sl[p + (p >> 4)] = tr[p];
+    }
+}
+
+// number of register accumulators a thread needs: one per output of each of its stage-0 butterflies
+template <int N>
+THZ_HD constexpr int p2k3_acc() {
+    return ((p2_row_lines(N) * P2Stage<N, 0>::NB + p2_row_threads(N) - 1) / p2_row_threads(N)) * P2Stage<N, 0>::R;
+}
+
+struct K3Storer {
+    cpx* yrow;            // output row (forward output or grad wrt field; may be NULL in DOE mode)
+    const cpx* xrow;      // saved input row (DOE mode)
+    const float* hrow;    // height-map row (DOE mode; NULL = plain forward)
+    float4 cf;
+    cpx gamma;
+    float base, scale;
+    int out_c0, outW;
+    float* acc;           // this butterfly's R accumulators
+    THZ_HD void operator()(int pos, int t, cpx v) const {
+        const int c = pos - out_c0;
+        if (c < 0 || c >= outW) return;
+        v = cscale(v, scale);
+        if (hrow == nullptr) {
+            yrow[c] = v;
+            return;
+        }
+        const cpx p = thz_doe_phase(thz_ldg(hrow + c), cf, base);
+        if (yrow) yrow[c] = cmulc(v, p);
+        const cpx xp = cmul(cmul(xrow[c], p), gamma);
+        acc[t] += v.x * xp.x + v.y * xp.y;
+    }
+};
+
+// inverse stage 0 + crop + scale + epilogue for field f; acc has p2k3_acc<N>() entries
+template <int N, int NACC>
+THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, int bx, int f, int tid, int nt, float (&acc)[NACC]) {
+    constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N), R = P2Stage<N, 0>::R;
+    K3Storer st;
+    st.cf = cmake4(0.f);
+    st.gamma = cmake(0.f, 0.f);
+    if (a.doe.hmap) {
+        st.cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
+        st.gamma = cmake(-st.cf.x * (0.5f * st.cf.y * st.cf.z), -st.cf.x * st.cf.w);
+    }
+    st.base = a.doe.base;
+    st.scale = a.scale;
+    st.out_c0 = a.out_c0;
+    st.outW = a.outW;
+    int k = 0;
+#pragma unroll
+    for (int w0 = 0; w0 < LINES * NB; w0 += p2_row_threads(N), ++k) {
+        const int w = w0 + tid;
+        if (w >= LINES * NB) break;
+        const int line = w / NB, j = w % NB;
+        const int r = bx * LINES + line;
+        if (r >= a.outH) break;
+        const size_t o = ((size_t)f * a.outH + r) * a.outW;
+        st.yrow = a.y ? a.y + o : nullptr;
+        st.xrow = a.xsaved ? a.xsaved + o : nullptr;
+        st.hrow = a.doe.hmap ? a.doe.hmap + (size_t)r * a.outW : nullptr;
+        st.acc = &acc[k * R];
+        p2_last_inverse_stage_to<N, 1>(s + line * PITCH, j, a.tw, st);
+    }
+}
+
+template <int N, int NACC>
+THZ_HD void p2k3_flush(const RowInvArgs& a, int bx, int tid, int nt, const float (&acc)[NACC]) {
+    if (!a.doe.hmap) return;
+    constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, R = P2Stage<N, 0>::R, M = P2Stage<N, 0>::M;
+    int k = 0;
+#pragma unroll
+    for (int w0 = 0; w0 < LINES * NB; w0 += p2_row_threads(N), ++k) {
+        const int w = w0 + tid;
+        if (w >= LINES * NB) break;
+        const int line = w / NB, j = w % NB;
+        const int r = bx * LINES + line;
+        if (r >= a.outH) break;
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const int c = j + t * M - a.out_c0;
+            if (c < 0 || c >= a.outW) continue;
+            float* g = a.gh + (size_t)r * a.outW + c;
+            if (a.gh_atomic) thz_atomic_add(g, acc[k * R + t]);
+            else *g = acc[k * R + t];
+        }
+    }
+}

@@ -182,9 +182,9 @@ extern "C" int thz_doe_modulate_bwd(const void* g, const void* x, const void* hm
 
 extern "C" int thz_quant_ste_fwd(const void* in, int32_t from_weights, float hmax, float clampv, const void* lut, int32_t L,
                                  void* q, void* idx, void* h_pre, uint64_t n, void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!in || !lut || !q) return thz_set_error(THZ_E_NULL, "thz_quant_ste_fwd: null pointer");
     if (L < 1 || L > THZ_MAX_LEVELS) return thz_set_error(THZ_E_SHAPE, "thz_quant_ste_fwd: 1 <= levels <= 64");
-    if (n == 0) return THZ_OK;
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
     thz_k_ste_fwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float*)in, from_weights, hmax, clampv, (const float*)lut,
                                                                  L, (float*)q, (int32_t*)idx, (float*)h_pre, n);
@@ -194,8 +194,8 @@ extern "C" int thz_quant_ste_fwd(const void* in, int32_t from_weights, float hma
 }
 
 extern "C" int thz_height_fwd(const void* w, float hmax, float clampv, void* h, uint64_t n, void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!w || !h) return thz_set_error(THZ_E_NULL, "thz_height_fwd: null pointer");
-    if (n == 0) return THZ_OK;
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
     thz_k_height_fwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float*)w, hmax, clampv, (float*)h, n);
     thz_launch_end((cudaStream_t)stream, THZ_KC_QUANT);
@@ -204,8 +204,8 @@ extern "C" int thz_height_fwd(const void* w, float hmax, float clampv, void* h, 
 }
 
 extern "C" int thz_height_bwd(const void* g, const void* w, float hmax, float clampv, void* gw, uint64_t n, void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!g || !w || !gw) return thz_set_error(THZ_E_NULL, "thz_height_bwd: null pointer");
-    if (n == 0) return THZ_OK;
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
     thz_k_height_bwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float*)g, (const float*)w, hmax, clampv, (float*)gw, n);
     thz_launch_end((cudaStream_t)stream, THZ_KC_QUANT);
@@ -215,10 +215,10 @@ extern "C" int thz_height_bwd(const void* g, const void* w, float hmax, float cl
 
 extern "C" int thz_quant_nn_fwd(const void* x, const void* lut, int32_t nlut, const void* mid, int32_t nmid, void* q, void* idx,
                                 uint64_t n, void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!x || !lut || !mid || !q || !idx) return thz_set_error(THZ_E_NULL, "thz_quant_nn_fwd: null pointer");
     if (nlut < 1 || nlut > THZ_MAX_LEVELS + 1 || nmid < 1 || nmid > THZ_MAX_LEVELS || nmid >= nlut + 1)
         return thz_set_error(THZ_E_SHAPE, "thz_quant_nn_fwd: bad lut sizes");
-    if (n == 0) return THZ_OK;
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
     thz_k_nn_fwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)lut, nlut, (const float*)mid, nmid,
                                                                 (float*)q, (int32_t*)idx, n);
@@ -229,9 +229,9 @@ extern "C" int thz_quant_nn_fwd(const void* x, const void* lut, int32_t nlut, co
 
 extern "C" int thz_quant_nn_bwd(const void* g, const void* x, const void* idx, const void* lut, int32_t nlut, float s,
                                 int32_t kind, void* gx, uint64_t n, void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!g || !x || !idx || !lut || !gx) return thz_set_error(THZ_E_NULL, "thz_quant_nn_bwd: null pointer");
     if (nlut < 1 || nlut > THZ_MAX_LEVELS + 1 || kind < 0 || kind > 2) return thz_set_error(THZ_E_SHAPE, "thz_quant_nn_bwd: bad arguments");
-    if (n == 0) return THZ_OK;
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
     thz_k_nn_bwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float*)g, (const float*)x, (const int32_t*)idx,
                                                                 (const float*)lut, nlut, s, kind, (float*)gx, n);
@@ -242,9 +242,9 @@ extern "C" int thz_quant_nn_bwd(const void* g, const void* x, const void* idx, c
 
 extern "C" int thz_quant_psq_fwd(const void* w, float hmax, int32_t L, float tau, void* out, void* dout_dw, uint64_t n,
                                  void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!w || !out) return thz_set_error(THZ_E_NULL, "thz_quant_psq_fwd: null pointer");
     if (L < 2) return thz_set_error(THZ_E_SHAPE, "thz_quant_psq_fwd: levels >= 2");
-    if (n == 0) return THZ_OK;
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
     thz_k_psq_fwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float*)w, hmax, L, tau, (float*)out, (float*)dout_dw, n);
     thz_launch_end((cudaStream_t)stream, THZ_KC_QUANT);
@@ -255,9 +255,9 @@ extern "C" int thz_quant_psq_fwd(const void* w, float hmax, int32_t L, float tau
 extern "C" int thz_quant_gumbel_v3_fwd(const void* w, const void* lut, int32_t L, const void* noise, float hmax, float kfac,
                                        float c_s, float tau, float tau_max, float s, float beta, float one_minus_beta,
                                        int32_t phase_input, void* h_out, void* idx, void* dh_dw, uint64_t n, void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!w || !lut || !noise || !h_out) return thz_set_error(THZ_E_NULL, "thz_quant_gumbel_v3_fwd: null pointer");
     if (L < 1 || L > THZ_MAX_LEVELS) return thz_set_error(THZ_E_SHAPE, "thz_quant_gumbel_v3_fwd: 1 <= levels <= 64");
-    if (n == 0) return THZ_OK;
     GumbelV3Params P;
     P.hmax = hmax;
     P.kfac = kfac;
@@ -279,9 +279,9 @@ extern "C" int thz_quant_gumbel_v3_fwd(const void* w, const void* lut, int32_t L
 
 extern "C" int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise, const void* lut, int32_t L, float tau, void* q,
                                           void* idx, void* dq, uint64_t n, void* stream) {
+    if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!logits || !noise || !lut || !q) return thz_set_error(THZ_E_NULL, "thz_quant_gumbel_naive_fwd: null pointer");
     if (L < 1 || L > THZ_MAX_LEVELS) return thz_set_error(THZ_E_SHAPE, "thz_quant_gumbel_naive_fwd: 1 <= levels <= 64");
-    if (n == 0) return THZ_OK;
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
     thz_k_gumbel_naive_fwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float*)logits, (const float*)noise,
                                                                           (const float*)lut, L, tau, (float*)q, (int32_t*)idx,

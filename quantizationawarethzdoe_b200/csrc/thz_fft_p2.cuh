@@ -1,0 +1,148 @@
+// Compile-time specialised power-of-two FFT stages (fast path for N = 256 ... 16384).
+//
+// Same algorithm and the same shared-memory layout as thz_fft.cuh (in-place DIF forward / DIT inverse,
+// digit-reversed spectra, one padding slot per 16), but the line length N is a template parameter, so
+//   * radices, strides and twiddle steps are constants: a butterfly addresses its R slots as
+//     base + immediate offsets (no per-element index arithmetic, no integer divisions);
+//   * the first forward stage can take its inputs straight from global memory and the last inverse
+//     stage can hand its outputs straight to global memory (functor arguments), which removes one
+//     shared-memory round trip and one barrier at each end of a kernel.
+// The ncu profile of the generic engine showed ~38 % of executed instructions to be integer/index work
+// (profiles/r01_*): this file exists to get rid of them.  thz_make_plan() (host) and p2_pick() (here)
+// must agree on the factorisation; tests/emul checks that.
+#pragma once
+#include "thz_fft.cuh"
+
+// ---------------------------------------------------------------- compile-time plan (mirrors thz_make_plan)
+THZ_HD constexpr int p2_pick(int rem) {
+    return (rem >= 256 || rem == 16) ? 16 : (rem == 128 ? 16 : (rem == 64 ? 8 : (rem == 32 ? 8 : rem)));
+}
+THZ_HD constexpr int p2_L(int N, int s) {   // block length entering stage s
+    int rem = N;
+    for (int i = 0; i < s; ++i) rem /= p2_pick(rem);
+    return rem;
+}
+THZ_HD constexpr int p2_radix(int N, int s) { return p2_L(N, s) > 1 ? p2_pick(p2_L(N, s)) : 1; }
+THZ_HD constexpr int p2_stages(int N) {
+    int rem = N, k = 0;
+    while (rem > 1) {
+        rem /= p2_pick(rem);
+        ++k;
+    }
+    return k;
+}
+THZ_HD constexpr int p2_log2(int v) {
+    int k = 0;
+    while ((1 << k) < v) ++k;
+    return k;
+}
+// slot offset of element t of a butterfly with sub-block length M (relative to the slot of element 0)
+THZ_HD constexpr int p2_coff(int M, int t) { return t * M + ((t * M) >> 4); }
+
+template <int N, int S>
+struct P2Stage {
+    static constexpr int R = p2_radix(N, S);
+    static constexpr int L = p2_L(N, S);
+    static constexpr int M = L / R;
+    static constexpr int WT = N / L;      // twiddle table step and bin weight of this digit
+    static constexpr int NB = N / R;      // butterflies per line
+};
+
+// slot -> bin for a slot that is the first element of a last-stage butterfly (p0 = u * R_last):
+// digits of stage s < last are (p0 / M_s) % R_s.
+template <int N>
+THZ_HD int p2_bin_of_slot(int pos) {
+    int bin = 0;
+#pragma unroll
+    for (int s = 0; s < p2_stages(N); ++s) {
+        const int M = p2_L(N, s) / p2_radix(N, s);
+        const int q = (pos / M) % p2_radix(N, s);
+        bin += q * (N / p2_L(N, s));
+    }
+    return bin;
+}
+
+template <int R>
+THZ_HD void p2_apply_twiddles(cpx (&v)[R], cpx w1) {
+    cpx w[R];
+    twiddle_powers<R>(w1, w);
+#pragma unroll
+    for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+}
+
+// ---------------------------------------------------------------- in-shared-memory stage S, one butterfly
+//   base: pointer to slot 0 of this line (row-major, STRIDE = 1) or to column l of slot 0 (column tile,
+//   STRIDE = number of columns in the tile)
+template <int N, int S, bool INV, int STRIDE>
+THZ_HD void p2_butterfly(cpx* base, int u, const cpx* __restrict__ tw) {
+    typedef P2Stage<N, S> St;
+    constexpr int R = St::R, M = St::M, L = St::L;
+    const int b = u / M, j = u % M;       // M is a power of two: shift / mask
+    const int p0 = b * L + j;
+    cpx* p = base + (p0 + (p0 >> 4)) * STRIDE;
+    cpx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
+    if (!INV) {
+        Dft<R, false>::run(v);
+        if (M > 1) p2_apply_twiddles<R>(v, thz_ldg(tw + j * St::WT));
+    } else {
+        if (M > 1) p2_apply_twiddles<R>(v, cconj(thz_ldg(tw + j * St::WT)));
+        Dft<R, true>::run(v);
+    }
+#pragma unroll
+    for (int t = 0; t < R; ++t) p[p2_coff(M, t) * STRIDE] = v[t];
+}
+
+// ---------------------------------------------------------------- first forward stage, inputs from a functor
+//   load(pos) returns the input at logical position pos in [0, N).  Stage 0 has a single block (L = N), so
+//   butterfly j touches positions j + t*M.
+template <int N, int STRIDE, typename Load>
+THZ_HD void p2_first_stage_from(cpx* base, int j, const cpx* __restrict__ tw, Load load) {
+    typedef P2Stage<N, 0> St;
+    constexpr int R = St::R, M = St::M;
+    cpx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = load(j + t * M);
+    Dft<R, false>::run(v);
+    p2_apply_twiddles<R>(v, thz_ldg(tw + j));
+    cpx* p = base + (j + (j >> 4)) * STRIDE;
+#pragma unroll
+    for (int t = 0; t < R; ++t) p[p2_coff(M, t) * STRIDE] = v[t];
+}
+
+// ---------------------------------------------------------------- last inverse stage, outputs to a functor
+template <int N, int STRIDE, typename Store>
+THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* __restrict__ tw, Store store) {
+    typedef P2Stage<N, 0> St;
+    constexpr int R = St::R, M = St::M;
+    const cpx* p = base + (j + (j >> 4)) * STRIDE;
+    cpx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
+    p2_apply_twiddles<R>(v, cconj(thz_ldg(tw + j)));
+    Dft<R, true>::run(v);
+#pragma unroll
+    for (int t = 0; t < R; ++t) store(j + t * M, t, v[t]);
+}
+
+// ---------------------------------------------------------------- all butterflies of in-smem stage S
+//   ROWS: LINES lines of pitch PITCH slots (row kernels), work item w -> (line = w / NB, u = w % NB)
+template <int N, int S, bool INV, int LINES>
+THZ_HD void p2_stage_rows(cpx* s, int tid, int nthreads, const cpx* __restrict__ tw) {
+    constexpr int NB = P2Stage<N, S>::NB;
+    constexpr int PITCH = N + (N >> 4);
+    for (int w = tid; w < LINES * NB; w += nthreads) {
+        const int line = w / NB, u = w % NB;
+        p2_butterfly<N, S, INV, 1>(s + line * PITCH, u, tw);
+    }
+}
+//   COLUMN TILE: COLS lines interleaved (slot * COLS + l), work item w -> (u = w / COLS, l = w % COLS)
+template <int N, int S, bool INV, int COLS>
+THZ_HD void p2_stage_cols(cpx* s, int tid, int nthreads, const cpx* __restrict__ tw) {
+    constexpr int NB = P2Stage<N, S>::NB;
+    for (int w = tid; w < COLS * NB; w += nthreads) {
+        const int u = w / COLS, l = w % COLS;
+        p2_butterfly<N, S, INV, COLS>(s + l, u, tw);
+    }
+}

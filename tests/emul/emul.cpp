@@ -82,6 +82,93 @@ static void run_k2f(const ColFftArgs& a, int gx, int gy, int nt, size_t smem) {
         }
 }
 
+
+// ------------------------------------------------------------------------------- power-of-two fast path replay
+template <int N, int S, int S1, int LINES>
+static void e_fwd_rows(cpx* s, int nt, const cpx* tw) {
+    if constexpr (S < S1) {
+        for_threads(nt, [&](int t) { p2_stage_rows<N, S, false, LINES>(s, t, nt, tw); });
+        e_fwd_rows<N, S + 1, S1, LINES>(s, nt, tw);
+    }
+}
+template <int N, int S, int S0, int LINES>
+static void e_inv_rows(cpx* s, int nt, const cpx* tw) {
+    if constexpr (S >= S0) {
+        for_threads(nt, [&](int t) { p2_stage_rows<N, S, true, LINES>(s, t, nt, tw); });
+        e_inv_rows<N, S - 1, S0, LINES>(s, nt, tw);
+    }
+}
+template <int N, int S, int S1, int COLS>
+static void e_fwd_cols(cpx* s, int nt, const cpx* tw) {
+    if constexpr (S < S1) {
+        for_threads(nt, [&](int t) { p2_stage_cols<N, S, false, COLS>(s, t, nt, tw); });
+        e_fwd_cols<N, S + 1, S1, COLS>(s, nt, tw);
+    }
+}
+template <int N, int S, int S0, int COLS>
+static void e_inv_cols(cpx* s, int nt, const cpx* tw) {
+    if constexpr (S >= S0) {
+        for_threads(nt, [&](int t) { p2_stage_cols<N, S, true, COLS>(s, t, nt, tw); });
+        e_inv_cols<N, S - 1, S0, COLS>(s, nt, tw);
+    }
+}
+
+template <int N>
+static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
+    std::vector<unsigned char> buf(smem);
+    cpx* s = (cpx*)buf.data();
+    for (int bx = 0; bx < grid; ++bx) {
+        for_threads(nt, [&](int t) { p2k1_first<N>(a, s, bx, t, nt); });
+        e_fwd_rows<N, 1, p2_stages(N), p2_row_lines(N)>(s, nt, a.tw);
+        for_threads(nt, [&](int t) { p2k1_store<N>(a, s, bx, t, nt); });
+    }
+}
+template <int N>
+static void run_p2_k2(const ColArgs& a, int gx, int gy, int nt, size_t smem) {
+    constexpr int COLS = p2_col_cols(N), NS = p2_stages(N);
+    std::vector<unsigned char> buf(smem);
+    cpx* s = (cpx*)buf.data();
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            for_threads(nt, [&](int t) { p2k2_first<N, COLS>(a, s, bx, by, t, nt); });
+            e_fwd_cols<N, 1, NS - 1, COLS>(s, nt, a.tw);
+            for_threads(nt, [&](int t) { p2k2_middle<N, COLS>(a, s, bx, by, t, nt); });
+            e_inv_cols<N, NS - 2, 1, COLS>(s, nt, a.tw);
+            for_threads(nt, [&](int t) { p2k2_last<N, COLS>(a, s, bx, by, t, nt); });
+        }
+}
+template <int N>
+static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) {
+    constexpr int NACC = p2k3_acc<N>();
+    typedef float acc_t[NACC];
+    std::vector<unsigned char> buf(smem);
+    cpx* s = (cpx*)buf.data();
+    std::vector<float> accs((size_t)nt * NACC);
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            std::fill(accs.begin(), accs.end(), 0.f);
+            const int f_lo = by * a.bc_per_cta, f_hi = thz_imin(a.nbc, f_lo + a.bc_per_cta);
+            for (int f = f_lo; f < f_hi; ++f) {
+                for_threads(nt, [&](int t) { p2k3_load<N>(a, s, bx, f, t, nt); });
+                e_inv_rows<N, p2_stages(N) - 1, 1, p2_row_lines(N)>(s, nt, a.tw);
+                for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, s, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+            }
+            for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+        }
+}
+
+#define P2_DISPATCH(FN, n, ...)                      \
+    switch (n) {                                     \
+    case 256: FN<256>(__VA_ARGS__); break;           \
+    case 512: FN<512>(__VA_ARGS__); break;           \
+    case 1024: FN<1024>(__VA_ARGS__); break;         \
+    case 2048: FN<2048>(__VA_ARGS__); break;         \
+    case 4096: FN<4096>(__VA_ARGS__); break;         \
+    case 8192: FN<8192>(__VA_ARGS__); break;         \
+    case 16384: FN<16384>(__VA_ARGS__); break;       \
+    default: return THZ_E_UNSUPPORTED;               \
+    }
+
 extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
     int rc = thz_asm_validate(d);
     if (rc != THZ_OK) return rc;
@@ -100,11 +187,17 @@ extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
             memset(d->doe_gh, 0, (size_t)d->outH * d->outW * sizeof(float));
             zeroed = true;
         }
-        if (L.mixed_w) run_k1<true>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
+        if (L.p2_w) {
+            P2_DISPATCH(run_p2_k1, d->Wp, L.k1, L.k1_grid, L.k1_threads, L.k1_smem)
+        } else if (L.mixed_w) run_k1<true>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
         else run_k1<false>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
-        if (L.mixed_h) run_k2<true>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
+        if (L.p2_h) {
+            P2_DISPATCH(run_p2_k2, d->Hp, L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem)
+        } else if (L.mixed_h) run_k2<true>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
         else run_k2<false>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
-        if (L.mixed_w) run_k3<true>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
+        if (L.p2_w) {
+            P2_DISPATCH(run_p2_k3, d->Wp, L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem)
+        } else if (L.mixed_w) run_k3<true>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
         else run_k3<false>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
     }
     return THZ_OK;

@@ -53,6 +53,12 @@ CASES = [
     (1, 1, 200, 200, None, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                           # 400 = 25*16 (config 4 layer size)
     (1, 1, 256, 256, None, [1e-3], 0.5e-3, 0.1, {}),
     (1, 1, 7, 21, 2, [1e-3], 0.5e-3, 0.02, dict(mode=1)),                                # odd sizes: 21 x 63 (radix 7, 3)
+    # power-of-two fast path (compile-time specialised kernels, Hp/Wp in 256..16384)
+    (2, 2, 128, 128, None, [1e-3, 1.01e-3], 0.5e-3, 0.1, dict(mode=1)),                  # 256 x 256: two stages
+    (1, 1, 256, 512, None, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                           # 512 x 1024: three stages, 8-col tiles
+    (1, 1, 128, 1024, None, [1e-3], 0.5e-3, 0.1, {}),                                    # 256 x 2048, in-register H
+    (1, 1, 100, 128, None, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                           # mixed: generic rows (200) + p2 cols
+    (3, 1, 256, 256, None, [1e-3], 0.5e-3, 0.1, dict(mode=1, unpad=False, chunk=2)),     # 512 x 512 padded output, chunks
 ]
 
 
@@ -97,6 +103,9 @@ def test_in_register_mask_is_bit_exact():
     (2, 3, 48, 40, None, 1, 148, 4),      # gh accumulated across chunks (atomic path)
     (5, 1, 50, 50, 2, 1, 4, 0),           # few SMs: one CTA walks all five fields, register accumulators
     (1, 2, 64, 64, None, 0, 148, 0),
+    (3, 2, 128, 256, None, 1, 148, 0),    # power-of-two fast path: 256 x 512
+    (3, 2, 128, 256, None, 1, 2, 4),      # same, few SMs (one CTA walks several fields) and chunks (atomic gh)
+    (1, 1, 512, 128, None, 0, 148, 0),    # 1024 x 256
 ])
 def test_doe_fused_forward_and_adjoint_replay(B, C, H, W, scale, mode, sm, chunk):
     lams = [1e-3, 1.02e-3, 1.05e-3][:C]

@@ -234,7 +234,25 @@ def test_errors_cross_the_abi_as_python_exceptions(dev):
     from quantizationawarethzdoe_b200 import ASM_prop, ElectricField
     a = ASM_prop(z_distance=0.1, device=dev)
     a.check_Zc = False
-    with pytest.raises(NotImplementedError, match="prime factor"):
-        a(ElectricField(torch.zeros(1, 1, 13, 13, dtype=torch.complex64, device=dev), 1e-3, 1e-3, device=dev))
+    nopad = ASM_prop(z_distance=0.1, do_padding=False, device=dev)
+    nopad.check_Zc = False
+    with pytest.raises(NotImplementedError, match="prime factor"):     # 13 is not a supported radix
+        nopad(ElectricField(torch.zeros(1, 1, 13, 13, dtype=torch.complex64, device=dev), 1e-3, 1e-3, device=dev))
     with pytest.raises(TypeError, match="complex64"):
         a(ElectricField(torch.zeros(1, 1, 16, 16, dtype=torch.complex128, device=dev), 1e-3, 1e-3, device=dev))
+
+
+def test_power_of_two_fast_path_agrees_with_generic_engine(dev, monkeypatch):
+    """The compile-time specialised kernels and the runtime-planned engine must give the same field
+    (same algorithm, same twiddles): run both on one input (THZ_NO_P2=1 selects the generic engine)."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField
+    torch.manual_seed(5)
+    x = torch.randn(2, 2, 512, 1024, dtype=torch.complex64, device=dev)
+    lams = [1 * mm, 1.02 * mm]
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("THZ_NO_P2", flag)
+        a = ASM_prop(z_distance=0.1, device=dev)
+        a.check_Zc = False
+        outs.append(a(ElectricField(x, wavelengths=lams, spacing=0.5 * mm, device=dev)).data)
+    assert rel_l2(outs[0].cpu(), outs[1].cpu()) < 1e-6
