@@ -81,8 +81,11 @@ typedef struct thz_asm_desc {
     /* transfer function */
     int32_t tf_mode;           /* 0 separable vectors -> H in registers; 1 cached table; 2 identity        */
     int32_t tf_conj;           /* 1: multiply by conj(H) (adjoint)                                         */
-    const void* tf_rowvec;     /* float32 [C,Hp,4] {Kx^2, Kx^2/(2 pi u_lim)^2, Kx^2/klam^2, 0}, FFT-bin order */
-    const void* tf_colvec;     /* float32 [C,Wp,4] {Ky^2, Ky^2/klam^2, Ky^2/(2 pi v_lim)^2, 0}, FFT-bin order */
+    const void* tf_rowvec;     /* float32 [C,Hp,2] {Kx^2, tau} in slot order (thz_fft_slot_to_bin): bin (r,c) is kept
+                                  iff Ky^2[c] <= tau[r]; tau folds the evanescent cut and both band-limit
+                                  constraints (ASM_Prop.py:262,297-306), evaluated on the host in the reference's
+                                  fp32 op order, so the mask is bit-identical to the reference's               */
+    const void* tf_colvec;     /* float32 [C,Wp]   Ky^2 in slot order                                           */
     const void* tf_scal;       /* float32 [C,2]    {klam^2, z}                                             */
     const void* tf_table;      /* complex64 [C,Hp,Wp] in slot order (see thz_fft_slot_to_bin)              */
     /* DOE */

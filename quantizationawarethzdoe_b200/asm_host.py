@@ -112,6 +112,44 @@ def tf_vectors(Hp, Wp, spacing, wavelengths, z, bandlimit=True, bandlimit_type="
     return rowvec, colvec, scal
 
 
+def tf_row_thresholds(rowvec, colvec, scal, chunk_rows=512):
+    """Fold the per-bin keep conditions into one threshold per row (natural bin order in and out).
+
+    keep(r, c) = (rowvec.y[r] + colvec.y[c] <= 1) & (rowvec.z[r] + colvec.z[c] <= 1) & !(klam^2 - (Kx^2[r] + Ky^2[c]) < 0)
+    is, for a fixed row, monotone non-increasing in Ky^2[c]; tau[r] = the largest Ky^2 that is kept (-1 if none),
+    so that keep(r, c) == (Ky^2[c] <= tau[r]) exactly.  Returns tau [C,Hp] or None if monotonicity fails
+    (never observed; the caller then falls back to the cached-table mode)."""
+    C, Hp, _ = rowvec.shape
+    tau = torch.empty(C, Hp)
+    for c in range(C):
+        order = torch.argsort(colvec[c, :, 0], stable=True)
+        ky2 = colvec[c, order, 0]
+        b1, b2 = colvec[c, order, 1], colvec[c, order, 2]
+        for r0 in range(0, Hp, chunk_rows):
+            rv = rowvec[c, r0:r0 + chunk_rows]
+            keep = ((rv[:, None, 1] + b1[None, :]) <= 1) & ((rv[:, None, 2] + b2[None, :]) <= 1)
+            keep &= ~((scal[c, 0] - (rv[:, None, 0] + ky2[None, :])) < 0)
+            if bool((keep[:, 1:] & ~keep[:, :-1]).any()):
+                return None
+            cnt = keep.sum(dim=1)
+            t = ky2[(cnt - 1).clamp_min(0)]
+            tau[c, r0:r0 + chunk_rows] = torch.where(cnt > 0, t, torch.full_like(t, -1.0))
+    return tau
+
+
+def tf_device_vectors(rowvec, colvec, scal, slot_to_bin_fn=None):
+    """What the kernels consume (tf_mode 0): rowtau [C,Hp,2] = {Kx^2, tau} and colk2 [C,Wp] = Ky^2, both in the
+    plans' slot order, plus scal.  Returns None if the thresholds cannot be formed."""
+    tau = tf_row_thresholds(rowvec, colvec, scal)
+    if tau is None:
+        return None
+    pr = N.slot_to_bin(rowvec.shape[1], slot_to_bin_fn)
+    pc = N.slot_to_bin(colvec.shape[1], slot_to_bin_fn)
+    rowtau = torch.stack([rowvec[:, :, 0], tau], dim=2)[:, pr].contiguous()
+    colk2 = colvec[:, pc, 0].contiguous()
+    return rowtau, colk2, scal
+
+
 def tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, bandlimit=True, bandlimit_type="exact"):
     """Full centred transfer function [C,Hp,Wp] complex64 assembled on the host from the separable
     vectors with the same torch CPU ops the reference uses per pixel (sqrt, exp(1j .)), so that the

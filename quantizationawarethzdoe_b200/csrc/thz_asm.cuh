@@ -27,8 +27,8 @@ struct AsmGeom {
 struct TfArgs {
     int mode;                 // 0: generate H in registers from separable vectors; 1: cached table; 2: H == 1
     int conj;                 // 1: use conj(H) (adjoint / backward)
-    const float4* rowvec;     // [C][Hp] {Kx^2, Kx^2/lim_u^2, Kx^2/klam^2, 0}  natural bin order
-    const float4* colvec;     // [C][Wp] {Ky^2, Ky^2/klam^2, Ky^2/lim_v^2, 0}  natural bin order
+    const float2* rowvec;     // [C][Hp] {Kx^2, tau} in SLOT order: bin (r, c) is kept iff Ky^2[c] <= tau[r]
+    const float* colvec;      // [C][Wp] Ky^2 in SLOT order
     const float2* scal;       // [C]     {klam^2, z}
     const cpx* table;         // [C][Hp][Wp] in (slot_r, slot_c) scrambled layout (mode 1)
 };
@@ -51,15 +51,17 @@ THZ_HD cpx thz_doe_phase(float h, float4 cf, float base) {
     return cmake(a * cs, a * sn);
 }
 
-// Transfer function value for (row bin vector entry rv, column entry cv): Props/ASM_Prop.py:249-301.
-THZ_HD cpx thz_tf_value(float4 rv, float4 cv, float2 sc, int conj) {
-    const float K2 = thz_add_rn(rv.x, cv.x);
+// Transfer function value for row entry rv = {Kx^2, tau} and column entry ky2 (Props/ASM_Prop.py:249-301).
+// The evanescent cut (:262) and both band-limit constraints (:297-306) are monotone in Ky^2 for a fixed row,
+// so the host folds them, evaluated with the reference's exact fp32 expressions, into one threshold tau per
+// row: the kept set is exactly {Ky^2 <= tau}.  The phase follows the reference's rounding order.
+THZ_HD cpx thz_tf_value(float2 rv, float ky2, float2 sc, int conj) {
+    if (!(ky2 <= rv.y)) return cmake(0.f, 0.f);
+    const float K2 = thz_add_rn(rv.x, ky2);
     const float d = thz_sub_rn(sc.x, K2);
-    const bool keep = (thz_add_rn(rv.y, cv.y) <= 1.0f) && (thz_add_rn(rv.z, cv.z) <= 1.0f) && !(d < 0.0f);
-    if (!keep) return cmake(0.f, 0.f);
     const float ang = thz_mul_rn(sc.y, thz_sqrt_rn(d));
     float sn, cs;
-    thz_sincos(ang, &sn, &cs);
+    thz_sincos_fast(ang, &sn, &cs);
     return cmake(cs, conj ? -sn : sn);
 }
 
@@ -153,7 +155,6 @@ THZ_HD void k2_load(const ColArgs& a, cpx* s, int bx, int by, int tid, int nthre
 // forward's final butterfly and the DIT inverse's first butterfly touch the same R slots.
 template <int R>
 THZ_HD void k2_middle_butterfly(const ColArgs& a, cpx* s, int l, int u, int col, int f) {
-    const int st = a.plan.ns - 1;
     const int p0 = u * R;   // M == 1 in the last stage
     cpx v[R];
 #pragma unroll
@@ -162,14 +163,14 @@ THZ_HD void k2_middle_butterfly(const ColArgs& a, cpx* s, int l, int u, int col,
     if (a.tf.mode != 2 && col < a.Wp) {
         const int c = (a.c0 + f) % a.C;
         if (a.tf.mode == 0) {
-            const int binc = thz_pos_to_bin(a.planW, col);
-            const float4 cv = thz_ldg(a.tf.colvec + (size_t)c * a.Wp + binc);
+            const float cv = thz_ldg(a.tf.colvec + (size_t)c * a.Wp + col);
             const float2 sc = thz_ldg(a.tf.scal + c);
-            const int bin0 = thz_pos_to_bin(a.plan, p0);
-            const float4* rvp = a.tf.rowvec + (size_t)c * a.Hp + bin0;
-            const int wt = a.plan.wt[st];
+            const float2* rvp = a.tf.rowvec + (size_t)c * a.Hp + p0;
+            float2 rv[R];
 #pragma unroll
-            for (int q = 0; q < R; ++q) v[q] = cmul(v[q], thz_tf_value(thz_ldg(rvp + q * wt), cv, sc, a.tf.conj));
+            for (int q = 0; q < R; ++q) rv[q] = thz_ldg(rvp + q);
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[q] = cmul(v[q], thz_tf_value(rv[q], cv, sc, a.tf.conj));
         } else {
             const cpx* tp = a.tf.table + ((size_t)c * a.Hp + p0) * a.Wp + col;
 #pragma unroll

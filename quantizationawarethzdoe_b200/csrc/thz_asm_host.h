@@ -151,8 +151,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a2.tw = (const cpx*)d->tw_h;
     a2.tf.mode = d->tf_mode;
     a2.tf.conj = d->tf_conj;
-    a2.tf.rowvec = (const float4*)d->tf_rowvec;
-    a2.tf.colvec = (const float4*)d->tf_colvec;
+    a2.tf.rowvec = (const float2*)d->tf_rowvec;
+    a2.tf.colvec = (const float*)d->tf_colvec;
     a2.tf.scal = (const float2*)d->tf_scal;
     a2.tf.table = (const cpx*)d->tf_table;
     {

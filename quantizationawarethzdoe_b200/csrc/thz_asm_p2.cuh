@@ -130,17 +130,28 @@ THZ_HD void p2k2_middle(const ColArgs& a, cpx* s, int bx, int by, int tid, int n
         const int p0 = u * R;
         cpx* p = s + (p0 + (p0 >> 4)) * COLS + l;
         cpx v[R];
+        // issue the transfer-function loads first: the forward butterfly below hides their latency
+        const bool gen = a.tf.mode == 0 && col < a.Wp;
+        float4 rv4[R / 2];
+        float cv = 0.f;
+        float2 sc = cmake(0.f, 0.f);
+        if (gen) {
+            const float4* rvp = reinterpret_cast<const float4*>(a.tf.rowvec + (size_t)c_chan * N + p0);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) rv4[q] = thz_ldg(rvp + q);
+            cv = thz_ldg(a.tf.colvec + (size_t)c_chan * a.Wp + col);
+            sc = thz_ldg(a.tf.scal + c_chan);
+        }
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = p[t * COLS];
         Dft<R, false>::run(v);
         if (a.tf.mode != 2 && col < a.Wp) {
             if (a.tf.mode == 0) {
-                const int binc = thz_pos_to_bin(a.planW, col);
-                const float4 cv = thz_ldg(a.tf.colvec + (size_t)c_chan * a.Wp + binc);
-                const float2 sc = thz_ldg(a.tf.scal + c_chan);
-                const float4* rvp = a.tf.rowvec + (size_t)c_chan * N + p2_bin_of_slot<N>(p0);
 #pragma unroll
-                for (int q = 0; q < R; ++q) v[q] = cmul(v[q], thz_tf_value(thz_ldg(rvp + q * St::WT), cv, sc, a.tf.conj));
+                for (int q = 0; q < R / 2; ++q) {
+                    v[2 * q] = cmul(v[2 * q], thz_tf_value(cmake(rv4[q].x, rv4[q].y), cv, sc, a.tf.conj));
+                    v[2 * q + 1] = cmul(v[2 * q + 1], thz_tf_value(cmake(rv4[q].z, rv4[q].w), cv, sc, a.tf.conj));
+                }
             } else {
                 const cpx* tp = a.tf.table + ((size_t)c_chan * N + p0) * a.Wp + col;
 #pragma unroll

@@ -30,7 +30,7 @@ def _setup(B, C, H, W, scale, lams, dxy, z, bt="exact", do_pad=True, unpad=True,
     ps = AH.normalise_padding_scale(scale, do_pad)
     ph, pw, Hp, Wp = AH.compute_padding(H, W, ps, do_pad)
     outH, outW, or0, oc0 = (H, W, ph, pw) if (do_pad and unpad) else (Hp, Wp, 0, 0)
-    rv, cv, sc = AH.tf_vectors(Hp, Wp, dxy, lams, z, True, bt)
+    rv, cv, sc = AH.tf_device_vectors(*AH.tf_vectors(Hp, Wp, dxy, lams, z, True, bt), E.thz_emul_slot_to_bin)
     table = None
     if mode == 1:
         table = AH.tf_table_slot_order(AH.tf_centred_reference_order(Hp, Wp, dxy, lams, z, True, bt), E.thz_emul_slot_to_bin)
