@@ -103,7 +103,9 @@ typedef struct thz_asm_desc {
     int32_t bc_chunk;          /* fields processed per kernel group (0 = all); keeps T L2-resident          */
     int32_t tune_k2_cols;      /* 0 = auto; column-tile width override                                     */
     int32_t tune_lines;        /* 0 = auto; rows per CTA override for the row kernels                      */
-    int32_t reserved;
+    int32_t stages;            /* 0 = whole pipeline; else bit mask 1 = row FFT (x -> ws), 2 = column pass (ws in
+                                  place), 4 = row iFFT + epilogue (ws -> y): the slab-decomposed multi-GPU FFT runs
+                                  the three stages separately around its all-to-all transposes                 */
 } thz_asm_desc;
 
 uint64_t thz_asm_workspace_bytes(const thz_asm_desc* desc);
@@ -175,6 +177,36 @@ int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise, const void
 uint64_t thz_launch_count(void);
 int thz_profile_enable(int32_t on);
 int thz_profile_read(int32_t nclasses, float* ms_sum, int32_t* count);
+
+/* ---------------------------------------------------------------------------------------------
+ * thz_toeplitz_gemm -- one separable pass of the chirp-z (Bluestein) propagator as a batched complex
+ * GEMM whose left operand is a Toeplitz matrix expanded on the fly from the chirp filter.
+ *
+ * Replaces CZT_prop.Bluestein_method + compute_fft (Props/CZT_Prop.py:132-225) for one axis, the
+ * field * F product (:238) as `pro`, and the F0 * U * z dx dy lambda product (:248) as `epi`;
+ * the adjoint passes use the same entry point with conj_* = 1 and the Toeplitz steps swapped.
+ *
+ *   C[b](m,n) = epi[b](m,n) * sum_k T[b](m,k) * ( pro[b](k,n) * B[b](k,n) ),
+ *   T[b](m,k) = g[b][ (off + sm*m + sk*k) mod L ]   (conjugated if conj_g)
+ *
+ * All operands complex64.  B / pro are addressed as base + b*sb_b + k*sb_k + n*sb_n (elements),
+ * C / epi as base + b*sc_b + m*sc_m + n*sc_n, so either orientation of either operand works without
+ * a transposition pass.  pro and epi may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct thz_toeplitz_gemm_desc {
+    int32_t batch, M, N, K;
+    const void* g;             /* complex64 [batch, L] chirp filter (1/h zero-extended to np2, CZT_Prop.py:161) */
+    int32_t L, off, sm, sk;    /* Toeplitz index = (off + sm*m + sk*k) mod L, sm, sk in {+1, -1}              */
+    int32_t conj_g, conj_pro, conj_epi, reserved;
+    const void* B;
+    int64_t sb_b, sb_k, sb_n;
+    const void* pro;
+    void* C;
+    int64_t sc_b, sc_m, sc_n;
+    const void* epi;
+} thz_toeplitz_gemm_desc;
+
+int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* desc, void* stream);
 
 #ifdef __cplusplus
 }

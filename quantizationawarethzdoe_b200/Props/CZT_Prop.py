@@ -1,0 +1,67 @@
+"""Chirp-z (Bluestein) zoomed Rayleigh-Sommerfeld propagation -- drop-in for Props/CZT_Prop.py.
+
+Same constructor and forward(field, outputHeight, outputWidth, outputPixel_dx, outputPixel_dy) ->
+ElectricField surface as the reference (Props/CZT_Prop.py:13-16, 252-314), same `z` property, same
+output spacing [dx_out, dy_out] (:308-312), without the reference's debug prints (:167-176, :217).
+The two Bluestein passes run as batched Toeplitz complex GEMMs on the GPU (thz_toeplitz_gemm); the
+chirp vectors and the two Rayleigh-Sommerfeld factor tables are built once per geometry on the host
+with the reference's own fp32 expressions (czt_host.py), which is what parity with the reference needs.
+Gradients flow to the input field through the explicit adjoint GEMMs.
+"""
+import torch
+import torch.nn as nn
+
+from .. import czt_host as CH
+from .. import functional as Fn
+from ..DataType.ElectricField import ElectricField
+
+
+class CZT_prop(nn.Module):
+
+    def __init__(self, z_distance=0.0, device=None):
+        super().__init__()
+        self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self._z = torch.tensor(z_distance, device=self.device)
+        self._plan_key = None
+        self._plan = None
+
+    @property
+    def z(self):
+        return self._z
+
+    @z.setter
+    def z(self, z):
+        if isinstance(z, torch.Tensor) and z.device != self.device:
+            z = z.to(self.device)
+        self._z = z
+
+    def _get_plan(self, field, out_h, out_w, out_dx, out_dy, device):
+        z = self._z.detach().cpu() if isinstance(self._z, torch.Tensor) else torch.tensor(float(self._z))
+        key = (tuple(field.wavelengths.detach().cpu().reshape(-1).tolist()), tuple(field.spacing.detach().cpu().reshape(-1).tolist()),
+               float(z), field.height, field.width, int(out_h), int(out_w), float(out_dx), float(out_dy), str(device))
+        if key != self._plan_key:
+            hp = CH.CztPlan(field.wavelengths, field.spacing, z, field.height, field.width, int(out_h), int(out_w),
+                            torch.as_tensor(out_dx).detach().cpu(), torch.as_tensor(out_dy).detach().cpu())
+            self._plan = Fn.CztDevicePlan(hp, device)
+            self._plan_key = key
+        return self._plan
+
+    def forward(self, field, outputHeight=None, outputWidth=None, outputPixel_dx=None, outputPixel_dy=None):
+        in_dx, in_dy = field.spacing[0], field.spacing[1]
+        if outputHeight is None:
+            outputHeight = field.height
+        if outputPixel_dx is None:
+            outputPixel_dx = in_dx
+        if outputWidth is None:
+            outputWidth = field.width
+        if outputPixel_dy is None:
+            outputPixel_dy = in_dy
+        data = field.data
+        plan = self._get_plan(field, outputHeight, outputWidth, outputPixel_dx, outputPixel_dy, data.device)
+        out = Fn.CztFn.apply(data, plan)
+        return ElectricField(data=out, wavelengths=field.wavelengths, spacing=[float(outputPixel_dx), float(outputPixel_dy)],
+                             device=data.device)
+
+
+class VCZT_prop(CZT_prop):
+    """The reference's VCZT_prop (Props/CZT_Prop.py:317-348) is an empty subclass of CZT_prop."""

@@ -41,7 +41,23 @@ class AsmDesc(ctypes.Structure):
         ("tw_h", ctypes.c_void_p), ("tw_w", ctypes.c_void_p),
         ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_uint64),
         ("bc_chunk", ctypes.c_int32), ("tune_k2_cols", ctypes.c_int32),
-        ("tune_lines", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("tune_lines", ctypes.c_int32), ("stages", ctypes.c_int32),
+    ]
+
+
+class ToeplitzGemmDesc(ctypes.Structure):
+    """Mirror of `thz_toeplitz_gemm_desc` (include/thzdoe.h)."""
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+        ("g", ctypes.c_void_p),
+        ("L", ctypes.c_int32), ("off", ctypes.c_int32), ("sm", ctypes.c_int32), ("sk", ctypes.c_int32),
+        ("conj_g", ctypes.c_int32), ("conj_pro", ctypes.c_int32), ("conj_epi", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("B", ctypes.c_void_p),
+        ("sb_b", ctypes.c_int64), ("sb_k", ctypes.c_int64), ("sb_n", ctypes.c_int64),
+        ("pro", ctypes.c_void_p),
+        ("C", ctypes.c_void_p),
+        ("sc_b", ctypes.c_int64), ("sc_m", ctypes.c_int64), ("sc_n", ctypes.c_int64),
+        ("epi", ctypes.c_void_p),
     ]
 
 
@@ -71,6 +87,7 @@ def _declare(l):
     l.thz_quant_psq_fwd.argtypes = [vp, f32, i32, f32, vp, vp, u64, vp]
     l.thz_quant_gumbel_v3_fwd.argtypes = [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp, u64, vp]
     l.thz_quant_gumbel_naive_fwd.argtypes = [vp, vp, vp, i32, f32, vp, vp, vp, u64, vp]
+    l.thz_toeplitz_gemm.argtypes = [ctypes.POINTER(ToeplitzGemmDesc), vp]
     l.thz_launch_count.restype = u64
     l.thz_profile_enable.argtypes = [i32]
     l.thz_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
@@ -86,7 +103,7 @@ EXPORTS = [
     "thz_doe_modulate_fwd", "thz_doe_modulate_bwd", "thz_height_fwd", "thz_height_bwd",
     "thz_quant_ste_fwd", "thz_quant_nn_fwd", "thz_quant_nn_bwd", "thz_quant_psq_fwd",
     "thz_quant_gumbel_v3_fwd", "thz_quant_gumbel_naive_fwd",
-    "thz_launch_count", "thz_profile_enable", "thz_profile_read",
+    "thz_launch_count", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm",
 ]
 
 

@@ -121,6 +121,7 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
     const int chunk = (int)thz_asm_chunk_fields(d);
     const int sm_count = thz_sm_count();
     const int nchunks = (nbc_all + chunk - 1) / chunk;
+    const int stages = d->stages ? d->stages : 7;
     bool zeroed = false;
     for (int f0 = 0; f0 < nbc_all; f0 += chunk) {
         const int nbc = nbc_all - f0 < chunk ? nbc_all - f0 : chunk;
@@ -130,22 +131,25 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
             return thz_set_error(rc, "thz_asm_propagate: transform length has a prime factor > 7 (or output row too wide)");
         if (rc != THZ_OK) return thz_set_error(rc, "thz_asm_propagate: line does not fit in shared memory");
         L.k3.gh_atomic = (d->doe_mode == 2 && (nchunks > 1 || L.k3_gridy > 1)) ? 1 : 0;
-        if (L.k3.gh_atomic && !zeroed) {
+        if ((stages & 4) && L.k3.gh_atomic && !zeroed) {
             cudaError_t e = cudaMemsetAsync(d->doe_gh, 0, (size_t)d->outH * d->outW * sizeof(float), stream);
             if (e != cudaSuccess) return thz_set_cuda_error("cudaMemsetAsync(gh)", e);
             zeroed = true;
         }
-        if (L.p2_w) {
+        if (!(stages & 1)) {
+        } else if (L.p2_w) {
             if ((rc = thz_p2_launch_k1(L.k1, L.k1_grid, L.k1_threads, L.k1_smem, stream)) != THZ_OK) return rc;
         } else {
             THZ_LAUNCH(thz_k1_row_fwd, THZ_KC_ROW_FWD, L.mixed_w, L.k1_grid, L.k1_threads, L.k1_smem, stream, L.k1);
         }
-        if (L.p2_h) {
+        if (!(stages & 2)) {
+        } else if (L.p2_h) {
             if ((rc = thz_p2_launch_k2(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem, stream)) != THZ_OK) return rc;
         } else {
             THZ_LAUNCH(thz_k2_col, THZ_KC_COL, L.mixed_h, dim3(L.k2_gridx, nbc), L.k2_threads, L.k2_smem, stream, L.k2);
         }
-        if (L.p2_w) {
+        if (!(stages & 4)) {
+        } else if (L.p2_w) {
             if ((rc = thz_p2_launch_k3(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem, stream)) != THZ_OK) return rc;
         } else {
             THZ_LAUNCH(thz_k3_row_inv, THZ_KC_ROW_INV, L.mixed_w, dim3(L.k3_gridx, L.k3_gridy), L.k3_threads, L.k3_smem, stream, L.k3);

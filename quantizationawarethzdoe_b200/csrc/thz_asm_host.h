@@ -26,18 +26,21 @@ static inline int thz_imin(int a, int b) { return a < b ? a : b; }
 
 static inline int thz_asm_validate(const thz_asm_desc* d) {
     if (!d) return THZ_E_NULL;
-    if (!d->x || !d->tw_h || !d->tw_w || !d->ws) return THZ_E_NULL;
+    const int st = d->stages ? d->stages : 7;
+    if (st < 0 || st > 7) return THZ_E_SHAPE;
+    if (st != 7 && d->bc_chunk > 0 && d->bc_chunk < d->B * d->C) return THZ_E_SHAPE;   // staged runs keep all fields in ws
+    if (((st & 1) && !d->x) || !d->tw_h || !d->tw_w || !d->ws) return THZ_E_NULL;
     if (d->B < 1 || d->C < 1 || d->inH < 1 || d->inW < 1 || d->outH < 1 || d->outW < 1) return THZ_E_SHAPE;
     if (d->in_r0 < 0 || d->in_c0 < 0 || d->out_r0 < 0 || d->out_c0 < 0) return THZ_E_SHAPE;
     if (d->in_r0 + d->inH > d->Hp || d->in_c0 + d->inW > d->Wp) return THZ_E_SHAPE;
     if (d->out_r0 + d->outH > d->Hp || d->out_c0 + d->outW > d->Wp) return THZ_E_SHAPE;
-    if (d->tf_mode == 0 && (!d->tf_rowvec || !d->tf_colvec || !d->tf_scal)) return THZ_E_NULL;
-    if (d->tf_mode == 1 && !d->tf_table) return THZ_E_NULL;
+    if ((st & 2) && d->tf_mode == 0 && (!d->tf_rowvec || !d->tf_colvec || !d->tf_scal)) return THZ_E_NULL;
+    if ((st & 2) && d->tf_mode == 1 && !d->tf_table) return THZ_E_NULL;
     if (d->tf_mode < 0 || d->tf_mode > 2) return THZ_E_SHAPE;
     if (d->doe_mode < 0 || d->doe_mode > 2) return THZ_E_SHAPE;
     if (d->doe_mode != 0 && (!d->doe_hmap || !d->doe_coef)) return THZ_E_NULL;
-    if (d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
-    if (d->doe_mode != 2 && !d->y) return THZ_E_NULL;
+    if ((st & 4) && d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
+    if ((st & 4) && d->doe_mode != 2 && !d->y) return THZ_E_NULL;
     return THZ_OK;
 }
 

@@ -1,0 +1,168 @@
+// Chirp-z propagation as separable Toeplitz complex GEMMs.
+//
+//   C[b](m, n) = epi[b](m, n) * sum_k T[b](m, k) * ( pro[b](k, n) * B[b](k, n) )
+//   T[b](m, k) = g[b][ (off + sm*m + sk*k) mod L ]            (optionally conjugated)
+//
+// One kernel serves both 1-D Bluestein passes of CZT_prop.forward (Props/CZT_Prop.py:179-250) and both
+// passes of its adjoint: the Toeplitz operand is never stored, its tiles are expanded in shared memory
+// from the O(m+M) chirp filter g; the input-side factor F*pre and the output-side factor F0*post*s are
+// applied while loading B / storing C.  B and C are addressed through element strides so that the
+// second pass (which contracts the W axis and writes the transposed orientation the reference produces)
+// needs no transposition pass.
+//
+// This file is the fp32 CUDA-core implementation (4 FFMA per complex MAC, 64x64x16 tiles, 4x4 register
+// blocking): the correctness baseline for the tcgen05 3xTF32 path.
+#include "thz_common.cuh"
+#include "thz_runtime.h"
+
+struct ToeplitzGemmArgs {
+    int batch, M, N, K;
+    const cpx* g;             // [batch][L]
+    int L, off, sm, sk, conj_g;
+    const cpx* B;             // element (b, k, n) at B[b*sb_b + k*sb_k + n*sb_n]
+    long long sb_b, sb_k, sb_n;
+    const cpx* pro;           // optional prologue factor, same indexing as B
+    int conj_pro;
+    cpx* C;                   // element (b, m, n) at C[b*sc_b + m*sc_m + n*sc_n]
+    long long sc_b, sc_m, sc_n;
+    const cpx* epi;           // optional epilogue factor, same indexing as C
+    int conj_epi;
+};
+
+#define TG_BM 64
+#define TG_BN 64
+#define TG_BK 16
+
+__global__ void __launch_bounds__(256) thz_k_toeplitz_gemm(const __grid_constant__ ToeplitzGemmArgs a) {
+    __shared__ cpx As[TG_BK][TG_BM + 1];
+    __shared__ cpx Bs[TG_BK][TG_BN + 1];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * TG_BN, m0 = blockIdx.y * TG_BM, b = blockIdx.z;
+    const cpx* g = a.g + (size_t)b * a.L;
+    const cpx* Bb = a.B + (size_t)b * a.sb_b;
+    const cpx* Pb = a.pro ? a.pro + (size_t)b * a.sb_b : nullptr;
+    cpx acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = cmake(0.f, 0.f);
+
+    for (int k0 = 0; k0 < a.K; k0 += TG_BK) {
+        // Toeplitz tile: As[kk][i] = g[(off + sm*(m0+i) + sk*(k0+kk)) mod L]
+#pragma unroll
+        for (int e = tid; e < TG_BM * TG_BK; e += 256) {
+            const int i = e & (TG_BM - 1), kk = e / TG_BM;
+            const int m = m0 + i, k = k0 + kk;
+            cpx v = cmake(0.f, 0.f);
+            if (m < a.M && k < a.K) {
+                long long idx = ((long long)a.off + (long long)a.sm * m + (long long)a.sk * k) % a.L;
+                if (idx < 0) idx += a.L;
+                v = __ldg(g + idx);
+                if (a.conj_g) v.y = -v.y;
+            }
+            As[kk][i] = v;
+        }
+        // B tile with the prologue factor
+#pragma unroll
+        for (int e = tid; e < TG_BK * TG_BN; e += 256) {
+            int kk, j;
+            if (a.sb_n == 1) {   // n contiguous: consecutive threads walk n
+                j = e & (TG_BN - 1);
+                kk = e / TG_BN;
+            } else {             // k contiguous: consecutive threads walk k
+                kk = e & (TG_BK - 1);
+                j = e / TG_BK;
+            }
+            const int k = k0 + kk, n = n0 + j;
+            cpx v = cmake(0.f, 0.f);
+            if (k < a.K && n < a.N) {
+                const size_t o = (size_t)k * a.sb_k + (size_t)n * a.sb_n;
+                v = Bb[o];
+                if (Pb) {
+                    cpx p = __ldg(Pb + o);
+                    v = a.conj_pro ? cmulc(v, p) : cmul(v, p);
+                }
+            }
+            Bs[kk][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TG_BK; ++kk) {
+            cpx av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j].x = fmaf(av[i].x, bv[j].x, acc[i][j].x);
+                    acc[i][j].x = fmaf(-av[i].y, bv[j].y, acc[i][j].x);
+                    acc[i][j].y = fmaf(av[i].x, bv[j].y, acc[i][j].y);
+                    acc[i][j].y = fmaf(av[i].y, bv[j].x, acc[i][j].y);
+                }
+        }
+        __syncthreads();
+    }
+    cpx* Cb = a.C + (size_t)b * a.sc_b;
+    const cpx* Eb = a.epi ? a.epi + (size_t)b * a.sc_b : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= a.N) continue;
+            const size_t o = (size_t)m * a.sc_m + (size_t)n * a.sc_n;
+            cpx v = acc[i][j];
+            if (Eb) {
+                cpx q = __ldg(Eb + o);
+                v = a.conj_epi ? cmulc(v, q) : cmul(v, q);
+            }
+            Cb[o] = v;
+        }
+    }
+}
+
+extern "C" int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* d, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d) return thz_set_error(THZ_E_NULL, "thz_toeplitz_gemm: null descriptor");
+    if (!d->g || !d->B || !d->C) return thz_set_error(THZ_E_NULL, "thz_toeplitz_gemm: null pointer");
+    if (d->batch < 1 || d->M < 1 || d->N < 1 || d->K < 1 || d->L < 1)
+        return thz_set_error(THZ_E_SHAPE, "thz_toeplitz_gemm: bad shape");
+    if ((d->sm != 1 && d->sm != -1) || (d->sk != 1 && d->sk != -1))
+        return thz_set_error(THZ_E_SHAPE, "thz_toeplitz_gemm: Toeplitz steps must be +1 or -1");
+    ToeplitzGemmArgs a;
+    a.batch = d->batch;
+    a.M = d->M;
+    a.N = d->N;
+    a.K = d->K;
+    a.g = (const cpx*)d->g;
+    a.L = d->L;
+    a.off = d->off;
+    a.sm = d->sm;
+    a.sk = d->sk;
+    a.conj_g = d->conj_g;
+    a.B = (const cpx*)d->B;
+    a.sb_b = d->sb_b;
+    a.sb_k = d->sb_k;
+    a.sb_n = d->sb_n;
+    a.pro = (const cpx*)d->pro;
+    a.conj_pro = d->conj_pro;
+    a.C = (cpx*)d->C;
+    a.sc_b = d->sc_b;
+    a.sc_m = d->sc_m;
+    a.sc_n = d->sc_n;
+    a.epi = (const cpx*)d->epi;
+    a.conj_epi = d->conj_epi;
+    dim3 grid((d->N + TG_BN - 1) / TG_BN, (d->M + TG_BM - 1) / TG_BM, d->batch);
+    thz_launch_begin(stream, THZ_KC_CZT);
+    thz_k_toeplitz_gemm<<<grid, 256, 0, stream>>>(a);
+    thz_launch_end(stream, THZ_KC_CZT);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return thz_set_cuda_error("thz_k_toeplitz_gemm", e);
+    return THZ_OK;
+}

@@ -19,6 +19,11 @@ TUNE = {"bc_chunk": 0, "k2_cols": 0, "lines": 0}
 _ws_cache = {}
 
 
+def _asm_call(desc, device):
+    """The one place the fused ASM pipeline is invoked (tests/ replace it with the CPU replay of the kernels)."""
+    N.check(N.lib().thz_asm_propagate(ctypes.byref(desc), N.current_stream_ptr(device)), "thz_asm_propagate")
+
+
 def _workspace(numel, device):
     """One cached complex64 scratch tensor per device, grown on demand (never shrunk)."""
     key = str(device)
@@ -76,7 +81,7 @@ class AsmPlan:
                           self.tf_mode, 1 if conj else 0, self.rowvec, self.colvec, self.scal, self.table,
                           doe_mode, BASE_PLANE_THICKNESS, hmap, coef, xsaved, gh, self.tw_h, self.tw_w, ws,
                           bc_chunk=TUNE["bc_chunk"], tune_k2_cols=TUNE["k2_cols"], tune_lines=TUNE["lines"])
-        N.check(N.lib().thz_asm_propagate(ctypes.byref(d), N.current_stream_ptr(x.device)), "thz_asm_propagate")
+        _asm_call(d, x.device)
         return y
 
 
@@ -351,3 +356,60 @@ def fft2_c2c(x, inverse=False, ortho=False):
                                  N.ptr(N.twiddles(H, x.device)), N.ptr(N.twiddles(W, x.device)), N.ptr(ws),
                                  ws.numel() * 8, N.current_stream_ptr(x.device)), "thz_fft2_c2c")
     return y
+
+
+# ----------------------------------------------------------------------------- chirp-z propagation
+def _toeplitz_gemm(batch, M, N_, K, g, L, off, sm, sk, conj_g, B, sb, pro, conj_pro, C, sc, epi, conj_epi, device):
+    d = N.ToeplitzGemmDesc()
+    d.batch, d.M, d.N, d.K = batch, M, N_, K
+    d.g, d.L, d.off, d.sm, d.sk = N.ptr(g), L, off, sm, sk
+    d.conj_g, d.conj_pro, d.conj_epi, d.reserved = conj_g, conj_pro, conj_epi, 0
+    d.B, (d.sb_b, d.sb_k, d.sb_n) = N.ptr(B), sb
+    d.pro = N.ptr(pro)
+    d.C, (d.sc_b, d.sc_m, d.sc_n) = N.ptr(C), sc
+    d.epi = N.ptr(epi)
+    N.check(N.lib().thz_toeplitz_gemm(ctypes.byref(d), N.current_stream_ptr(device)), "thz_toeplitz_gemm")
+
+
+class CztDevicePlan:
+    """Device copies of a czt_host.CztPlan."""
+
+    def __init__(self, hp, device):
+        self.P, self.Q = hp.P.to(device), hp.Q.to(device)
+        self.gy, self.gx = hp.gy.to(device), hp.gx.to(device)
+        self.Ly, self.Lx = hp.Ly, hp.Lx
+        self.C, self.H, self.W, self.M1, self.M2 = hp.C, hp.H, hp.W, hp.M1, hp.M2
+
+
+class CztFn(torch.autograd.Function):
+    """out = Q * (Ty . (P * x) . Tx^T) per wavelength, two Toeplitz GEMMs; backward = the two adjoint GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x = _c64(x, "field.data")
+        Bn, C, H, W = x.shape
+        M1, M2 = p.M1, p.M2
+        out = torch.empty(Bn, C, M1, M2, dtype=torch.complex64, device=x.device)
+        u1 = torch.empty(C, M1, W, dtype=torch.complex64, device=x.device)
+        for b in range(Bn):
+            _toeplitz_gemm(C, M1, W, H, p.gy, p.Ly, H, 1, -1, 0, x[b], (H * W, W, 1), p.P, 0, u1, (M1 * W, W, 1), None, 0, x.device)
+            _toeplitz_gemm(C, M2, M1, W, p.gx, p.Lx, W, 1, -1, 0, u1, (M1 * W, 1, W), None, 0, out[b], (M1 * M2, 1, M2), p.Q, 0,
+                           x.device)
+        ctx.p = p
+        ctx.in_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p = ctx.p
+        g = _c64(g, "grad_output")
+        Bn, C, H, W = ctx.in_shape
+        M1, M2 = p.M1, p.M2
+        gx = torch.empty(Bn, C, H, W, dtype=torch.complex64, device=g.device)
+        v = torch.empty(C, M1, W, dtype=torch.complex64, device=g.device)
+        for b in range(Bn):
+            # V[c,k1,w] = sum_k2 conj(Tx[k2,w]) conj(Q) G        (m = w, k = k2, n = k1)
+            _toeplitz_gemm(C, W, M1, M2, p.gx, p.Lx, W, -1, 1, 1, g[b], (M1 * M2, 1, M2), p.Q, 1, v, (M1 * W, 1, W), None, 0, g.device)
+            # gx[c,h,w] = conj(P) sum_k1 conj(Ty[k1,h]) V         (m = h, k = k1, n = w)
+            _toeplitz_gemm(C, H, W, M1, p.gy, p.Ly, H, -1, 1, 1, v, (M1 * W, W, 1), None, 0, gx[b], (H * W, W, 1), p.P, 1, g.device)
+        return gx, None

@@ -176,6 +176,7 @@ extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
     const int nbc_all = d->B * d->C;
     const int chunk = (int)thz_asm_chunk_fields(d);
     const int nchunks = (nbc_all + chunk - 1) / chunk;
+    const int stages = d->stages ? d->stages : 7;
     bool zeroed = false;
     for (int f0 = 0; f0 < nbc_all; f0 += chunk) {
         const int nbc = nbc_all - f0 < chunk ? nbc_all - f0 : chunk;
@@ -183,19 +184,22 @@ extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
         rc = thz_asm_plan_chunk(d, f0, nbc, sm_count, &L);
         if (rc != THZ_OK) return rc;
         L.k3.gh_atomic = (d->doe_mode == 2 && (nchunks > 1 || L.k3_gridy > 1)) ? 1 : 0;
-        if (L.k3.gh_atomic && !zeroed) {
+        if ((stages & 4) && L.k3.gh_atomic && !zeroed) {
             memset(d->doe_gh, 0, (size_t)d->outH * d->outW * sizeof(float));
             zeroed = true;
         }
-        if (L.p2_w) {
+        if (!(stages & 1)) {
+        } else if (L.p2_w) {
             P2_DISPATCH(run_p2_k1, d->Wp, L.k1, L.k1_grid, L.k1_threads, L.k1_smem)
         } else if (L.mixed_w) run_k1<true>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
         else run_k1<false>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
-        if (L.p2_h) {
+        if (!(stages & 2)) {
+        } else if (L.p2_h) {
             P2_DISPATCH(run_p2_k2, d->Hp, L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem)
         } else if (L.mixed_h) run_k2<true>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
         else run_k2<false>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
-        if (L.p2_w) {
+        if (!(stages & 4)) {
+        } else if (L.p2_w) {
             P2_DISPATCH(run_p2_k3, d->Wp, L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem)
         } else if (L.mixed_w) run_k3<true>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
         else run_k3<false>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);

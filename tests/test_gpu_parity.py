@@ -256,3 +256,53 @@ def test_power_of_two_fast_path_agrees_with_generic_engine(dev, monkeypatch):
         a.check_Zc = False
         outs.append(a(ElectricField(x, wavelengths=lams, spacing=0.5 * mm, device=dev)).data)
     assert rel_l2(outs[0].cpu(), outs[1].cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_names("czt_"))
+def test_czt_matches_reference_vectors(name, dev):
+    """CZT_prop forward against the reference's own output; tolerance 1e-5 rel-L2 (north_star)."""
+    from quantizationawarethzdoe_b200 import CZT_prop, ElectricField
+    g = golden(name)
+    M = int(g["M"])
+    f = ElectricField(g["x"].to(dev), wavelengths=g["wavelengths"].float(), spacing=g["spacing"].float(), device=dev)
+    czt = CZT_prop(z_distance=g["z"], device=dev)
+    out = czt(f, outputHeight=M, outputWidth=M, outputPixel_dx=g["out_dx"], outputPixel_dy=g["out_dx"])
+    assert out.data.shape == g["y"].shape
+    assert rel_l2(out.data.cpu(), g["y"]) < TOL
+    assert torch.allclose(out.spacing.cpu(), g["out_spacing"].float())
+
+
+def test_czt_adjoint_and_oracle(dev):
+    """Gradient wrt the input field: explicit adjoint GEMMs vs autograd through the oracle's dense form,
+    plus the adjoint identity <A x, y> = <x, A^H y> at a larger size."""
+    from oracle import czt_oracle as CO
+    from quantizationawarethzdoe_b200 import CZT_prop, ElectricField
+    torch.manual_seed(4)
+    H, W, M, lams = 72, 56, 40, [1 * mm, 1.07 * mm]
+    x = torch.randn(1, 2, H, W, dtype=torch.complex64)
+    gy = torch.randn(1, 2, M, M, dtype=torch.complex64)
+    xo = x.clone().requires_grad_(True)
+    yo = CO.czt_forward_dense(xo, torch.tensor(lams), torch.tensor([0.5 * mm, 0.5 * mm]), torch.tensor(0.4), M, M, 0.2 * mm, 0.2 * mm)
+    (gxo,) = torch.autograd.grad(yo, xo, gy)
+    czt = CZT_prop(z_distance=0.4, device=dev)
+    xd = x.to(dev).requires_grad_(True)
+    y = czt(ElectricField(xd, wavelengths=lams, spacing=0.5 * mm, device=dev), M, M, 0.2 * mm, 0.2 * mm).data
+    (gx,) = torch.autograd.grad(y, xd, gy.to(dev))
+    assert rel_l2(y.detach().cpu(), yo.detach()) < TOL
+    assert rel_l2(gx.cpu(), gxo) < TOL
+    # larger, non-multiple-of-tile sizes: adjoint identity
+    H, W, M = 300, 260, 150
+    czt2 = CZT_prop(z_distance=0.5, device=dev)
+    xa = torch.randn(1, 1, H, W, dtype=torch.complex64, device=dev).requires_grad_(True)
+    yv = torch.randn(1, 1, M, M, dtype=torch.complex64, device=dev)
+    Ax = czt2(ElectricField(xa, wavelengths=[1 * mm], spacing=0.5 * mm, device=dev), M, M, 0.1 * mm, 0.1 * mm).data
+    (AHy,) = torch.autograd.grad(Ax, xa, yv)
+    lhs, rhs = torch.sum(Ax.detach().conj() * yv), torch.sum(xa.detach().conj() * AHy)
+    assert abs(lhs - rhs) / abs(lhs) < 1e-4
+
+
+def test_czt_rejects_non_square_output_like_the_reference(dev):
+    from quantizationawarethzdoe_b200 import CZT_prop, ElectricField
+    f = ElectricField(torch.zeros(1, 1, 32, 32, dtype=torch.complex64, device=dev), 1e-3, 1e-3, device=dev)
+    with pytest.raises(RuntimeError, match="outputHeight must equal outputWidth"):
+        CZT_prop(z_distance=0.5, device=dev)(f, outputHeight=16, outputWidth=24)
