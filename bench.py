@@ -235,12 +235,13 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- per-kernel attribution with CUDA events on the launching stream (separate pass, slight overhead)
     kernels = None
+    psteps = min(args.steps, 5)
     if rank == 0:
         lib.thz_profile_enable(1)
-        psteps = min(args.steps, 5)
-        for _ in range(psteps):
-            step(x_dev)
-        torch.cuda.synchronize(dev)
+    for _ in range(psteps):          # every rank runs these steps (they contain the all-reduce); rank 0 records events
+        step(x_dev)
+    barrier()
+    if rank == 0:
         ms_sum = (ctypes.c_float * 8)()
         cnt = (ctypes.c_int32 * 8)()
         lib.thz_profile_read(8, ms_sum, cnt)

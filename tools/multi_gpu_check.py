@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Multi-GPU functional check (launch with torchrun, one rank per GPU):
+   * slab-decomposed ASM over all ranks == single-GPU ASM_prop on rank 0 (forward and adjoint);
+   * data-parallel DOE step: all-reduced weight gradient == single-GPU full-batch gradient.
+   Prints one line per check on rank 0 and exits non-zero on failure."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, STEQuantizedDOELayer, parallel as P  # noqa: E402
+
+mm = 1e-3
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+n = int(os.environ.get("THZ_SLAB_N", "2048"))
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+# ---- slab vs single GPU
+lams = [1 * mm, 1.03 * mm]
+torch.manual_seed(0)
+x = torch.randn(1, 2, n, n, dtype=torch.complex64, device=dev)
+g = torch.randn(1, 2, n, n, dtype=torch.complex64, device=dev)
+lo, hi = P.shard_range(n, rank, world)
+slab = P.SlabAsm(z_distance=0.1)
+xl = x[:, :, lo:hi].contiguous().requires_grad_(True)
+yl = slab(ElectricField(xl, wavelengths=lams, spacing=0.5 * mm, device=dev)).data
+(gxl,) = torch.autograd.grad(yl, xl, g[:, :, lo:hi].contiguous())
+asm = ASM_prop(z_distance=0.1, device=dev)
+asm.check_Zc = False
+xf = x.clone().requires_grad_(True)
+yf = asm(ElectricField(xf, wavelengths=lams, spacing=0.5 * mm, device=dev)).data
+(gxf,) = torch.autograd.grad(yf, xf, g)
+e = torch.tensor([rel(yl.detach(), yf.detach()[:, :, lo:hi]), rel(gxl, gxf[:, :, lo:hi])], device=dev)
+dist.all_reduce(e, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("slab %d^2 over %d GPUs vs single GPU: fwd %.2e adjoint %.2e" % (n, world, e[0], e[1]))
+ok &= bool(e.max() < 2e-6)
+
+# ---- data parallel over wavelengths
+C = 2 * world
+lam_all = [1 * mm * (1 + 0.01 * c) for c in range(C)]
+torch.manual_seed(1)
+xa = torch.randn(1, C, 512, 512, dtype=torch.complex64, device=dev)
+torch.manual_seed(2)
+doe = STEQuantizedDOELayer(dict(doe_size=[512, 512], doe_dxy=0.5 * mm, doe_level=4, height_constraint_max=1 * mm, tolerance=None,
+                                material=[2.66, 0.003]), {}, device=dev)
+full = ElectricField(xa, wavelengths=lam_all, spacing=0.5 * mm, device=dev)
+y = asm(doe(P.shard_field(full, rank, world))).data
+(0.5 * (y.real ** 2 + y.imag ** 2).sum()).backward()
+P.allreduce_gradients(doe.parameters())
+g_dp = doe.weight_height_map.grad.clone()
+doe.weight_height_map.grad = None
+y = asm(doe(full)).data
+(0.5 * (y.real ** 2 + y.imag ** 2).sum()).backward()
+e = torch.tensor([rel(g_dp, doe.weight_height_map.grad)], device=dev)
+dist.all_reduce(e, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("data-parallel grad over %d GPUs vs full batch: %.2e" % (world, e[0]))
+ok &= bool(e.max() < 1e-5)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
