@@ -74,7 +74,9 @@ static inline void thz_asm_apply_p2(const thz_asm_desc* d, int nbc, int sm_count
         L->k1.lines = lines;
         L->k1_threads = threads;
         L->k1_grid = (nbc * d->inH + lines - 1) / lines;
+        // line buffer + staged raw rows (+ staged height-map rows), see thz_p2_k1
         L->k1_smem = smem;
+        if (p2_row_pipelined(d->Wp)) L->k1_smem += (size_t)lines * d->inW * sizeof(cpx) + (size_t)lines * d->inW * sizeof(float);
         L->k3.lines = lines;
         L->k3_threads = threads;
         L->k3_gridx = (d->outH + lines - 1) / lines;
@@ -83,7 +85,7 @@ static inline void thz_asm_apply_p2(const thz_asm_desc* d, int nbc, int sm_count
         gy = thz_imin(gy, nbc);
         L->k3.bc_per_cta = (nbc + gy - 1) / gy;
         L->k3_gridy = (nbc + L->k3.bc_per_cta - 1) / L->k3.bc_per_cta;
-        L->k3_smem = smem;
+        L->k3_smem = p2_row_pipelined(d->Wp) ? 2 * smem : smem;   // double-buffered line (thz_p2_k3 prefetches the next field)
     }
     if (L->p2_h) {
         const int cols = thz_p2_col_cols_rt(d->Hp);

@@ -40,13 +40,36 @@ __device__ __forceinline__ void inv_cols(cpx* s, int tid, int nt, const cpx* tw)
 // ------------------------------------------------------------------------------- kernels
 template <int N>
 __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k1(const __grid_constant__ RowFwdArgs a) {
+    constexpr int LINES = p2_row_lines(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);
-    const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x;
-    p2k1_first<N>(a, s, bx, tid, nt);
-    __syncthreads();
-    fwd_rows<N, 1, p2_stages(N), p2_row_lines(N)>(s, tid, nt, a.tw);
-    p2k1_store<N>(a, s, bx, tid, nt);
+    cpx* xs = s + LINES * p2_pitch(N);                                   // staged raw rows
+    float* hs = reinterpret_cast<float*>(xs + (size_t)LINES * a.inW);      // staged height-map rows
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int ngroups = (a.nbc * a.inH + LINES - 1) / LINES;
+    int grp = blockIdx.x;
+    if constexpr (!p2_row_pipelined(N)) {     // no room for staging: plain load -> transform -> store per group
+        for (; grp < ngroups; grp += gridDim.x) {
+            p2k1_first<N>(a, s, grp, tid, nt);
+            __syncthreads();
+            fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, a.tw);
+            p2k1_store<N>(a, s, grp, tid, nt);
+            __syncthreads();
+        }
+        return;
+    }
+    if (grp < ngroups) p2k1_prefetch<N>(a, xs, hs, grp, tid, nt);
+    thz_cp_async_commit();
+    for (; grp < ngroups; grp += gridDim.x) {
+        thz_cp_async_wait_all();
+        __syncthreads();                      // staging complete; previous group's store has drained the line buffer
+        p2k1_first_staged<N>(a, s, xs, hs, grp, tid, nt);
+        __syncthreads();                      // staging consumed
+        if (grp + (int)gridDim.x < ngroups) p2k1_prefetch<N>(a, xs, hs, grp + gridDim.x, tid, nt);
+        thz_cp_async_commit();
+        fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, a.tw);
+        p2k1_store<N>(a, s, grp, tid, nt);
+    }
 }
 
 template <int N>
@@ -66,21 +89,37 @@ __global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
 
 template <int N>
 __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k3(const __grid_constant__ RowInvArgs a) {
-    constexpr int NACC = p2k3_acc<N>();
+    constexpr int NACC = p2k3_acc<N>(), LINES = p2_row_lines(N), BUF = LINES * p2_pitch(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cpx* s = reinterpret_cast<cpx*>(smem_raw);
+    cpx* s = reinterpret_cast<cpx*>(smem_raw);      // two line buffers: [0, BUF) and [BUF, 2 BUF)
     const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x;
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
     const int f_lo = blockIdx.y * a.bc_per_cta;
     const int f_hi = min(a.nbc, f_lo + a.bc_per_cta);
-    for (int f = f_lo; f < f_hi; ++f) {
-        p2k3_load<N>(a, s, bx, f, tid, nt);
-        __syncthreads();
-        inv_rows<N, p2_stages(N) - 1, 1, p2_row_lines(N)>(s, tid, nt, a.tw);
-        p2k3_last<N, NACC>(a, s, bx, f, tid, nt, acc);
-        __syncthreads();
+    int cur = 0;
+    if constexpr (!p2_row_pipelined(N)) {     // single line buffer
+        for (int f = f_lo; f < f_hi; ++f) {
+            p2k3_load<N>(a, s, bx, f, tid, nt);
+            __syncthreads();
+            inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, tid, nt, a.tw);
+            p2k3_last<N, NACC>(a, s, bx, f, tid, nt, acc);
+            __syncthreads();
+        }
+        p2k3_flush<N, NACC>(a, bx, tid, nt, acc);
+        return;
+    }
+    if (f_lo < f_hi) p2k3_prefetch<N>(a, s, bx, f_lo, tid, nt);
+    thz_cp_async_commit();
+    for (int f = f_lo; f < f_hi; ++f, cur ^= 1) {
+        cpx* sc = s + cur * BUF;
+        thz_cp_async_wait_all();
+        __syncthreads();                      // rows of field f have landed; the other buffer is free (its epilogue ran)
+        if (f + 1 < f_hi) p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, tid, nt);
+        thz_cp_async_commit();
+        inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, tid, nt, a.tw);
+        p2k3_last<N, NACC>(a, sc, bx, f, tid, nt, acc);
     }
     p2k3_flush<N, NACC>(a, bx, tid, nt, acc);
 }
@@ -121,6 +160,9 @@ static int set_smem_p2(K kernel, size_t bytes) {
     }
 
 int thz_p2_launch_k1(const RowFwdArgs& a, int grid, int threads, size_t smem, cudaStream_t stream) {
+    // persistent CTAs: a few per SM, each walking line groups bx, bx + grid, ... (software pipeline inside)
+    const int resident = thz_sm_count() * (a.Wp >= 8192 ? 1 : 3);
+    if (grid > resident) grid = resident;
     THZ_P2_SWITCH(thz_p2_k1, a.Wp, THZ_KC_ROW_FWD, grid, threads, smem, stream, a)
     return THZ_OK;
 }

@@ -21,6 +21,8 @@ THZ_HD constexpr int p2_row_threads(int N) { return N >= 8192 ? 512 : 256; }
 THZ_HD constexpr int p2_col_cols(int N) { return N >= 16384 ? 1 : (N >= 4096 ? 2 : (N >= 2048 ? 4 : (N >= 1024 ? 8 : 16))); }
 THZ_HD constexpr int p2_col_threads(int N) { return N >= 8192 ? 512 : 256; }
 THZ_HD constexpr int p2_pitch(int N) { return N + (N >> 4); }
+// the software pipelines of the row kernels need extra shared memory; 16384-point lines do without
+THZ_HD constexpr bool p2_row_pipelined(int N) { return N <= 8192; }
 
 // =============================================================================== K1<N>
 struct K1Loader {
@@ -34,7 +36,7 @@ struct K1Loader {
         if (xr == nullptr || c < 0 || c >= inW) return cmake(0.f, 0.f);
         cpx v = xr[c];
         if (conj_in) v.y = -v.y;
-        if (hr) v = cmul(v, thz_doe_phase(thz_ldg(hr + c), cf, base));
+        if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
         return v;
     }
 };
@@ -60,6 +62,61 @@ THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
             if (a.doe.hmap) {
                 ld.cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
                 ld.hr = a.doe.hmap + (size_t)r * a.inW;
+            }
+        }
+        p2_first_stage_from<N, 1>(s + line * PITCH, j, a.tw, ld);
+    }
+}
+
+// ---- software-pipelined variant: the CTA is persistent over line groups; the raw input rows (and the
+// height-map rows in DOE mode) of the NEXT group are staged in shared memory by cp.async while the
+// current group is transformed.  Staging layout: xs[LINES][inW] complex, then hs[LINES][inW] float.
+template <int N>
+THZ_HD void p2k1_prefetch(const RowFwdArgs& a, cpx* xs, float* hs, int grp, int tid, int nt) {
+    constexpr int LINES = p2_row_lines(N);
+    const int total_lines = a.nbc * a.inH;
+    for (int line = 0; line < LINES; ++line) {
+        const int gl = grp * LINES + line;
+        if (gl >= total_lines) break;
+        const cpx* xr = a.x + (size_t)gl * a.inW;
+        cpx* xd = xs + (size_t)line * a.inW;
+        if ((a.inW & 1) == 0) {
+            for (int c = tid * 2; c < a.inW; c += nt * 2) thz_cp_async16(xd + c, xr + c);
+        } else {
+            for (int c = tid; c < a.inW; c += nt) thz_cp_async8(xd + c, xr + c);
+        }
+        if (a.doe.hmap) {
+            const float* hr = a.doe.hmap + (size_t)(gl % a.inH) * a.inW;
+            float* hd = hs + (size_t)line * a.inW;
+            if ((a.inW & 3) == 0) {
+                for (int c = tid * 4; c < a.inW; c += nt * 4) thz_cp_async16(hd + c, hr + c);
+            } else {
+                for (int c = tid; c < a.inW; c += nt) thz_cp_async4(hd + c, hr + c);
+            }
+        }
+    }
+}
+
+template <int N>
+THZ_HD void p2k1_first_staged(const RowFwdArgs& a, cpx* s, const cpx* xs, const float* hs, int grp, int tid, int nt) {
+    constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N);
+    const int total_lines = a.nbc * a.inH;
+    for (int w = tid; w < LINES * NB; w += nt) {
+        const int line = w / NB, j = w % NB;
+        const int gl = grp * LINES + line;
+        K1Loader ld;
+        ld.xr = nullptr;
+        ld.hr = nullptr;
+        ld.cf = cmake4(0.f);
+        ld.base = a.doe.base;
+        ld.in_c0 = a.in_c0;
+        ld.inW = a.inW;
+        ld.conj_in = a.conj_in;
+        if (gl < total_lines) {
+            ld.xr = xs + (size_t)line * a.inW;
+            if (a.doe.hmap) {
+                ld.cf = thz_ldg(a.doe.coef + (a.c0 + gl / a.inH) % a.C);
+                ld.hr = hs + (size_t)line * a.inW;
             }
         }
         p2_first_stage_from<N, 1>(s + line * PITCH, j, a.tw, ld);
@@ -193,6 +250,21 @@ THZ_HD void p2k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int n
         const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         cpx* sl = s + l * PITCH;
         for (int p = tid; p < N; p += nt) sl[p + (p >> 4)] = tr[p];
+    }
+}
+
+// asynchronous variant of the load: T rows of field f -> padded line buffer `s` (8-byte cp.async: the padded
+// slots of odd 16-groups are only 8-byte aligned)
+template <int N>
+THZ_HD void p2k3_prefetch(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nt) {
+    constexpr int LINES = p2_row_lines(N), PITCH = p2_pitch(N);
+#pragma unroll
+    for (int l = 0; l < LINES; ++l) {
+        const int r = bx * LINES + l;
+        if (r >= a.outH) break;
+        const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
+        cpx* sl = s + l * PITCH;
+        for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), tr + p);
     }
 }
 

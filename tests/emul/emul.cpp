@@ -115,12 +115,31 @@ static void e_inv_cols(cpx* s, int nt, const cpx* tw) {
 
 template <int N>
 static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
+    constexpr int LINES = p2_row_lines(N);
     std::vector<unsigned char> buf(smem);
     cpx* s = (cpx*)buf.data();
-    for (int bx = 0; bx < grid; ++bx) {
-        for_threads(nt, [&](int t) { p2k1_first<N>(a, s, bx, t, nt); });
-        e_fwd_rows<N, 1, p2_stages(N), p2_row_lines(N)>(s, nt, a.tw);
-        for_threads(nt, [&](int t) { p2k1_store<N>(a, s, bx, t, nt); });
+    cpx* xs = s + LINES * p2_pitch(N);
+    float* hs = (float*)(xs + (size_t)LINES * a.inW);
+    const int ngroups = (a.nbc * a.inH + LINES - 1) / LINES;
+    const int g = grid < 5 ? grid : 5;   // a few persistent "CTAs", each walking groups bx, bx+g, ...
+    for (int bx = 0; bx < g; ++bx) {
+        int grp = bx;
+        if constexpr (!p2_row_pipelined(N)) {
+            for (; grp < ngroups; grp += g) {
+                for_threads(nt, [&](int t) { p2k1_first<N>(a, s, grp, t, nt); });
+                e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, a.tw);
+                for_threads(nt, [&](int t) { p2k1_store<N>(a, s, grp, t, nt); });
+            }
+            continue;
+        }
+        if (grp < ngroups) for_threads(nt, [&](int t) { p2k1_prefetch<N>(a, xs, hs, grp, t, nt); });
+        for (; grp < ngroups; grp += g) {
+            // the replay copies synchronously, so the "next" prefetch must not clobber the staging buffer before it is consumed
+            for_threads(nt, [&](int t) { p2k1_first_staged<N>(a, s, xs, hs, grp, t, nt); });
+            if (grp + g < ngroups) for_threads(nt, [&](int t) { p2k1_prefetch<N>(a, xs, hs, grp + g, t, nt); });
+            e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, a.tw);
+            for_threads(nt, [&](int t) { p2k1_store<N>(a, s, grp, t, nt); });
+        }
     }
 }
 template <int N>
@@ -139,7 +158,7 @@ static void run_p2_k2(const ColArgs& a, int gx, int gy, int nt, size_t smem) {
 }
 template <int N>
 static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) {
-    constexpr int NACC = p2k3_acc<N>();
+    constexpr int NACC = p2k3_acc<N>(), LINES = p2_row_lines(N), BUF = LINES * p2_pitch(N);
     typedef float acc_t[NACC];
     std::vector<unsigned char> buf(smem);
     cpx* s = (cpx*)buf.data();
@@ -148,10 +167,22 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
         for (int bx = 0; bx < gx; ++bx) {
             std::fill(accs.begin(), accs.end(), 0.f);
             const int f_lo = by * a.bc_per_cta, f_hi = thz_imin(a.nbc, f_lo + a.bc_per_cta);
-            for (int f = f_lo; f < f_hi; ++f) {
-                for_threads(nt, [&](int t) { p2k3_load<N>(a, s, bx, f, t, nt); });
-                e_inv_rows<N, p2_stages(N) - 1, 1, p2_row_lines(N)>(s, nt, a.tw);
-                for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, s, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+            int cur = 0;
+            if constexpr (!p2_row_pipelined(N)) {
+                for (int f = f_lo; f < f_hi; ++f) {
+                    for_threads(nt, [&](int t) { p2k3_load<N>(a, s, bx, f, t, nt); });
+                    e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, nt, a.tw);
+                    for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, s, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                }
+                for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                continue;
+            }
+            if (f_lo < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s, bx, f_lo, t, nt); });
+            for (int f = f_lo; f < f_hi; ++f, cur ^= 1) {
+                cpx* sc = s + cur * BUF;
+                if (f + 1 < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, t, nt); });
+                e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, nt, a.tw);
+                for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, sc, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
             }
             for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
         }
