@@ -10,24 +10,16 @@
 // second pass (which contracts the W axis and writes the transposed orientation the reference produces)
 // needs no transposition pass.
 //
-// This file is the fp32 CUDA-core implementation (4 FFMA per complex MAC, 64x64x16 tiles, 4x4 register
-// blocking): the correctness baseline for the tcgen05 3xTF32 path.
+// This file holds the C entry point and the fp32 CUDA-core implementation (4 FFMA per complex MAC, 64x64x16
+// tiles, 4x4 register blocking), kept as the correctness baseline (THZ_CZT_IMPL=simt) for the tcgen05 3xTF32
+// kernel in thz_czt_tc.cu, which is the default.
+#include <stdlib.h>
+#include <string.h>
+
 #include "thz_common.cuh"
+#include "thz_czt_args.h"
 #include "thz_runtime.h"
 
-struct ToeplitzGemmArgs {
-    int batch, M, N, K;
-    const cpx* g;             // [batch][L]
-    int L, off, sm, sk, conj_g;
-    const cpx* B;             // element (b, k, n) at B[b*sb_b + k*sb_k + n*sb_n]
-    long long sb_b, sb_k, sb_n;
-    const cpx* pro;           // optional prologue factor, same indexing as B
-    int conj_pro;
-    cpx* C;                   // element (b, m, n) at C[b*sc_b + m*sc_m + n*sc_n]
-    long long sc_b, sc_m, sc_n;
-    const cpx* epi;           // optional epilogue factor, same indexing as C
-    int conj_epi;
-};
 
 #define TG_BM 64
 #define TG_BN 64
@@ -158,6 +150,9 @@ extern "C" int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* d, void* stream_)
     a.sc_n = d->sc_n;
     a.epi = (const cpx*)d->epi;
     a.conj_epi = d->conj_epi;
+    // implementation choice: tcgen05 3xTF32 tensor-core kernel unless THZ_CZT_IMPL=simt asks for the CUDA-core one
+    const char* impl = getenv("THZ_CZT_IMPL");
+    if (!(impl && strcmp(impl, "simt") == 0)) return thz_toeplitz_gemm_tc_launch(a, stream);
     dim3 grid((d->N + TG_BN - 1) / TG_BN, (d->M + TG_BM - 1) / TG_BM, d->batch);
     thz_launch_begin(stream, THZ_KC_CZT);
     thz_k_toeplitz_gemm<<<grid, 256, 0, stream>>>(a);

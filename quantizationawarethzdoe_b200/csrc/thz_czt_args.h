@@ -1,0 +1,22 @@
+// Kernel arguments of the Toeplitz complex GEMM, shared by the CUDA-core (thz_czt.cu) and tcgen05 (thz_czt_tc.cu) paths.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "thz_common.cuh"
+
+struct ToeplitzGemmArgs {
+    int batch, M, N, K;
+    const cpx* g;             // [batch][L]
+    int L, off, sm, sk, conj_g;
+    const cpx* B;             // element (b, k, n) at B[b*sb_b + k*sb_k + n*sb_n]
+    long long sb_b, sb_k, sb_n;
+    const cpx* pro;           // optional prologue factor, same indexing as B
+    int conj_pro;
+    cpx* C;                   // element (b, m, n) at C[b*sc_b + m*sc_m + n*sc_n]
+    long long sc_b, sc_m, sc_n;
+    const cpx* epi;           // optional epilogue factor, same indexing as C
+    int conj_epi;
+};
+
+// tcgen05 / TMEM implementation (thz_czt_tc.cu)
+int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a, cudaStream_t stream);

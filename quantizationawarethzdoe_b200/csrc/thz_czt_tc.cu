@@ -1,0 +1,375 @@
+// Toeplitz complex GEMM on the 5th-generation tensor cores (tcgen05, TMEM accumulators), fp32-accurate through a
+// 3xTF32 split AND fp32 promotion of partial sums.  Same contract as the CUDA-core kernel in thz_czt.cu
+// (include/thzdoe.h: thz_toeplitz_gemm).
+//
+// Real-valued formulation.  For complex C = T . B' (B' = pro * B) a tile accumulator holds, for complex row m
+// (TMEM lane m) and complex column n,   Cr in column n   and   Ci in column 64 + n   of its 128-column buffer:
+//      [Cr | Ci] = [Tr | Ti] . [[ Br,  Bi ],
+//                               [-Bi,  Br ]]
+// i.e. ONE tcgen05.mma (kind::tf32, M=128, N=128) per 8 real K-elements, A = [Tr | Ti] (128 x 32 per stage: 16
+// complex k), B stored K-major as 128 rows x 32.  Every operand is split x = hi + lo (hi = RN-to-TF32, lo = x - hi
+// exactly) and the product accumulated as hi*hi + hi*lo + lo*hi (lo*lo < 2^-22 relative): 12 MMAs per stage.
+//
+// Promotion.  The tensor core adds into its fp32 accumulator with truncation, so a single long accumulation
+// drifts linearly with K (measured: 7.8e-6 / 2.7e-5 / 5.3e-5 relative at K = 256 / 1024 / 2048 with one TMEM
+// accumulator -- above the 1e-5 parity bound).  Therefore the K loop is cut into chunks of 4 stages (64 complex
+// k, 48 MMAs) that each START FROM ZERO in one of two TMEM buffers; 8 accumulate warps drain a finished buffer
+// with tcgen05.ld and add it to fp32 register accumulators with IEEE rounding while the MMA warp already works
+// on the other buffer.
+//
+// Nothing is loaded by TMA: both operands are *generated* -- the Toeplitz tile from the chirp filter g, the B tile
+// from the prologue-scaled input -- by 8 producer warps that write the canonical K-major SWIZZLE_128B layout
+// directly (16-byte chunk c of row r goes to chunk c ^ (r & 7) of its 128-byte row), then fence to the async proxy.
+//
+// Roles (17 warps): warps 0-7 accumulate/epilogue (warp w: TMEM lanes 32 (w%4).., complex columns 32 (w/4)..),
+// warps 8-15 producers, warp 16 MMA issuer.  One 128 x 64 complex output tile per CTA, 3 smem stages of 64 KB.
+//   producers:  wait empty[s] -> fill A_hi/A_lo/B_hi/B_lo[s] -> fence.proxy.async -> arrive full[s]
+//   MMA warp :  per chunk: wait tmem_empty[b]; per stage: wait full[s] -> 12 x tcgen05.mma -> commit empty[s];
+//               commit tmem_full[b]
+//   accumulate: wait tmem_full[b] -> tcgen05.ld -> acc += -> arrive tmem_empty[b];  finally * epi -> global
+#include "thz_common.cuh"
+#include "thz_czt_args.h"
+#include "thz_runtime.h"
+
+#define TC_BM 128                     // complex rows per tile = TMEM lanes
+#define TC_BN 64                      // complex columns per tile -> 128 real accumulator columns
+#define TC_KC 16                      // complex k per stage -> 32 real k = one 128-byte swizzle row
+#define TC_STAGES 3
+#define TC_CHUNK 4                    // stages per promotion chunk
+#define TC_A_BYTES (TC_BM * 128)      // 16 KB: 128 rows x 128 B
+#define TC_B_BYTES (2 * TC_BN * 128)  // 16 KB: 128 rows x 128 B
+#define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)   // hi + lo of both operands: 64 KB
+#define TC_ACC_WARPS 8
+#define TC_PROD_WARPS 8
+#define TC_THREADS ((TC_ACC_WARPS + TC_PROD_WARPS + 1) * 32)
+#define TC_TMEM_COLS 256              // two 128-column accumulator buffers
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU -- trap instead (the launch then fails loudly).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc], kind::tf32, K = 8
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                   "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10,
+// K-major A and B (0) @15/@16, N >> 3 @17, M >> 4 @24.
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+// byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a K-major SWIZZLE_128B tile (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void st_split4(unsigned char* hi_tile, unsigned char* lo_tile, uint32_t off, const float (&v)[4]) {
+    float4 h, l;
+    h.x = tf32_hi(v[0]);
+    h.y = tf32_hi(v[1]);
+    h.z = tf32_hi(v[2]);
+    h.w = tf32_hi(v[3]);
+    l.x = v[0] - h.x;
+    l.y = v[1] - h.y;
+    l.z = v[2] - h.z;
+    l.w = v[3] - h.w;
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+__device__ __forceinline__ int wrap_mod(long long v, int L) {
+    v %= L;
+    return (int)(v < 0 ? v + L : v);
+}
+
+// ------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __grid_constant__ ToeplitzGemmArgs a) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 4];
+    __shared__ uint32_t tmem_base_holder;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM, b = blockIdx.z;
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_STAGES]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * TC_STAGES]), tempty0 = smem_u32(&bars[2 * TC_STAGES + 2]);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, TC_PROD_WARPS);   // one arrival per producer warp
+            mbar_init(empty0 + 8 * s, 1);              // one tcgen05.commit
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(tfull0 + 8 * t, 1);              // one tcgen05.commit per chunk
+            mbar_init(tempty0 + 8 * t, TC_ACC_WARPS);  // one arrival per accumulate warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_holder), TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_holder;
+    const int KB = (a.K + TC_KC - 1) / TC_KC;
+    const int NC = (KB + TC_CHUNK - 1) / TC_CHUNK;
+
+    if (warp >= TC_ACC_WARPS && warp < TC_ACC_WARPS + TC_PROD_WARPS) {
+        // ===================================================================== producers
+        const int ptid = tid - TC_ACC_WARPS * 32;                  // 0..255
+        const cpx* g = a.g + (size_t)b * a.L;
+        const cpx* Bb = a.B + (size_t)b * a.sb_b;
+        const cpx* Pb = a.pro ? a.pro + (size_t)b * a.sb_b : nullptr;
+        // A items: (row r = item & 127, k-chunk c = item >> 7), two per thread; Toeplitz index tracked incrementally
+        int aidx[2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int item = ptid + it * 256, r = item & 127, c = item >> 7;
+            aidx[it] = wrap_mod((long long)a.off + (long long)a.sm * (m0 + r) + (long long)a.sk * (4 * c), a.L);
+        }
+        const int kstep = wrap_mod((long long)a.sk * TC_KC, a.L);
+        // B item: (column r = ptid & 63, k-chunk c = ptid >> 6), one per thread
+        const int bn = ptid & 63, bc = ptid >> 6;
+        const int n = n0 + bn;
+        // Register-level software pipeline: the global loads of stage kb+1 are issued before stage kb is converted
+        // and stored, so their latency is hidden behind the wait for a free smem stage and the split/store work.
+        cpx ga[2][4], gb[4], gp[4];
+        auto load_stage = [&](int kb, cpx (&A)[2][4], cpx (&Bv)[4], cpx (&Pv)[4]) {
+            const int k0 = kb * TC_KC;
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int item = ptid + it * 256, r = item & 127, c = item >> 7;
+                const int m = m0 + r;
+                int idx = aidx[it];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = k0 + 4 * c + e;
+                    A[it][e] = (m < a.M && k < a.K) ? __ldg(g + idx) : cmake(0.f, 0.f);
+                    idx += a.sk;
+                    if (idx >= a.L) idx -= a.L;
+                    if (idx < 0) idx += a.L;
+                }
+                aidx[it] += kstep;
+                if (aidx[it] >= a.L) aidx[it] -= a.L;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + 4 * bc + e;
+                Bv[e] = cmake(0.f, 0.f);
+                Pv[e] = cmake(1.f, 0.f);
+                if (k < a.K && n < a.N) {
+                    const size_t o = (size_t)k * a.sb_k + (size_t)n * a.sb_n;
+                    Bv[e] = Bb[o];
+                    if (Pb) Pv[e] = __ldg(Pb + o);
+                }
+            }
+        };
+        load_stage(0, ga, gb, gp);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % TC_STAGES, use = kb / TC_STAGES;
+            cpx na[2][4], nb[4], np[4];
+            if (kb + 1 < KB) load_stage(kb + 1, na, nb, np);
+            mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
+            unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
+            unsigned char *Ahi = st, *Alo = st + TC_A_BYTES, *Bhi = st + 2 * TC_A_BYTES, *Blo = st + 2 * TC_A_BYTES + TC_B_BYTES;
+            // ---- A: Toeplitz rows [Tr | Ti]
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int item = ptid + it * 256, r = item & 127, c = item >> 7;
+                float re[4], im[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    re[e] = ga[it][e].x;
+                    im[e] = a.conj_g ? -ga[it][e].y : ga[it][e].y;
+                }
+                st_split4(Ahi, Alo, sw128(r, c), re);
+                st_split4(Ahi, Alo, sw128(r, 4 + c), im);
+            }
+            // ---- B: rows n -> [Br | -Bi], rows 64+n -> [Bi | Br]
+            {
+                float br[4], bi[4], nbi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    cpx v = gb[e];
+                    if (Pb) v = a.conj_pro ? cmulc(v, gp[e]) : cmul(v, gp[e]);
+                    br[e] = v.x;
+                    bi[e] = v.y;
+                    nbi[e] = -v.y;
+                }
+                st_split4(Bhi, Blo, sw128(bn, bc), br);
+                st_split4(Bhi, Blo, sw128(bn, 4 + bc), nbi);
+                st_split4(Bhi, Blo, sw128(TC_BN + bn, bc), bi);
+                st_split4(Bhi, Blo, sw128(TC_BN + bn, 4 + bc), br);
+            }
+            fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);
+            if (kb + 1 < KB) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ga[0][e] = na[0][e];
+                    ga[1][e] = na[1][e];
+                    gb[e] = nb[e];
+                    gp[e] = np[e];
+                }
+            }
+        }
+    } else if (warp == TC_ACC_WARPS + TC_PROD_WARPS) {
+        // ===================================================================== MMA issuer
+        const uint32_t idesc = make_idesc(TC_BM, 2 * TC_BN);
+        int kb = 0;
+        for (int c = 0; c < NC; ++c) {
+            const int buf = c & 1;
+            mbar_wait(tempty0 + 8 * buf, ((c >> 1) & 1) ^ 1);       // accumulate warps have drained this buffer
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 2 * TC_BN);
+            const int kb_end = min(KB, kb + TC_CHUNK);
+            for (int first = 1; kb < kb_end; ++kb) {
+                const int s = kb % TC_STAGES, use = kb / TC_STAGES;
+                mbar_wait(full0 + 8 * s, use & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES);
+                    const uint32_t Ahi = st, Alo = st + TC_A_BYTES, Bhi = st + 2 * TC_A_BYTES, Blo = st + 2 * TC_A_BYTES + TC_B_BYTES;
+#pragma unroll
+                    for (int combo = 0; combo < 3; ++combo) {
+                        const uint32_t A = combo == 2 ? Alo : Ahi;
+                        const uint32_t Bm = combo == 1 ? Blo : Bhi;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {   // 4 K-steps of 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                            umma_tf32(tmem_d, make_desc(A + 32 * j), make_desc(Bm + 32 * j), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                    umma_commit(empty0 + 8 * s);                     // smem stage reusable once these MMAs have read it
+                    if (kb == kb_end - 1) umma_commit(tfull0 + 8 * buf);   // chunk complete in TMEM
+                }
+                __syncwarp();
+                first = 0;
+            }
+        }
+    } else {
+        // ===================================================================== accumulate warps / epilogue
+        const int q = warp & 3, half = warp >> 2;                  // TMEM lane quarter, complex column half
+        float accr[32], acci[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) accr[i] = acci[i] = 0.f;
+        for (int c = 0; c < NC; ++c) {
+            const int buf = c & 1;
+            mbar_wait(tfull0 + 8 * buf, (c >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + half * 32);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float r[16], im[16];
+                tmem_ld16(t0 + 16 * j, r);
+                tmem_ld16(t0 + TC_BN + 16 * j, im);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    accr[16 * j + e] += r[e];
+                    acci[16 * j + e] += im[e];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        }
+        const int m = m0 + q * 32 + lane;
+        if (m < a.M) {
+            cpx* Cb = a.C + (size_t)b * a.sc_b;
+            const cpx* Eb = a.epi ? a.epi + (size_t)b * a.sc_b : nullptr;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int n = n0 + half * 32 + e;
+                if (n >= a.N) continue;
+                const size_t o = (size_t)m * a.sc_m + (size_t)n * a.sc_n;
+                cpx v = cmake(accr[e], acci[e]);
+                if (Eb) {
+                    const cpx qv = __ldg(Eb + o);
+                    v = a.conj_epi ? cmulc(v, qv) : cmul(v, qv);
+                }
+                Cb[o] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a, cudaStream_t stream) {
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
+    cudaError_t e = cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return thz_set_cuda_error("cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc)", e);
+    dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM, a.batch);
+    thz_launch_begin(stream, THZ_KC_CZT);
+    thz_k_toeplitz_gemm_tc<<<grid, TC_THREADS, smem, stream>>>(a);
+    thz_launch_end(stream, THZ_KC_CZT);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return thz_set_cuda_error("thz_k_toeplitz_gemm_tc", e);
+    return THZ_OK;
+}
