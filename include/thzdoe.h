@@ -204,6 +204,7 @@ typedef struct thz_toeplitz_gemm_desc {
     void* C;
     int64_t sc_b, sc_m, sc_n;
     const void* epi;
+    void* scratch;             /* optional complex64 [batch*K*N]: lets the tensor-core kernel fold `pro` into B first */
 } thz_toeplitz_gemm_desc;
 
 int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* desc, void* stream);

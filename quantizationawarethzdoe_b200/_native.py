@@ -58,6 +58,7 @@ class ToeplitzGemmDesc(ctypes.Structure):
         ("C", ctypes.c_void_p),
         ("sc_b", ctypes.c_int64), ("sc_m", ctypes.c_int64), ("sc_n", ctypes.c_int64),
         ("epi", ctypes.c_void_p),
+        ("scratch", ctypes.c_void_p),
     ]
 
 

@@ -152,7 +152,10 @@ extern "C" int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* d, void* stream_)
     a.conj_epi = d->conj_epi;
     // implementation choice: tcgen05 3xTF32 tensor-core kernel unless THZ_CZT_IMPL=simt asks for the CUDA-core one
     const char* impl = getenv("THZ_CZT_IMPL");
-    if (!(impl && strcmp(impl, "simt") == 0)) return thz_toeplitz_gemm_tc_launch(a, stream);
+    if (!(impl && strcmp(impl, "simt") == 0)) {
+        const int rc = thz_toeplitz_gemm_tc_launch(a, d->scratch, stream);
+        if (rc != THZ_E_WORKSPACE) return rc;       // else: no scratch for the prologue factor -> CUDA-core kernel
+    }
     dim3 grid((d->N + TG_BN - 1) / TG_BN, (d->M + TG_BM - 1) / TG_BM, d->batch);
     thz_launch_begin(stream, THZ_KC_CZT);
     thz_k_toeplitz_gemm<<<grid, 256, 0, stream>>>(a);

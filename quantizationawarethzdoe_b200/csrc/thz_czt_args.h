@@ -19,4 +19,5 @@ struct ToeplitzGemmArgs {
 };
 
 // tcgen05 / TMEM implementation (thz_czt_tc.cu)
-int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a, cudaStream_t stream);
+// Returns THZ_E_WORKSPACE (without launching) if `pro` is set but no dense scratch buffer is available.
+int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a, void* scratch, cudaStream_t stream);

@@ -36,6 +36,7 @@
 #define TC_KC 16                      // complex k per stage -> 32 real k = one 128-byte swizzle row
 #define TC_STAGES 3
 #define TC_CHUNK 4                    // stages per promotion chunk
+#define TC_PF 3                       // B-tile prefetch distance (stages) in the producers' register ring
 #define TC_A_BYTES (TC_BM * 128)      // 16 KB: 128 rows x 128 B
 #define TC_B_BYTES (2 * TC_BN * 128)  // 16 KB: 128 rows x 128 B
 #define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)   // hi + lo of both operands: 64 KB
@@ -129,7 +130,11 @@ __device__ __forceinline__ float tf32_hi(float x) {
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
-__device__ __forceinline__ void st_split4(unsigned char* hi_tile, unsigned char* lo_tile, uint32_t off, const float (&v)[4]) {
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// hi/lo split of four values and their 16-byte stores into the hi and lo tiles (32-bit shared addresses)
+__device__ __forceinline__ void st_split4(uint32_t hi_tile, uint32_t lo_tile, uint32_t off, const float (&v)[4]) {
     float4 h, l;
     h.x = tf32_hi(v[0]);
     h.y = tf32_hi(v[1]);
@@ -139,8 +144,8 @@ __device__ __forceinline__ void st_split4(unsigned char* hi_tile, unsigned char*
     l.y = v[1] - h.y;
     l.z = v[2] - h.z;
     l.w = v[3] - h.w;
-    *reinterpret_cast<float4*>(hi_tile + off) = h;
-    *reinterpret_cast<float4*>(lo_tile + off) = l;
+    sts128(hi_tile + off, h);
+    sts128(lo_tile + off, l);
 }
 __device__ __forceinline__ int wrap_mod(long long v, int L) {
     v %= L;
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
         const int ptid = tid - TC_ACC_WARPS * 32;                  // 0..255
         const cpx* g = a.g + (size_t)b * a.L;
         const cpx* Bb = a.B + (size_t)b * a.sb_b;
-        const cpx* Pb = a.pro ? a.pro + (size_t)b * a.sb_b : nullptr;
+        // (the prologue factor `pro` has been folded into B by thz_k_cmul before this kernel runs)
         // A items: (row r = item & 127, k-chunk c = item >> 7), two per thread; Toeplitz index tracked incrementally
         int aidx[2];
 #pragma unroll
@@ -195,10 +200,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
         // B item: (column r = ptid & 63, k-chunk c = ptid >> 6), one per thread
         const int bn = ptid & 63, bc = ptid >> 6;
         const int n = n0 + bn;
-        // Register-level software pipeline: the global loads of stage kb+1 are issued before stage kb is converted
-        // and stored, so their latency is hidden behind the wait for a free smem stage and the split/store work.
-        cpx ga[2][4], gb[4], gp[4];
-        auto load_stage = [&](int kb, cpx (&A)[2][4], cpx (&Bv)[4], cpx (&Pv)[4]) {
+        // Register-level software pipeline: the B-tile loads (L2 / HBM latency) run TC_PF stages ahead of their
+        // use, the Toeplitz gathers (L1 / L2) one stage ahead, so that neither is on the per-stage critical path.
+        const uint32_t tiles_s = smem_u32(tiles);
+        cpx ga[4 * 2], na[4 * 2];
+        cpx gb[TC_PF][4];
+        auto load_a = [&](int kb, cpx (&A)[8]) {
             const int k0 = kb * TC_KC;
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int k = k0 + 4 * c + e;
-                    A[it][e] = (m < a.M && k < a.K) ? __ldg(g + idx) : cmake(0.f, 0.f);
+                    A[4 * it + e] = (m < a.M && k < a.K) ? __ldg(g + idx) : cmake(0.f, 0.f);
                     idx += a.sk;
                     if (idx >= a.L) idx -= a.L;
                     if (idx < 0) idx += a.L;
@@ -216,66 +223,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
                 aidx[it] += kstep;
                 if (aidx[it] >= a.L) aidx[it] -= a.L;
             }
+        };
+        auto load_b = [&](int kb, cpx (&Bv)[4]) {
+            const int k0 = kb * TC_KC;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int k = k0 + 4 * bc + e;
-                Bv[e] = cmake(0.f, 0.f);
-                Pv[e] = cmake(1.f, 0.f);
-                if (k < a.K && n < a.N) {
-                    const size_t o = (size_t)k * a.sb_k + (size_t)n * a.sb_n;
-                    Bv[e] = Bb[o];
-                    if (Pb) Pv[e] = __ldg(Pb + o);
-                }
+                Bv[e] = (kb < KB && k < a.K && n < a.N) ? Bb[(size_t)k * a.sb_k + (size_t)n * a.sb_n] : cmake(0.f, 0.f);
             }
         };
-        load_stage(0, ga, gb, gp);
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % TC_STAGES, use = kb / TC_STAGES;
-            cpx na[2][4], nb[4], np[4];
-            if (kb + 1 < KB) load_stage(kb + 1, na, nb, np);
-            mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
-            unsigned char* st = tiles + (size_t)s * TC_STAGE_BYTES;
-            unsigned char *Ahi = st, *Alo = st + TC_A_BYTES, *Bhi = st + 2 * TC_A_BYTES, *Blo = st + 2 * TC_A_BYTES + TC_B_BYTES;
-            // ---- A: Toeplitz rows [Tr | Ti]
+        load_a(0, ga);
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int item = ptid + it * 256, r = item & 127, c = item >> 7;
-                float re[4], im[4];
+        for (int d = 0; d < TC_PF; ++d) load_b(d, gb[d]);
+        for (int kb0 = 0; kb0 < KB; kb0 += TC_PF) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    re[e] = ga[it][e].x;
-                    im[e] = a.conj_g ? -ga[it][e].y : ga[it][e].y;
-                }
-                st_split4(Ahi, Alo, sw128(r, c), re);
-                st_split4(Ahi, Alo, sw128(r, 4 + c), im);
-            }
-            // ---- B: rows n -> [Br | -Bi], rows 64+n -> [Bi | Br]
-            {
+            for (int d = 0; d < TC_PF; ++d) {          // unrolled so that the prefetch ring is addressed statically
+                const int kb = kb0 + d;
+                if (kb >= KB) break;
+                const int s = kb % TC_STAGES, use = kb / TC_STAGES;
+                if (kb + 1 < KB) load_a(kb + 1, na);
+                // convert the B values of this stage now (frees their ring slot), then refill the slot TC_PF stages ahead
                 float br[4], bi[4], nbi[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    cpx v = gb[e];
-                    if (Pb) v = a.conj_pro ? cmulc(v, gp[e]) : cmul(v, gp[e]);
+                    const cpx v = gb[d][e];
                     br[e] = v.x;
                     bi[e] = v.y;
                     nbi[e] = -v.y;
                 }
+                load_b(kb + TC_PF, gb[d]);
+                mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
+                const uint32_t st = tiles_s + (uint32_t)(s * TC_STAGE_BYTES);
+                const uint32_t Ahi = st, Alo = st + TC_A_BYTES, Bhi = st + 2 * TC_A_BYTES, Blo = st + 2 * TC_A_BYTES + TC_B_BYTES;
+                // ---- A: Toeplitz rows [Tr | Ti]
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int item = ptid + it * 256, r = item & 127, c = item >> 7;
+                    float re[4], im[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        re[e] = ga[4 * it + e].x;
+                        im[e] = a.conj_g ? -ga[4 * it + e].y : ga[4 * it + e].y;
+                    }
+                    st_split4(Ahi, Alo, sw128(r, c), re);
+                    st_split4(Ahi, Alo, sw128(r, 4 + c), im);
+                }
+                // ---- B: rows n -> [Br | -Bi], rows 64+n -> [Bi | Br]
                 st_split4(Bhi, Blo, sw128(bn, bc), br);
                 st_split4(Bhi, Blo, sw128(bn, 4 + bc), nbi);
                 st_split4(Bhi, Blo, sw128(TC_BN + bn, bc), bi);
                 st_split4(Bhi, Blo, sw128(TC_BN + bn, 4 + bc), br);
-            }
-            fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);
-            if (kb + 1 < KB) {
+                fence_proxy_async();         // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * s);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    ga[0][e] = na[0][e];
-                    ga[1][e] = na[1][e];
-                    gb[e] = nb[e];
-                    gp[e] = np[e];
-                }
+                for (int e = 0; e < 8; ++e) ga[e] = na[e];
             }
         }
     } else if (warp == TC_ACC_WARPS + TC_PROD_WARPS) {
@@ -361,7 +363,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
     if (warp == 0) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
-int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a, cudaStream_t stream) {
+// out[i] = x[i] * p[i]  (or x[i] * conj(p[i])): folds the prologue factor into the B operand once, so that the GEMM
+// producers stream 8 instead of 16 bytes per element (they are latency/L2-bound, see profiles/README.md).
+__global__ void __launch_bounds__(256) thz_k_cmul(const cpx* __restrict__ x, const cpx* __restrict__ p, cpx* __restrict__ out,
+                                                  size_t n, int conj_p) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const cpx a = x[i], b = __ldg(p + i);
+        out[i] = conj_p ? cmulc(a, b) : cmul(a, b);
+    }
+}
+
+int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a_in, void* scratch, cudaStream_t stream) {
+    ToeplitzGemmArgs a = a_in;
+    if (a.pro) {
+        const bool dense = a.sb_b == (long long)a.K * a.N && ((a.sb_k == a.N && a.sb_n == 1) || (a.sb_k == 1 && a.sb_n == a.K));
+        if (!scratch || !dense) return THZ_E_WORKSPACE;      // caller falls back to the CUDA-core kernel
+        const size_t n = (size_t)a.batch * a.K * a.N;
+        size_t blocks = (n + 255) / 256;
+        const size_t cap = (size_t)thz_sm_count() * 16;
+        thz_launch_begin(stream, THZ_KC_CZT);
+        thz_k_cmul<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, stream>>>(a.B, a.pro, (cpx*)scratch, n, a.conj_pro);
+        thz_launch_end(stream, THZ_KC_CZT);
+        a.B = (const cpx*)scratch;
+        a.pro = nullptr;
+    }
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return thz_set_cuda_error("cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc)", e);

@@ -360,6 +360,7 @@ def fft2_c2c(x, inverse=False, ortho=False):
 
 # ----------------------------------------------------------------------------- chirp-z propagation
 def _toeplitz_gemm(batch, M, N_, K, g, L, off, sm, sk, conj_g, B, sb, pro, conj_pro, C, sc, epi, conj_epi, device):
+    scratch = _workspace(batch * K * N_, device) if pro is not None else None
     d = N.ToeplitzGemmDesc()
     d.batch, d.M, d.N, d.K = batch, M, N_, K
     d.g, d.L, d.off, d.sm, d.sk = N.ptr(g), L, off, sm, sk
@@ -368,6 +369,7 @@ def _toeplitz_gemm(batch, M, N_, K, g, L, off, sm, sk, conj_g, B, sb, pro, conj_
     d.pro = N.ptr(pro)
     d.C, (d.sc_b, d.sc_m, d.sc_n) = N.ptr(C), sc
     d.epi = N.ptr(epi)
+    d.scratch = N.ptr(scratch)
     N.check(N.lib().thz_toeplitz_gemm(ctypes.byref(d), N.current_stream_ptr(device)), "thz_toeplitz_gemm")
 
 
