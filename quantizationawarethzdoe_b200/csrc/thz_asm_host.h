@@ -55,7 +55,7 @@ static inline uint64_t thz_asm_ws_bytes(const thz_asm_desc* d) {
 }
 
 
-static inline bool thz_is_p2_size(int n) { return n >= THZ_P2_MIN && n <= THZ_P2_MAX && (n & (n - 1)) == 0; }
+static inline bool thz_is_p2_size(int n) { return thz_sp_instantiated(n); }
 
 static inline int thz_p2_row_lines_rt(int n) { return p2_row_lines(n); }
 static inline int thz_p2_row_threads_rt(int n) { return p2_row_threads(n); }

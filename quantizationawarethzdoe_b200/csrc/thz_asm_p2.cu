@@ -151,6 +151,12 @@ static int set_smem_p2(K kernel, size_t bytes) {
         THZ_P2_CASE(KERN, 4096, cls, grid, block, smem, stream, args)                    \
         THZ_P2_CASE(KERN, 8192, cls, grid, block, smem, stream, args)                    \
         THZ_P2_CASE(KERN, 16384, cls, grid, block, smem, stream, args)                   \
+        THZ_P2_CASE(KERN, 400, cls, grid, block, smem, stream, args)                     \
+        THZ_P2_CASE(KERN, 800, cls, grid, block, smem, stream, args)                     \
+        THZ_P2_CASE(KERN, 1600, cls, grid, block, smem, stream, args)                    \
+        THZ_P2_CASE(KERN, 2000, cls, grid, block, smem, stream, args)                    \
+        THZ_P2_CASE(KERN, 3200, cls, grid, block, smem, stream, args)                    \
+        THZ_P2_CASE(KERN, 4000, cls, grid, block, smem, stream, args)                    \
     default:                                                                             \
         return thz_set_error(THZ_E_UNSUPPORTED, "power-of-two fast path: size not instantiated"); \
     }                                                                                    \

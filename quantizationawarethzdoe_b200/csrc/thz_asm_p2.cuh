@@ -13,12 +13,19 @@
 #include "thz_asm.cuh"
 #include "thz_fft_p2.cuh"
 
-#define THZ_P2_MIN 256
-#define THZ_P2_MAX 16384
+// lengths with a compiled static path: powers of two 256 .. 16384 and the multiples of 16 of the form 25*16*2^a / 25*20*4*2^a
+// that the BASELINE configs and the reference notebooks produce (200 -> 400, 1000 -> 2000, ...)
+#define THZ_SP_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384) X(400) X(800) X(1600) X(2000) X(3200) X(4000)
+THZ_HD constexpr bool thz_sp_instantiated(int n) {
+#define THZ_SP_CMP(NN) if (n == NN) return true;
+    THZ_SP_SIZES(THZ_SP_CMP)
+#undef THZ_SP_CMP
+    return false;
+}
 
 THZ_HD constexpr int p2_row_lines(int N) { return N >= 4096 ? 1 : 4096 / N; }        // lines per CTA, row kernels
 THZ_HD constexpr int p2_row_threads(int N) { return N >= 8192 ? 512 : 256; }
-THZ_HD constexpr int p2_col_cols(int N) { return N >= 16384 ? 1 : (N >= 4096 ? 2 : (N >= 2048 ? 4 : (N >= 1024 ? 8 : 16))); }
+THZ_HD constexpr int p2_col_cols(int N) { return N > 8192 ? 1 : (N > 2048 ? 2 : (N > 1024 ? 4 : (N > 512 ? 8 : 16))); }
 THZ_HD constexpr int p2_col_threads(int N) { return N >= 8192 ? 512 : 256; }
 THZ_HD constexpr int p2_pitch(int N) { return N + (N >> 4); }
 // the software pipelines of the row kernels need extra shared memory; 16384-point lines do without

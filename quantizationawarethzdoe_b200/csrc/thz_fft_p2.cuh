@@ -14,8 +14,15 @@
 #include "thz_fft.cuh"
 
 // ---------------------------------------------------------------- compile-time plan (mirrors thz_make_plan)
+// (the name p2_* is historical: the same machinery serves every length whose plan keeps the padded-slot offsets
+//  of a butterfly compile-time constants, see sp_static_ok below -- powers of two and e.g. 400 = 25*16, 2000 = 25*20*4)
 THZ_HD constexpr int p2_pick(int rem) {
-    return (rem >= 256 || rem == 16) ? 16 : (rem == 128 ? 16 : (rem == 64 ? 8 : (rem == 32 ? 8 : rem)));
+    if ((rem & (rem - 1)) == 0)
+        return (rem >= 256 || rem == 16) ? 16 : (rem == 128 ? 16 : (rem == 64 ? 8 : (rem == 32 ? 8 : rem)));
+    constexpr int cand[14] = {25, 20, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    for (int i = 0; i < 14; ++i)
+        if (rem % cand[i] == 0) return cand[i];
+    return rem;
 }
 THZ_HD constexpr int p2_L(int N, int s) {   // block length entering stage s
     int rem = N;
@@ -39,8 +46,21 @@ THZ_HD constexpr int p2_log2(int v) {
 // slot offset of element t of a butterfly with sub-block length M (relative to the slot of element 0)
 THZ_HD constexpr int p2_coff(int M, int t) { return t * M + ((t * M) >> 4); }
 
+// A length can use the static path iff, in every stage, the padded slot of element t of a butterfly is
+// slot(element 0) + a constant: that needs  (p0 & 15) + ((t M) & 15) < 16  for every butterfly, which holds when the
+// block length L and the sub-block length M are each a multiple of 16 or a divisor of 16.
+THZ_HD constexpr bool sp_len_ok(int v) { return (v % 16 == 0) || (v < 16 && 16 % v == 0); }
+THZ_HD constexpr bool sp_static_ok(int N) {
+    for (int s = 0; s < p2_stages(N); ++s) {
+        const int L = p2_L(N, s), R = p2_radix(N, s);
+        if (R > 25 || !sp_len_ok(L) || !sp_len_ok(L / R)) return false;
+    }
+    return p2_stages(N) >= 2;
+}
+
 template <int N, int S>
 struct P2Stage {
+    static_assert(sp_static_ok(N), "length cannot use the static-offset FFT path");
     static constexpr int R = p2_radix(N, S);
     static constexpr int L = p2_L(N, S);
     static constexpr int M = L / R;

@@ -197,6 +197,12 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
     case 4096: FN<4096>(__VA_ARGS__); break;         \
     case 8192: FN<8192>(__VA_ARGS__); break;         \
     case 16384: FN<16384>(__VA_ARGS__); break;       \
+    case 400: FN<400>(__VA_ARGS__); break;           \
+    case 800: FN<800>(__VA_ARGS__); break;           \
+    case 1600: FN<1600>(__VA_ARGS__); break;         \
+    case 2000: FN<2000>(__VA_ARGS__); break;         \
+    case 3200: FN<3200>(__VA_ARGS__); break;         \
+    case 4000: FN<4000>(__VA_ARGS__); break;         \
     default: return THZ_E_UNSUPPORTED;               \
     }
 

@@ -59,6 +59,10 @@ CASES = [
     (1, 1, 128, 1024, None, [1e-3], 0.5e-3, 0.1, {}),                                    # 256 x 2048, in-register H
     (1, 1, 100, 128, None, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                           # mixed: generic rows (200) + p2 cols
     (3, 1, 256, 256, None, [1e-3], 0.5e-3, 0.1, dict(mode=1, unpad=False, chunk=2)),     # 512 x 512 padded output, chunks
+    # static path for mixed-radix lengths whose slot offsets stay compile-time constants
+    (2, 1, 200, 200, None, [1e-3], 0.5e-3, 0.05, {}),                                    # 400 x 400 = (25*16)^2, in-register H
+    (1, 1, 1000, 128, None, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                          # 2000 (25*20*4) x 256
+    (1, 2, 128, 400, None, [1e-3, 1.1e-3], 0.5e-3, 0.1, dict(mode=1)),                   # 256 x 800 (25*16*2)
 ]
 
 
@@ -106,6 +110,7 @@ def test_in_register_mask_is_bit_exact():
     (3, 2, 128, 256, None, 1, 148, 0),    # power-of-two fast path: 256 x 512
     (3, 2, 128, 256, None, 1, 2, 4),      # same, few SMs (one CTA walks several fields) and chunks (atomic gh)
     (1, 1, 512, 128, None, 0, 148, 0),    # 1024 x 256
+    (3, 1, 200, 200, None, 1, 148, 0),    # 400 x 400 static mixed-radix path (DONN layer size), DOE fwd + adjoint
 ])
 def test_doe_fused_forward_and_adjoint_replay(B, C, H, W, scale, mode, sm, chunk):
     lams = [1e-3, 1.02e-3, 1.05e-3][:C]
