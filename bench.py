@@ -177,11 +177,13 @@ def run_ours(args, rank, local_rank, world):
     asm = ASM_prop(z_distance=Z, device=dev, kernel_mode=os.environ.get("THZ_KERNEL_MODE", "inregister"))
     asm.check_Zc = False
     x_dev = x_host.to(dev).requires_grad_(True)
+    lam_t = torch.tensor(lams, dtype=torch.float32, device=dev)        # built once: the modules key their plans on these objects
+    sp_t = torch.tensor([SPACING, SPACING], dtype=torch.float32, device=dev)
     gw_host = torch.empty(1, 1, n, n, dtype=torch.float32).pin_memory()
 
     def step(x):
         """One hot-path pass; returns the gradient wrt the DOE weights (all-reduced when world > 1)."""
-        field = ElectricField(x, wavelengths=lams, spacing=SPACING, device=dev)
+        field = ElectricField(x, wavelengths=lam_t, spacing=sp_t, device=dev)
         y = asm(doe(field)).data
         gx, gw = torch.autograd.grad(y, (x, doe.weight_height_map), y.detach())
         if world > 1:
@@ -242,7 +244,7 @@ def run_ours(args, rank, local_rank, world):
                     bufs[b ^ 1].copy_(x_host, non_blocking=True)
                     ready[b ^ 1].record(copy_stream)
             cur.wait_event(ready[b])
-            gw = step(bufs[b].requires_grad_(True))
+            gw = step(bufs[b].detach().requires_grad_(True))     # fresh leaf over the same storage
             freed[b].record(cur)
             gw_host.copy_(gw, non_blocking=True)
         cur.synchronize()

@@ -86,14 +86,21 @@ class DOELayer(nn.Module):
         return NotImplemented
 
     def _coef(self, wavelengths, epsilon, tand, device):
-        key = (tuple(torch.as_tensor(wavelengths).detach().cpu().reshape(-1).tolist()), float(epsilon), float(tand), str(device))
+        """Per-wavelength coefficient table on the device, cached per (tensor objects, in-place versions) so that a
+        steady-state forward does no device->host read."""
+        def tok(t):
+            return (id(t), t._version) if torch.is_tensor(t) else ("py", t)
+        fast = (tok(wavelengths), tok(epsilon), tok(tand), str(device))
         cache = self.__dict__.setdefault("_coef_cache", {})
-        c = cache.get(key)
-        if c is None:
-            c = AH.doe_coefficients(wavelengths, epsilon, tand).to(device)
-            cache.clear()
-            cache[key] = c
-        return c
+        if cache.get("fast") == fast:
+            return cache["coef"]
+        key = (tuple(torch.as_tensor(wavelengths).detach().cpu().reshape(-1).tolist()), float(epsilon), float(tand), str(device))
+        if cache.get("key") != key:
+            cache["coef"] = AH.doe_coefficients(wavelengths, epsilon, tand).to(device)
+            cache["key"] = key
+        cache["fast"] = fast
+        cache["refs"] = (wavelengths, epsilon, tand)
+        return cache["coef"]
 
     def modulate(self, input_field, preprocessed_height_map, height_tolerance, epsilon, tand):
         """Components/QuantizedDOE.py:92-126, deferred (see module docstring)."""

@@ -108,9 +108,15 @@ class ASM_prop(nn.Module):
         self._z = z
 
     def _z_f32(self):
+        """z as an fp32 host scalar.  Reading a CUDA tensor synchronises, so the value is cached per
+        (tensor object, in-place version)."""
         z = self._z
         if isinstance(z, torch.Tensor):
-            return z.detach().to("cpu", torch.float32).reshape(())
+            tok = (id(z), z._version)
+            if getattr(self, "_z_tok", None) != tok:
+                self._z_host = z.detach().to("cpu", torch.float32).reshape(())
+                self._z_tok = tok
+            return self._z_host
         return torch.tensor(float(z), dtype=torch.float32)
 
     def create_kernel(self, field):
@@ -126,6 +132,13 @@ class ASM_prop(nn.Module):
     # ---- plan cache ------------------------------------------------------------------------
     def _get_plan(self, B, C, H, W, spacing, wavelengths, device):
         z = self._z_f32()
+        # fast path: same tensor objects (unchanged in place) as last time -> same plan, no device->host reads
+        fast = (id(spacing), spacing._version, id(wavelengths), wavelengths._version, C, H, W, float(z), str(device),
+                self.do_padding, self.do_unpad_after_pad, self.bandlimit_kernel, self.bandlimit_type, self.kernel_mode,
+                id(self.padding_scale))
+        if self._plan is not None and getattr(self, "_fast_key", None) == fast:
+            self._plan.B = B
+            return self._plan
         key = (C, H, W, tuple(spacing.detach().cpu().reshape(-1).tolist()),
                tuple(wavelengths.detach().cpu().reshape(-1).tolist()), float(z), str(device),
                self.do_padding, self.do_unpad_after_pad,
@@ -154,6 +167,8 @@ class ASM_prop(nn.Module):
             unpad = bool(self.do_padding and self.do_unpad_after_pad)
             self._plan = Fn.AsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, mode)
             self._plan_key = key
+        self._fast_key = fast
+        self._fast_refs = (spacing, wavelengths)      # keep the keyed tensors alive so their ids stay unique
         self._plan.B = B
         return self._plan
 

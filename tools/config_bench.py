@@ -41,9 +41,10 @@ def donn():
     for a in asms:
         a.check_Zc = False
     x = torch.randn(B, 1, n, n, dtype=torch.complex64, device=dev)
+    lam_t, sp_t = torch.tensor([1 * mm], device=dev), torch.tensor([0.5 * mm, 0.5 * mm], device=dev)
 
     def step():
-        f = ElectricField(x, wavelengths=[1 * mm], spacing=0.5 * mm, device=dev)
+        f = ElectricField(x, wavelengths=lam_t, spacing=sp_t, device=dev)
         for d, a in zip(does, asms):
             f = a(d(f))
         y = f.data
@@ -61,9 +62,10 @@ def c2():
     asm = ASM_prop(z_distance=0.1, device=dev)
     asm.check_Zc = False
     x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+    lam_t, sp_t = torch.tensor([1 * mm], device=dev), torch.tensor([0.5 * mm, 0.5 * mm], device=dev)
 
     def step():
-        y = asm(doe(ElectricField(x, wavelengths=[1 * mm], spacing=0.5 * mm, device=dev))).data
+        y = asm(doe(ElectricField(x, wavelengths=lam_t, spacing=sp_t, device=dev))).data
         torch.autograd.grad(y, doe.weight_height_map, y.detach())
 
     ms = timeit(step, reps=50)
