@@ -285,11 +285,21 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
-    achieved = BYTES_PER_SAMPLE * (B * C * Np * Np) / (ms_step * 1e-3) / 1e9      # per GPU
+    step_achieved = BYTES_PER_SAMPLE * (B * C * Np * Np) / (ms_step * 1e-3) / 1e9      # per GPU, whole step
     dom = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kernels else None
     for ent in (kernels or {}).values():
         if "achieved_gbs" in ent:
             ent["frac"] = ent["achieved_gbs"] / peak
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (scaled to this launch size)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k2_dram_traffic.json")) as f:
+            t = json.load(f)
+        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * (B * C) / t["fields_per_launch"]
+    except Exception:
+        pass
+    dk = (kernels or {}).get(dom, {})
+    dom_alg_bytes = 16.0 * n * Np * B * C                  # column pass: read + write of the live rows, per launch
     cpu_val, cpu_t = (None, None)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -311,10 +321,15 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": gw_host.numel() * 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_sample": BYTES_PER_SAMPLE,
-                     "scope": "whole step (6 FFT-pipeline launches + 2 level-selection launches), per GPU",
-                     "dominant_kernel": dom, "kernels": kernels},
+        # dominant kernel (the column pass K2): algorithmic bytes per launch / its mean launch duration (CUDA events on the
+        # launching stream); `step` = the whole hot path at SURVEY 8d's 42 B per padded sample.
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": dk.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
+                     "frac": dk.get("frac"), "traffic": traffic, "algorithmic_bytes_per_launch": dom_alg_bytes,
+                     "launch_ms": (dk.get("ms_per_step") / dk.get("launches_per_step")) if dk else None,
+                     "peak_source": peak_src,
+                     "step": {"achieved": step_achieved, "frac": step_achieved / peak, "bytes_per_sample": BYTES_PER_SAMPLE,
+                              "scope": "whole step: 6 FFT-pipeline launches + 2 level-selection launches, per GPU"},
+                     "kernels": kernels},
         "fields_per_s": value * 1e6 / (Np * Np),
     }
     if cpu:

@@ -46,8 +46,8 @@ THZ_HD cpx thz_doe_phase(float h, float4 cf, float base) {
     const float la = thz_mul_rn(thz_mul_rn(thz_mul_rn(thz_mul_rn(-0.5f, cf.x), hb), cf.y), cf.z);
     const float ph = thz_mul_rn(thz_mul_rn(-cf.x, hb), cf.w);
     float sn, cs;
-    thz_sincos(ph, &sn, &cs);
-    const float a = expf(la);
+    thz_sincos_fast(ph, &sn, &cs);      // |ph| is a few tens of radians: exact 2 pi reduction + SFU, abs error ~4e-7
+    const float a = thz_exp_fast(la);
     return cmake(a * cs, a * sn);
 }
 
