@@ -327,3 +327,40 @@ def test_czt_tensor_core_kernel_agrees_with_cuda_core_kernel(dev, monkeypatch):
         f = ElectricField(x, wavelengths=[1 * mm, 1.05 * mm], spacing=0.5 * mm, device=dev)
         outs[impl] = czt(f, 512, 512, 0.1 * mm, 0.1 * mm).data
     assert rel_l2(outs["tc"].cpu(), outs["simt"].cpu()) < 5e-6     # each is ~2e-6 from a float64 evaluation
+
+
+def test_step_is_cuda_graph_capturable(dev):
+    """The whole optimisation step (DOE level selection -> fused DOE+ASM forward -> loss gradient -> adjoint ->
+    weight gradient) makes no host synchronisation and allocates only through torch, so it can be captured
+    in a CUDA graph and replayed: replay reproduces the eager gradient bit for bit."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, STEQuantizedDOELayer
+    n = 256
+    torch.manual_seed(0)
+    doe = STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=0.5 * mm, doe_level=8, height_constraint_max=1 * mm, tolerance=None,
+                                    material=[2.66, 0.003]), {}, device=dev)
+    asm = ASM_prop(z_distance=0.1, device=dev)
+    asm.check_Zc = False
+    x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+    lam_t, sp_t = torch.tensor([1 * mm], device=dev), torch.tensor([0.5 * mm, 0.5 * mm], device=dev)
+
+    def step():
+        y = asm(doe(ElectricField(x, wavelengths=lam_t, spacing=sp_t, device=dev))).data
+        (gw,) = torch.autograd.grad(y, doe.weight_height_map, y.detach())
+        return gw
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            eager = step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        static_gw = step()
+    with torch.no_grad():
+        doe.weight_height_map.add_(0.25)          # new weights: the replay must see them
+    g.replay()
+    torch.cuda.synchronize()
+    fresh = step()
+    assert torch.equal(static_gw, fresh)
+    assert not torch.equal(static_gw, eager)
