@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
         __syncthreads();                      // rows of field f have landed; the other buffer is free (its epilogue ran)
         if (f + 1 < f_hi) p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, tid, nt);
         thz_cp_async_commit();
+        p2k3_prefetch_epilogue<N>(a, bx, f, tid, nt);
         inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, tid, nt, a.tw);
         p2k3_last<N, NACC>(a, sc, bx, f, tid, nt, acc);
     }

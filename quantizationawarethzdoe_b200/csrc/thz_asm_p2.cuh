@@ -305,6 +305,28 @@ struct K3Storer {
     }
 };
 
+// DOE adjoint only: ask the L2 for the saved-field and height-map sectors this thread's epilogue will read, three FFT
+// stages before it reads them (one request per 32-byte sector), so that those loads find L2 instead of HBM latency.
+template <int N>
+THZ_HD void p2k3_prefetch_epilogue(const RowInvArgs& a, int bx, int f, int tid, int nt) {
+    if (!a.doe.hmap) return;
+    constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, R = P2Stage<N, 0>::R, M = P2Stage<N, 0>::M;
+    for (int w = tid; w < LINES * NB; w += nt) {
+        const int line = w / NB, j = w % NB;
+        const int r = bx * LINES + line;
+        if (r >= a.outH) break;
+        const cpx* xrow = a.xsaved + ((size_t)f * a.outH + r) * a.outW;
+        const float* hrow = a.doe.hmap + (size_t)r * a.outW;
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const int c = j + t * M - a.out_c0;
+            if (c < 0 || c >= a.outW) continue;
+            if ((c & 3) == 0) thz_prefetch_l2(xrow + c);
+            if ((c & 7) == 0) thz_prefetch_l2(hrow + c);
+        }
+    }
+}
+
 // inverse stage 0 + crop + scale + epilogue for field f; acc has p2k3_acc<N>() entries
 template <int N, int NACC>
 THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, int bx, int f, int tid, int nt, float (&acc)[NACC]) {
