@@ -150,6 +150,7 @@ extern "C" int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* d, void* stream_)
     a.sc_n = d->sc_n;
     a.epi = (const cpx*)d->epi;
     a.conj_epi = d->conj_epi;
+    { const char* dbg = getenv("THZ_CZT_DEBUG"); a.debug_mode = dbg ? atoi(dbg) : 0; }
     // implementation choice: tcgen05 3xTF32 tensor-core kernel unless THZ_CZT_IMPL=simt asks for the CUDA-core one
     const char* impl = getenv("THZ_CZT_IMPL");
     if (!(impl && strcmp(impl, "simt") == 0)) {

@@ -16,6 +16,7 @@ struct ToeplitzGemmArgs {
     long long sc_b, sc_m, sc_n;
     const cpx* epi;           // optional epilogue factor, same indexing as C
     int conj_epi;
+    int debug_mode;           // 0 normal; 1 producers skip the smem stores; 2 MMA warp skips the MMAs (bottleneck experiments)
 };
 
 // tcgen05 / TMEM implementation (thz_czt_tc.cu)

@@ -36,10 +36,17 @@
 #define TC_KC 16                      // complex k per stage -> 32 real k = one 128-byte swizzle row
 #define TC_STAGES 3
 #define TC_CHUNK 4                    // stages per promotion chunk
-#define TC_PF 3                       // B-tile prefetch distance (stages) in the producers' register ring
-#define TC_A_BYTES (TC_BM * 128)      // 16 KB: 128 rows x 128 B
+#define TC_PF 3                       // prefetch distance (stages) of the producers' cp.async raw ring
 #define TC_B_BYTES (2 * TC_BN * 128)  // 16 KB: 128 rows x 128 B
-#define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)   // hi + lo of both operands: 64 KB
+#define TC_STAGE_BYTES (2 * TC_B_BYTES)                    // hi + lo of the B operand: 32 KB per stage
+// The Toeplitz operand is a sliding window: T(m0+r, k0+kk) = g[off + sm (m0 + rho) + sk kk] depends on r and k0 only
+// through rho = r - k0 (sm = -sk), so the A tile of stage kb is rows [-16 kb, -16 kb + 128) of ONE strip and each new
+// stage adds just 16 rows.  The strip lives in a circular buffer of TC_AW rows, stored twice (row i and i + TC_AW), so
+// that every 128-row window is contiguous for the UMMA descriptor.
+#define TC_AW 192                                          // window rows kept: 128 + 16 * 4 stages of slack
+#define TC_AS_BYTES (2 * TC_AW * 128)                      // one mirrored strip (hi or lo): 48 KB
+#define TC_SMEM_BYTES (2 * TC_AS_BYTES + TC_STAGES * TC_STAGE_BYTES)   // 96 KB + 96 KB
+#define TC_RAW_BYTES ((256 + 64) * 32)                     // raw (unconverted) cp.async landing slots of one stage: 10 KB
 #define TC_ACC_WARPS 8
 #define TC_PROD_WARPS 8
 #define TC_THREADS ((TC_ACC_WARPS + TC_PROD_WARPS + 1) * 32)
@@ -147,12 +154,40 @@ __device__ __forceinline__ void st_split4(uint32_t hi_tile, uint32_t lo_tile, ui
     sts128(hi_tile + off, h);
     sts128(lo_tile + off, l);
 }
+__device__ __forceinline__ void split4(float4 v, float4& h, float4& l) {
+    h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+__device__ __forceinline__ float4 neg4(float4 v) { return make_float4(-v.x, -v.y, -v.z, -v.w); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, cpx v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ int wrap_mod(long long v, int L) {
     v %= L;
     return (int)(v < 0 ? v + L : v);
 }
 
 // ------------------------------------------------------------------------------- kernel
+// Debug timeline (THZ_CZT_DEBUG=3): clock64 stamps of CTA (0,0,0): [role][stage or chunk][point]
+#define TC_TL_N 256
+__device__ long long g_tc_timeline[3][TC_TL_N][4];
+#define TC_STAMP(role, idx, pt)                                                                          \
+    do {                                                                                                 \
+        if (tl && (idx) < TC_TL_N) g_tc_timeline[role][idx][pt] = clock64();                             \
+    } while (0)
 __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __grid_constant__ ToeplitzGemmArgs a) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 4];
@@ -180,6 +215,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_holder;
+    const bool tl = a.debug_mode == 3 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == TC_ACC_WARPS || warp == TC_ACC_WARPS + TC_PROD_WARPS);
     const int KB = (a.K + TC_KC - 1) / TC_KC;
     const int NC = (KB + TC_CHUNK - 1) / TC_CHUNK;
 
@@ -189,97 +225,125 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
         const cpx* g = a.g + (size_t)b * a.L;
         const cpx* Bb = a.B + (size_t)b * a.sb_b;
         // (the prologue factor `pro` has been folded into B by thz_k_cmul before this kernel runs)
-        // A items: (row r = item & 127, k-chunk c = item >> 7), two per thread; Toeplitz index tracked incrementally
-        int aidx[2];
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int item = ptid + it * 256, r = item & 127, c = item >> 7;
-            aidx[it] = wrap_mod((long long)a.off + (long long)a.sm * (m0 + r) + (long long)a.sk * (4 * c), a.L);
-        }
-        const int kstep = wrap_mod((long long)a.sk * TC_KC, a.L);
-        // B item: (column r = ptid & 63, k-chunk c = ptid >> 6), one per thread
+        // B item: (column bn = ptid & 63, k-chunk bc = ptid >> 6), one per thread and stage
         const int bn = ptid & 63, bc = ptid >> 6;
         const int n = n0 + bn;
-        // Register-level software pipeline: the B-tile loads (L2 / HBM latency) run TC_PF stages ahead of their
-        // use, the Toeplitz gathers (L1 / L2) one stage ahead, so that neither is on the per-stage critical path.
         const uint32_t tiles_s = smem_u32(tiles);
-        cpx ga[4 * 2], na[4 * 2];
-        cpx gb[TC_PF][4];
-        auto load_a = [&](int kb, cpx (&A)[8]) {
-            const int k0 = kb * TC_KC;
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int item = ptid + it * 256, r = item & 127, c = item >> 7;
-                const int m = m0 + r;
-                int idx = aidx[it];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k0 + 4 * c + e;
-                    A[4 * it + e] = (m < a.M && k < a.K) ? __ldg(g + idx) : cmake(0.f, 0.f);
-                    idx += a.sk;
-                    if (idx >= a.L) idx -= a.L;
-                    if (idx < 0) idx += a.L;
-                }
-                aidx[it] += kstep;
-                if (aidx[it] >= a.L) aidx[it] -= a.L;
-            }
-        };
-        auto load_b = [&](int kb, cpx (&Bv)[4]) {
-            const int k0 = kb * TC_KC;
+        const uint32_t Ahi = tiles_s, Alo = tiles_s + TC_AS_BYTES, Bst0 = tiles_s + 2 * TC_AS_BYTES;
+        // strip entry (rho, kk) = g[(off + sm (m0 + rho) + sk kk) mod L]; one item = 4 consecutive kk of one strip row,
+        // written as a real chunk and an imaginary chunk, hi and lo, into both mirror images of the circular buffer
+        auto strip_load = [&](int rho, int c, cpx (&gv)[4]) {
+            int idx = wrap_mod((long long)a.off + (long long)a.sm * (m0 + rho) + (long long)a.sk * (4 * c), a.L);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int k = k0 + 4 * bc + e;
-                Bv[e] = (kb < KB && k < a.K && n < a.N) ? Bb[(size_t)k * a.sb_k + (size_t)n * a.sb_n] : cmake(0.f, 0.f);
+                gv[e] = __ldg(g + idx);
+                idx += a.sk;
+                if (idx >= a.L) idx -= a.L;
+                if (idx < 0) idx += a.L;
             }
         };
-        load_a(0, ga);
+        auto strip_store = [&](int rho, int c, const cpx (&gv)[4]) {
+            int row = rho % TC_AW;
+            if (row < 0) row += TC_AW;
+            float re[4], im[4];
 #pragma unroll
-        for (int d = 0; d < TC_PF; ++d) load_b(d, gb[d]);
-        for (int kb0 = 0; kb0 < KB; kb0 += TC_PF) {
+            for (int e = 0; e < 4; ++e) {
+                re[e] = gv[e].x;
+                im[e] = a.conj_g ? -gv[e].y : gv[e].y;
+            }
 #pragma unroll
-            for (int d = 0; d < TC_PF; ++d) {          // unrolled so that the prefetch ring is addressed statically
-                const int kb = kb0 + d;
-                if (kb >= KB) break;
-                const int s = kb % TC_STAGES, use = kb / TC_STAGES;
-                if (kb + 1 < KB) load_a(kb + 1, na);
-                // convert the B values of this stage now (frees their ring slot), then refill the slot TC_PF stages ahead
-                float br[4], bi[4], nbi[4];
+            for (int copy = 0; copy < 2; ++copy) {
+                st_split4(Ahi, Alo, sw128(row + copy * TC_AW, c), re);
+                st_split4(Ahi, Alo, sw128(row + copy * TC_AW, 4 + c), im);
+            }
+        };
+        // initial window: rows rho = 0 .. 127 (512 items, two per thread)
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int item = ptid + it * 256;
+            cpx gv[4];
+            strip_load(item & 127, item >> 7, gv);
+            strip_store(item & 127, item >> 7, gv);
+        }
+        // Per stage every thread owns one B item (4 complex values) and, for threads 0..63, one item of the 16 strip rows
+        // rho = -16 (kb+1) .. -16 (kb+1) + 15 that enter the window with stage kb + 1.  Both are fetched with cp.async
+        // into a private 32-byte slot of a TC_PF-deep raw ring (cp.async groups complete in order per thread, which a
+        // register prefetch ring does not guarantee: loads sharing a scoreboard would serialise on the newest one).
+        const bool a_worker = ptid < 64;
+        const int a_r = ptid & 15, a_c = (ptid >> 4) & 3;
+        const uint32_t raw0 = tiles_s + TC_SMEM_BYTES;
+        const uint32_t rawB = raw0 + (uint32_t)ptid * 32u, rawA = raw0 + 256u * 32u + (uint32_t)ptid * 32u;
+        auto issue = [&](int kb) {
+            if (kb < KB) {
+                const uint32_t slot = (uint32_t)(kb % TC_PF) * TC_RAW_BYTES;
+                const int k0 = kb * TC_KC + 4 * bc;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const cpx v = gb[d][e];
-                    br[e] = v.x;
-                    bi[e] = v.y;
-                    nbi[e] = -v.y;
+                    const int k = k0 + e;
+                    if (k < a.K && n < a.N)
+                        cp_async8(rawB + slot + 8u * e, Bb + (size_t)k * a.sb_k + (size_t)n * a.sb_n);
+                    else
+                        sts64(rawB + slot + 8u * e, cmake(0.f, 0.f));
                 }
-                load_b(kb + TC_PF, gb[d]);
-                mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
-                const uint32_t st = tiles_s + (uint32_t)(s * TC_STAGE_BYTES);
-                const uint32_t Ahi = st, Alo = st + TC_A_BYTES, Bhi = st + 2 * TC_A_BYTES, Blo = st + 2 * TC_A_BYTES + TC_B_BYTES;
-                // ---- A: Toeplitz rows [Tr | Ti]
-#pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const int item = ptid + it * 256, r = item & 127, c = item >> 7;
-                    float re[4], im[4];
+                if (a_worker && kb + 1 < KB) {
+                    int idx = wrap_mod((long long)a.off + (long long)a.sm * (m0 - TC_KC * (kb + 1) + a_r) + (long long)a.sk * (4 * a_c), a.L);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        re[e] = ga[4 * it + e].x;
-                        im[e] = a.conj_g ? -ga[4 * it + e].y : ga[4 * it + e].y;
+                        cp_async8(rawA + slot + 8u * e, g + idx);
+                        idx += a.sk;
+                        if (idx >= a.L) idx -= a.L;
+                        if (idx < 0) idx += a.L;
                     }
-                    st_split4(Ahi, Alo, sw128(r, c), re);
-                    st_split4(Ahi, Alo, sw128(r, 4 + c), im);
                 }
-                // ---- B: rows n -> [Br | -Bi], rows 64+n -> [Bi | Br]
-                st_split4(Bhi, Blo, sw128(bn, bc), br);
-                st_split4(Bhi, Blo, sw128(bn, 4 + bc), nbi);
-                st_split4(Bhi, Blo, sw128(TC_BN + bn, bc), bi);
-                st_split4(Bhi, Blo, sw128(TC_BN + bn, 4 + bc), br);
-                fence_proxy_async();         // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + 8 * s);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) ga[e] = na[e];
             }
+            cp_async_commit();               // one group per stage, empty past the end, so that wait_group counts stay uniform
+        };
+#pragma unroll
+        for (int d = 0; d < TC_PF; ++d) issue(d);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % TC_STAGES, use = kb / TC_STAGES;
+            const uint32_t slot = (uint32_t)(kb % TC_PF) * TC_RAW_BYTES;
+            cp_async_wait<TC_PF - 1>();                      // this thread's stage-kb group has landed
+            const float4 b01 = lds128(rawB + slot), b23 = lds128(rawB + slot + 16u);
+            float4 brh, brl, bih, bil;
+            split4(make_float4(b01.x, b01.z, b23.x, b23.z), brh, brl);
+            split4(make_float4(b01.y, b01.w, b23.y, b23.w), bih, bil);
+            cpx ga[4];
+            const bool a_now = a_worker && kb + 1 < KB;
+            if (a_now) {
+                const float4 a01 = lds128(rawA + slot), a23 = lds128(rawA + slot + 16u);
+                ga[0] = cmake(a01.x, a01.y);
+                ga[1] = cmake(a01.z, a01.w);
+                ga[2] = cmake(a23.x, a23.y);
+                ga[3] = cmake(a23.z, a23.w);
+            }
+            TC_STAMP(0, kb, 0);
+            mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);       // MMAs of stage kb - TC_STAGES (and all older) are done
+            TC_STAMP(0, kb, 1);
+            if (a.debug_mode != 1) {
+                // ---- A: the 16 strip rows that enter the window with the NEXT stage (its MMAs cannot start before this
+                //      stage's `full` arrival, and the rows they replace were last read >= 5 stages ago)
+                if (a_now) strip_store(-TC_KC * (kb + 1) + a_r, a_c, ga);
+                // ---- B: rows n -> [Br | -Bi], rows 64+n -> [Bi | Br]
+                const uint32_t Bhi = Bst0 + (uint32_t)(s * TC_STAGE_BYTES), Blo = Bhi + TC_B_BYTES;
+                const uint32_t o0 = sw128(bn, bc), o1 = sw128(bn, 4 + bc), o2 = sw128(TC_BN + bn, bc), o3 = sw128(TC_BN + bn, 4 + bc);
+                sts128(Bhi + o0, brh);
+                sts128(Blo + o0, brl);
+                sts128(Bhi + o1, neg4(bih));
+                sts128(Blo + o1, neg4(bil));
+                sts128(Bhi + o2, bih);
+                sts128(Blo + o2, bil);
+                sts128(Bhi + o3, brh);
+                sts128(Blo + o3, brl);
+            }
+            TC_STAMP(0, kb, 2);
+            fence_proxy_async();         // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);
+            TC_STAMP(0, kb, 3);
+            issue(kb + TC_PF);           // refills the raw slot just consumed
         }
+        cp_async_wait<0>();
     } else if (warp == TC_ACC_WARPS + TC_PROD_WARPS) {
         // ===================================================================== MMA issuer
         const uint32_t idesc = make_idesc(TC_BM, 2 * TC_BN);
@@ -292,17 +356,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
             const int kb_end = min(KB, kb + TC_CHUNK);
             for (int first = 1; kb < kb_end; ++kb) {
                 const int s = kb % TC_STAGES, use = kb / TC_STAGES;
+                TC_STAMP(1, kb, 0);
                 mbar_wait(full0 + 8 * s, use & 1);
                 tc_fence_after();
+                TC_STAMP(1, kb, 1);
                 if (lane == 0) {
-                    const uint32_t st = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES);
-                    const uint32_t Ahi = st, Alo = st + TC_A_BYTES, Bhi = st + 2 * TC_A_BYTES, Blo = st + 2 * TC_A_BYTES + TC_B_BYTES;
+                    // A window of stage kb: strip rows [-16 kb, -16 kb + 128) = buffer rows [w0, w0 + 128), w0 = (-16 kb) mod TC_AW
+                    const uint32_t tiles_s = smem_u32(tiles);
+                    const int w0 = (TC_AW - (kb * TC_KC) % TC_AW) % TC_AW;
+                    const uint32_t Ahi = tiles_s + (uint32_t)(w0 * 128), Alo = Ahi + TC_AS_BYTES;
+                    const uint32_t Bhi = tiles_s + 2 * TC_AS_BYTES + (uint32_t)(s * TC_STAGE_BYTES), Blo = Bhi + TC_B_BYTES;
 #pragma unroll
                     for (int combo = 0; combo < 3; ++combo) {
                         const uint32_t A = combo == 2 ? Alo : Ahi;
                         const uint32_t Bm = combo == 1 ? Blo : Bhi;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {   // 4 K-steps of 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                            if (a.debug_mode != 2 || first)
                             umma_tf32(tmem_d, make_desc(A + 32 * j), make_desc(Bm + 32 * j), idesc, first ? 0u : 1u);
                             first = 0;
                         }
@@ -310,6 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
                     umma_commit(empty0 + 8 * s);                     // smem stage reusable once these MMAs have read it
                     if (kb == kb_end - 1) umma_commit(tfull0 + 8 * buf);   // chunk complete in TMEM
                 }
+                TC_STAMP(1, kb, 2);
                 __syncwarp();
                 first = 0;
             }
@@ -322,8 +393,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
         for (int i = 0; i < 32; ++i) accr[i] = acci[i] = 0.f;
         for (int c = 0; c < NC; ++c) {
             const int buf = c & 1;
+            TC_STAMP(2, c, 0);
             mbar_wait(tfull0 + 8 * buf, (c >> 1) & 1);
             tc_fence_after();
+            TC_STAMP(2, c, 1);
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + half * 32);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -339,6 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            TC_STAMP(2, c, 2);
         }
         const int m = m0 + q * 32 + lane;
         if (m < a.M) {
@@ -373,6 +447,10 @@ __global__ void __launch_bounds__(256) thz_k_cmul(const cpx* __restrict__ x, con
     }
 }
 
+extern "C" int thz_debug_tc_timeline(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_tc_timeline, sizeof(long long) * 3 * TC_TL_N * 4);
+}
+
 int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a_in, void* scratch, cudaStream_t stream) {
     ToeplitzGemmArgs a = a_in;
     if (a.pro) {
@@ -387,7 +465,8 @@ int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a_in, void* scratch, cud
         a.B = (const cpx*)scratch;
         a.pro = nullptr;
     }
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
+    if (a.sm != -a.sk) return THZ_E_WORKSPACE;                   // the sliding-strip A operand needs T(m, k) = g[off + sm (m - k)]
+    const size_t smem = (size_t)TC_SMEM_BYTES + (size_t)TC_PF * TC_RAW_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return thz_set_cuda_error("cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc)", e);
     dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM, a.batch);

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
+for dbg in 0 1 2; do echo "debug $dbg"; THZ_CZT_DEBUG=$dbg timeout 200 python tools/config_bench.py czt 2>&1 | grep "^{" | cut -c1-200; done
