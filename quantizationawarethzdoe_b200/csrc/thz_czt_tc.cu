@@ -2,29 +2,36 @@
 // 3xTF32 split AND fp32 promotion of partial sums.  Same contract as the CUDA-core kernel in thz_czt.cu
 // (include/thzdoe.h: thz_toeplitz_gemm).
 //
-// Real-valued formulation.  For complex C = T . B' (B' = pro * B) a tile accumulator holds, for complex row m
-// (TMEM lane m) and complex column n,   Cr in column n   and   Ci in column 64 + n   of its 128-column buffer:
-//      [Cr | Ci] = [Tr | Ti] . [[ Br,  Bi ],
-//                               [-Bi,  Br ]]
-// i.e. ONE tcgen05.mma (kind::tf32, M=128, N=128) per 8 real K-elements, A = [Tr | Ti] (128 x 32 per stage: 16
-// complex k), B stored K-major as 128 rows x 32.  Every operand is split x = hi + lo (hi = RN-to-TF32, lo = x - hi
-// exactly) and the product accumulated as hi*hi + hi*lo + lo*hi (lo*lo < 2^-22 relative): 12 MMAs per stage.
+// Real-valued formulation.  For complex C = T . B' (B' = pro * B, folded into B by thz_k_cmul) two tile accumulators
+// D1 = Tr . [Br | Bi]  and  D2 = Ti . [Br | Bi]  (128 TMEM columns each; column n real part, column 64 + n imaginary
+// part of complex column n) are built by tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8) and combined when they are
+// drained:  Cr[n] = D1[n] - D2[64 + n],  Ci[n] = D1[64 + n] + D2[n].  B is therefore stored ONCE ([Br | Bi], K-major),
+// not as the 2 x 2 real block matrix -- the producers' shared-memory stores compete with the tensor core's operand
+// reads for the 128 B/clk of the SM, which is what bounds this kernel (profiles/README.md, "tcgen05 CZT timeline").
+// Every operand is split x = hi + lo (hi = RN-to-TF32, lo = x - hi exactly) and the product accumulated as
+// hi*hi + hi*lo + lo*hi (lo*lo < 2^-22 relative): 12 MMAs per 16 complex k.
+//
+// Toeplitz operand = sliding strip.  T(m0 + r, k0 + kk) = g[off + sm (m0 + rho) + sk kk] depends on r and k0 only
+// through rho = r - k0 (sm = -sk), so the 128 x 16 A tile of k-block kb is rows [-16 kb, -16 kb + 128) of ONE strip
+// whose row rho holds [Re g(rho, 0..15) | Im g(rho, 0..15)] (128 bytes), and each k-block adds just 16 new rows.  The
+// strip lives in a circular buffer of TC_AW rows whose first 112 rows are mirrored behind its end, so that every
+// 128-row window is contiguous for the UMMA descriptor.
 //
 // Promotion.  The tensor core adds into its fp32 accumulator with truncation, so a single long accumulation
 // drifts linearly with K (measured: 7.8e-6 / 2.7e-5 / 5.3e-5 relative at K = 256 / 1024 / 2048 with one TMEM
-// accumulator -- above the 1e-5 parity bound).  Therefore the K loop is cut into chunks of 4 stages (64 complex
-// k, 48 MMAs) that each START FROM ZERO in one of two TMEM buffers; 8 accumulate warps drain a finished buffer
-// with tcgen05.ld and add it to fp32 register accumulators with IEEE rounding while the MMA warp already works
-// on the other buffer.
+// accumulator -- above the 1e-5 parity bound).  Therefore the K loop is cut into chunks of 64 complex k (48 MMAs)
+// that each START FROM ZERO in one of two TMEM buffer pairs; 8 accumulate warps drain a finished pair with
+// tcgen05.ld and add it to fp32 register accumulators with IEEE rounding while the MMA warp already works on the
+// other pair (2 x 2 x 128 = all 512 TMEM columns).
 //
-// Nothing is loaded by TMA: both operands are *generated* -- the Toeplitz tile from the chirp filter g, the B tile
-// from the prologue-scaled input -- by 8 producer warps that write the canonical K-major SWIZZLE_128B layout
-// directly (16-byte chunk c of row r goes to chunk c ^ (r & 7) of its 128-byte row), then fence to the async proxy.
+// Nothing is loaded by TMA: both operands are *generated* -- the strip from the chirp filter g, the B tile from the
+// prologue-scaled input -- by 8 producer warps that write the canonical K-major SWIZZLE_128B layout directly
+// (16-byte chunk c of row r goes to chunk c ^ (r & 7) of its 128-byte row), then fence to the async proxy.
 //
 // Roles (17 warps): warps 0-7 accumulate/epilogue (warp w: TMEM lanes 32 (w%4).., complex columns 32 (w/4)..),
-// warps 8-15 producers, warp 16 MMA issuer.  One 128 x 64 complex output tile per CTA, 3 smem stages of 64 KB.
-//   producers:  wait empty[s] -> fill A_hi/A_lo/B_hi/B_lo[s] -> fence.proxy.async -> arrive full[s]
-//   MMA warp :  per chunk: wait tmem_empty[b]; per stage: wait full[s] -> 12 x tcgen05.mma -> commit empty[s];
+// warps 8-15 producers, warp 16 MMA issuer.  One 128 x 64 complex output tile per CTA; a stage is 32 complex k:
+//   producers:  wait empty[s] -> 32 new strip rows + B_hi/B_lo[s] -> fence.proxy.async -> arrive full[s]
+//   MMA warp :  per chunk: wait tmem_empty[b]; per stage: wait full[s] -> 24 x tcgen05.mma -> commit empty[s];
 //               commit tmem_full[b]
 //   accumulate: wait tmem_full[b] -> tcgen05.ld -> acc += -> arrive tmem_empty[b];  finally * epi -> global
 #include "thz_common.cuh"
@@ -32,25 +39,24 @@
 #include "thz_runtime.h"
 
 #define TC_BM 128                     // complex rows per tile = TMEM lanes
-#define TC_BN 64                      // complex columns per tile -> 128 real accumulator columns
-#define TC_KC 16                      // complex k per stage -> 32 real k = one 128-byte swizzle row
+#define TC_BN 64                      // complex columns per tile -> 128 real accumulator columns per D1 / D2
+#define TC_KC 16                      // complex k per k-block = one strip row (16 re | 16 im = 128 bytes)
+#define TC_KS 32                      // complex k per stage = one 128-byte row of the B tile = two k-blocks
 #define TC_STAGES 3
-#define TC_CHUNK 4                    // stages per promotion chunk
-#define TC_PF 3                       // prefetch distance (stages) of the producers' cp.async raw ring
-#define TC_B_BYTES (2 * TC_BN * 128)  // 16 KB: 128 rows x 128 B
+#define TC_CHUNK 2                    // stages per promotion chunk (64 complex k)
+#define TC_B_BYTES (2 * TC_BN * 128)  // 16 KB: 128 rows ([Br | Bi] of 64 columns) x 128 B (32 k)
 #define TC_STAGE_BYTES (2 * TC_B_BYTES)                    // hi + lo of the B operand: 32 KB per stage
-// The Toeplitz operand is a sliding window: T(m0+r, k0+kk) = g[off + sm (m0 + rho) + sk kk] depends on r and k0 only
-// through rho = r - k0 (sm = -sk), so the A tile of stage kb is rows [-16 kb, -16 kb + 128) of ONE strip and each new
-// stage adds just 16 rows.  The strip lives in a circular buffer of TC_AW rows, stored twice (row i and i + TC_AW), so
-// that every 128-row window is contiguous for the UMMA descriptor.
-#define TC_AW 192                                          // window rows kept: 128 + 16 * 4 stages of slack
-#define TC_AS_BYTES (2 * TC_AW * 128)                      // one mirrored strip (hi or lo): 48 KB
-#define TC_SMEM_BYTES (2 * TC_AS_BYTES + TC_STAGES * TC_STAGE_BYTES)   // 96 KB + 96 KB
-#define TC_RAW_BYTES ((256 + 64) * 32)                     // raw (unconverted) cp.async landing slots of one stage: 10 KB
+// Strip window: a row written for k-block kb replaces the row last read by k-block kb - (TC_AW - 128) / 16 - 1; the
+// producers write the rows of k-blocks 2S and 2S + 1 after the MMAs of stage S - TC_STAGES (k-blocks <= 2S - 5) have
+// completed, hence TC_AW >= 128 + 16 * 5.
+#define TC_AW 208
+#define TC_AROWS (TC_AW + 112)                             // + mirror of rows 0..111 (window start <= TC_AW - 16)
+#define TC_AS_BYTES (TC_AROWS * 128)                       // one strip (hi or lo): 40 KB
+#define TC_SMEM_BYTES (2 * TC_AS_BYTES + TC_STAGES * TC_STAGE_BYTES)   // 80 KB + 96 KB
 #define TC_ACC_WARPS 8
 #define TC_PROD_WARPS 8
 #define TC_THREADS ((TC_ACC_WARPS + TC_PROD_WARPS + 1) * 32)
-#define TC_TMEM_COLS 256              // two 128-column accumulator buffers
+#define TC_TMEM_COLS 512              // two buffers of (D1, D2) = 2 x 128 columns each
 
 // ------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,6 +116,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
     for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
 
+// Two 8-column TMEM loads in flight, then ONE wait; the wait names the destination registers as read-write operands
+// so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld8x2(uint32_t ta, uint32_t tb, float (&ra)[8], float (&rb)[8]) {
+    uint32_t u[8], v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(ta));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(tb));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(v[0]),
+                   "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ra[i] = __uint_as_float(u[i]);
+        rb[i] = __uint_as_float(v[i]);
+    }
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
@@ -167,14 +195,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts64(uint32_t addr, cpx v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ int wrap_mod(long long v, int L) {
     v %= L;
     return (int)(v < 0 ? v + L : v);
@@ -216,24 +236,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_holder;
     const bool tl = a.debug_mode == 3 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == TC_ACC_WARPS || warp == TC_ACC_WARPS + TC_PROD_WARPS);
-    const int KB = (a.K + TC_KC - 1) / TC_KC;
-    const int NC = (KB + TC_CHUNK - 1) / TC_CHUNK;
+    const int NS = (a.K + TC_KS - 1) / TC_KS;               // stages
+    const int NC = (NS + TC_CHUNK - 1) / TC_CHUNK;           // promotion chunks
 
     if (warp >= TC_ACC_WARPS && warp < TC_ACC_WARPS + TC_PROD_WARPS) {
         // ===================================================================== producers
         const int ptid = tid - TC_ACC_WARPS * 32;                  // 0..255
         const cpx* g = a.g + (size_t)b * a.L;
         const cpx* Bb = a.B + (size_t)b * a.sb_b;
-        // (the prologue factor `pro` has been folded into B by thz_k_cmul before this kernel runs)
-        // B item: (column bn = ptid & 63, k-chunk bc = ptid >> 6), one per thread and stage
-        const int bn = ptid & 63, bc = ptid >> 6;
-        const int n = n0 + bn;
         const uint32_t tiles_s = smem_u32(tiles);
         const uint32_t Ahi = tiles_s, Alo = tiles_s + TC_AS_BYTES, Bst0 = tiles_s + 2 * TC_AS_BYTES;
         // strip entry (rho, kk) = g[(off + sm (m0 + rho) + sk kk) mod L]; one item = 4 consecutive kk of one strip row,
-        // written as a real chunk and an imaginary chunk, hi and lo, into both mirror images of the circular buffer
-        auto strip_load = [&](int rho, int c, cpx (&gv)[4]) {
-            int idx = wrap_mod((long long)a.off + (long long)a.sm * (m0 + rho) + (long long)a.sk * (4 * c), a.L);
+        // written as a real chunk and an imaginary chunk, hi and lo (and mirrored if it is one of the first 112 rows)
+        auto strip_load = [&](int idx, cpx (&gv)[4]) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 gv[e] = __ldg(g + idx);
@@ -245,142 +260,156 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
         auto strip_store = [&](int rho, int c, const cpx (&gv)[4]) {
             int row = rho % TC_AW;
             if (row < 0) row += TC_AW;
-            float re[4], im[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                re[e] = gv[e].x;
-                im[e] = a.conj_g ? -gv[e].y : gv[e].y;
+            float4 reh, rel, imh, iml;
+            split4(make_float4(gv[0].x, gv[1].x, gv[2].x, gv[3].x), reh, rel);
+            split4(make_float4(gv[0].y, gv[1].y, gv[2].y, gv[3].y), imh, iml);
+            if (a.conj_g) {
+                imh = neg4(imh);
+                iml = neg4(iml);
             }
-#pragma unroll
-            for (int copy = 0; copy < 2; ++copy) {
-                st_split4(Ahi, Alo, sw128(row + copy * TC_AW, c), re);
-                st_split4(Ahi, Alo, sw128(row + copy * TC_AW, 4 + c), im);
+            const uint32_t o0 = sw128(row, c), o1 = sw128(row, 4 + c);
+            sts128(Ahi + o0, reh);
+            sts128(Alo + o0, rel);
+            sts128(Ahi + o1, imh);
+            sts128(Alo + o1, iml);
+            if (row < TC_AROWS - TC_AW) {
+                const uint32_t p0 = sw128(row + TC_AW, c), p1 = sw128(row + TC_AW, 4 + c);
+                sts128(Ahi + p0, reh);
+                sts128(Alo + p0, rel);
+                sts128(Ahi + p1, imh);
+                sts128(Alo + p1, iml);
             }
         };
-        // initial window: rows rho = 0 .. 127 (512 items, two per thread)
+        // initial strip: rows rho = -16 .. 127 (k-blocks 0 and 1 of stage 0): 144 rows x 4 chunks
+        for (int item = ptid; item < 144 * 4; item += 256) {
+            const int rho = (item >> 2) - 16, c = item & 3;
+            cpx gv[4];
+            strip_load(wrap_mod((long long)a.off + (long long)a.sm * (m0 + rho) + (long long)a.sk * (4 * c), a.L), gv);
+            strip_store(rho, c, gv);
+        }
+        // stage S >= 1 adds the 32 rows rho = -32 S - 16 .. -32 S + 15: 128 items, threads 0..127; the g index of a
+        // thread's item moves by -32 sm per stage
+        const bool a_worker = ptid < 128;
+        const int a_r = ptid & 31, a_c = (ptid >> 5) & 3;
+        int a_idx = wrap_mod((long long)a.off + (long long)a.sm * (m0 - 48 + a_r) + (long long)a.sk * (4 * a_c), a.L);   // stage 1
+        const int a_step = wrap_mod(-32LL * a.sm, a.L);
+        // B items of a stage: 64 columns x 8 k-chunks of 4 complex -> two per thread.  Lanes run along the contiguous
+        // axis of B in global memory: along n (column bn = ptid & 63, chunks ptid >> 6 and + 4), or, when k is the
+        // contiguous axis (sb_k == 1: the second GEMM of a CZT reads its B transposed), along k (chunk ptid & 7,
+        // columns ptid >> 3 and + 32) with 16-byte loads -- a warp-wide load then touches 4 rows instead of 32.
+        const bool kmajor = a.sb_k == 1 && (a.sb_n & 1) == 0 && (a.sb_b & 1) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0;
+        int bn_[2], ch_[2];
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const int item = ptid + it * 256;
-            cpx gv[4];
-            strip_load(item & 127, item >> 7, gv);
-            strip_store(item & 127, item >> 7, gv);
+            bn_[it] = kmajor ? (ptid >> 3) + 32 * it : (ptid & 63);
+            ch_[it] = kmajor ? (ptid & 7) : (ptid >> 6) + 4 * it;
         }
-        // Per stage every thread owns one B item (4 complex values) and, for threads 0..63, one item of the 16 strip rows
-        // rho = -16 (kb+1) .. -16 (kb+1) + 15 that enter the window with stage kb + 1.  Both are fetched with cp.async
-        // into a private 32-byte slot of a TC_PF-deep raw ring (cp.async groups complete in order per thread, which a
-        // register prefetch ring does not guarantee: loads sharing a scoreboard would serialise on the newest one).
-        const bool a_worker = ptid < 64;
-        const int a_r = ptid & 15, a_c = (ptid >> 4) & 3;
-        const uint32_t raw0 = tiles_s + TC_SMEM_BYTES;
-        const uint32_t rawB = raw0 + (uint32_t)ptid * 32u, rawA = raw0 + 256u * 32u + (uint32_t)ptid * 32u;
-        auto issue = [&](int kb) {
-            if (kb < KB) {
-                const uint32_t slot = (uint32_t)(kb % TC_PF) * TC_RAW_BYTES;
-                const int k0 = kb * TC_KC + 4 * bc;
+        auto load_b = [&](int S, cpx (&Bv)[2][4]) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k0 + e;
-                    if (k < a.K && n < a.N)
-                        cp_async8(rawB + slot + 8u * e, Bb + (size_t)k * a.sb_k + (size_t)n * a.sb_n);
-                    else
-                        sts64(rawB + slot + 8u * e, cmake(0.f, 0.f));
-                }
-                if (a_worker && kb + 1 < KB) {
-                    int idx = wrap_mod((long long)a.off + (long long)a.sm * (m0 - TC_KC * (kb + 1) + a_r) + (long long)a.sk * (4 * a_c), a.L);
+            for (int it = 0; it < 2; ++it) {
+                const int n = n0 + bn_[it], k = S * TC_KS + 4 * ch_[it];
+                const cpx* src = Bb + (size_t)n * a.sb_n + (size_t)k * a.sb_k;
+                if (kmajor && n < a.N && k + 3 < a.K) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 2);
+                    Bv[it][0] = cmake(v0.x, v0.y);
+                    Bv[it][1] = cmake(v0.z, v0.w);
+                    Bv[it][2] = cmake(v1.x, v1.y);
+                    Bv[it][3] = cmake(v1.z, v1.w);
+                } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        cp_async8(rawA + slot + 8u * e, g + idx);
-                        idx += a.sk;
-                        if (idx >= a.L) idx -= a.L;
-                        if (idx < 0) idx += a.L;
-                    }
+                    for (int e = 0; e < 4; ++e)
+                        Bv[it][e] = (n < a.N && k + e < a.K) ? src[(size_t)e * a.sb_k] : cmake(0.f, 0.f);
                 }
             }
-            cp_async_commit();               // one group per stage, empty past the end, so that wait_group counts stay uniform
         };
+        // register prefetch, one stage ahead (a stage lasts longer than an L2 / HBM round trip)
+        cpx gb[2][4], ga[4];
+        load_b(0, gb);
+        if (a_worker && NS > 1) strip_load(a_idx, ga);
+        for (int S = 0; S < NS; ++S) {
+            const int s = S % TC_STAGES, use = S / TC_STAGES;
+            float4 brh[2], brl[2], bih[2], bil[2];
 #pragma unroll
-        for (int d = 0; d < TC_PF; ++d) issue(d);
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % TC_STAGES, use = kb / TC_STAGES;
-            const uint32_t slot = (uint32_t)(kb % TC_PF) * TC_RAW_BYTES;
-            cp_async_wait<TC_PF - 1>();                      // this thread's stage-kb group has landed
-            const float4 b01 = lds128(rawB + slot), b23 = lds128(rawB + slot + 16u);
-            float4 brh, brl, bih, bil;
-            split4(make_float4(b01.x, b01.z, b23.x, b23.z), brh, brl);
-            split4(make_float4(b01.y, b01.w, b23.y, b23.w), bih, bil);
-            cpx ga[4];
-            const bool a_now = a_worker && kb + 1 < KB;
-            if (a_now) {
-                const float4 a01 = lds128(rawA + slot), a23 = lds128(rawA + slot + 16u);
-                ga[0] = cmake(a01.x, a01.y);
-                ga[1] = cmake(a01.z, a01.w);
-                ga[2] = cmake(a23.x, a23.y);
-                ga[3] = cmake(a23.z, a23.w);
+            for (int it = 0; it < 2; ++it) {
+                split4(make_float4(gb[it][0].x, gb[it][1].x, gb[it][2].x, gb[it][3].x), brh[it], brl[it]);
+                split4(make_float4(gb[it][0].y, gb[it][1].y, gb[it][2].y, gb[it][3].y), bih[it], bil[it]);
             }
-            TC_STAMP(0, kb, 0);
-            mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);       // MMAs of stage kb - TC_STAGES (and all older) are done
-            TC_STAMP(0, kb, 1);
+            cpx gs[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gs[e] = ga[e];
+            if (S + 1 < NS) load_b(S + 1, gb);
+            if (a_worker && S >= 1 && S + 1 < NS) {
+                a_idx += a_step;
+                if (a_idx >= a.L) a_idx -= a.L;
+                strip_load(a_idx, ga);
+            }
+            TC_STAMP(0, S, 0);
+            mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);       // MMAs of stage S - TC_STAGES (and all older) are done
+            TC_STAMP(0, S, 1);
             if (a.debug_mode != 1) {
-                // ---- A: the 16 strip rows that enter the window with the NEXT stage (its MMAs cannot start before this
-                //      stage's `full` arrival, and the rows they replace were last read >= 5 stages ago)
-                if (a_now) strip_store(-TC_KC * (kb + 1) + a_r, a_c, ga);
-                // ---- B: rows n -> [Br | -Bi], rows 64+n -> [Bi | Br]
+                if (a_worker && S >= 1) strip_store(-TC_KS * S - 16 + a_r, a_c, gs);
+                // ---- B: row n -> Br(k = 0..31), row 64 + n -> Bi(k = 0..31)
                 const uint32_t Bhi = Bst0 + (uint32_t)(s * TC_STAGE_BYTES), Blo = Bhi + TC_B_BYTES;
-                const uint32_t o0 = sw128(bn, bc), o1 = sw128(bn, 4 + bc), o2 = sw128(TC_BN + bn, bc), o3 = sw128(TC_BN + bn, 4 + bc);
-                sts128(Bhi + o0, brh);
-                sts128(Blo + o0, brl);
-                sts128(Bhi + o1, neg4(bih));
-                sts128(Blo + o1, neg4(bil));
-                sts128(Bhi + o2, bih);
-                sts128(Blo + o2, bil);
-                sts128(Bhi + o3, brh);
-                sts128(Blo + o3, brl);
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const uint32_t o0 = sw128(bn_[it], ch_[it]), o1 = sw128(TC_BN + bn_[it], ch_[it]);
+                    sts128(Bhi + o0, brh[it]);
+                    sts128(Blo + o0, brl[it]);
+                    sts128(Bhi + o1, bih[it]);
+                    sts128(Blo + o1, bil[it]);
+                }
             }
-            TC_STAMP(0, kb, 2);
+            TC_STAMP(0, S, 2);
             fence_proxy_async();         // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);
-            TC_STAMP(0, kb, 3);
-            issue(kb + TC_PF);           // refills the raw slot just consumed
+            TC_STAMP(0, S, 3);
         }
-        cp_async_wait<0>();
     } else if (warp == TC_ACC_WARPS + TC_PROD_WARPS) {
         // ===================================================================== MMA issuer
         const uint32_t idesc = make_idesc(TC_BM, 2 * TC_BN);
-        int kb = 0;
+        const uint32_t tiles_s = smem_u32(tiles);
+        int S = 0;
         for (int c = 0; c < NC; ++c) {
             const int buf = c & 1;
-            mbar_wait(tempty0 + 8 * buf, ((c >> 1) & 1) ^ 1);       // accumulate warps have drained this buffer
+            TC_STAMP(1, S, 3);
+            mbar_wait(tempty0 + 8 * buf, ((c >> 1) & 1) ^ 1);       // accumulate warps have drained this buffer pair
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 2 * TC_BN);
-            const int kb_end = min(KB, kb + TC_CHUNK);
-            for (int first = 1; kb < kb_end; ++kb) {
-                const int s = kb % TC_STAGES, use = kb / TC_STAGES;
-                TC_STAMP(1, kb, 0);
+            const uint32_t tmem_d1 = tmem_base + (uint32_t)(buf * 4 * TC_BN), tmem_d2 = tmem_d1 + 2 * TC_BN;
+            const int S_end = min(NS, S + TC_CHUNK);
+            for (int first = 1; S < S_end; ++S) {
+                const int s = S % TC_STAGES, use = S / TC_STAGES;
+                TC_STAMP(1, S, 0);
                 mbar_wait(full0 + 8 * s, use & 1);
                 tc_fence_after();
-                TC_STAMP(1, kb, 1);
+                TC_STAMP(1, S, 1);
                 if (lane == 0) {
-                    // A window of stage kb: strip rows [-16 kb, -16 kb + 128) = buffer rows [w0, w0 + 128), w0 = (-16 kb) mod TC_AW
-                    const uint32_t tiles_s = smem_u32(tiles);
-                    const int w0 = (TC_AW - (kb * TC_KC) % TC_AW) % TC_AW;
-                    const uint32_t Ahi = tiles_s + (uint32_t)(w0 * 128), Alo = Ahi + TC_AS_BYTES;
                     const uint32_t Bhi = tiles_s + 2 * TC_AS_BYTES + (uint32_t)(s * TC_STAGE_BYTES), Blo = Bhi + TC_B_BYTES;
 #pragma unroll
-                    for (int combo = 0; combo < 3; ++combo) {
-                        const uint32_t A = combo == 2 ? Alo : Ahi;
-                        const uint32_t Bm = combo == 1 ? Blo : Bhi;
+                    for (int h = 0; h < 2; ++h) {
+                        // A window of k-block kb = 2S + h: strip rows [-16 kb, -16 kb + 128) = buffer rows [w0, w0 + 128)
+                        const int kb = 2 * S + h;
+                        const int w0 = (TC_AW - (kb * TC_KC) % TC_AW) % TC_AW;
+                        const uint32_t Ahi = tiles_s + (uint32_t)(w0 * 128), Alo = Ahi + TC_AS_BYTES;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {   // 4 K-steps of 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                            if (a.debug_mode != 2 || first)
-                            umma_tf32(tmem_d, make_desc(A + 32 * j), make_desc(Bm + 32 * j), idesc, first ? 0u : 1u);
-                            first = 0;
+                        for (int combo = 0; combo < 3; ++combo) {
+                            const uint32_t A = combo == 2 ? Alo : Ahi;
+                            const uint32_t Bm = combo == 1 ? Blo : Bhi;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {   // K-steps of 8 tf32 = 32 bytes inside the 128-byte swizzle rows
+                                const uint64_t db = make_desc(Bm + 32 * (2 * h + j));
+                                if (a.debug_mode != 2 || first) {
+                                    umma_tf32(tmem_d1, make_desc(A + 32 * j), db, idesc, first ? 0u : 1u);        // Tr . [Br|Bi]
+                                    umma_tf32(tmem_d2, make_desc(A + 32 * (2 + j)), db, idesc, first ? 0u : 1u);  // Ti . [Br|Bi]
+                                }
+                                first = 0;
+                            }
                         }
                     }
                     umma_commit(empty0 + 8 * s);                     // smem stage reusable once these MMAs have read it
-                    if (kb == kb_end - 1) umma_commit(tfull0 + 8 * buf);   // chunk complete in TMEM
+                    if (S == S_end - 1) umma_commit(tfull0 + 8 * buf);   // chunk complete in TMEM
                 }
-                TC_STAMP(1, kb, 2);
+                TC_STAMP(1, S, 2);
                 __syncwarp();
                 first = 0;
             }
@@ -397,17 +426,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
             mbar_wait(tfull0 + 8 * buf, (c >> 1) & 1);
             tc_fence_after();
             TC_STAMP(2, c, 1);
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + half * 32);
+            const uint32_t d1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 4 * TC_BN + half * 32);
+            const uint32_t d2 = d1 + 2 * TC_BN;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                float r[16], im[16];
-                tmem_ld16(t0 + 16 * j, r);
-                tmem_ld16(t0 + TC_BN + 16 * j, im);
+            for (int j = 0; j < 4; ++j) {
+                float p[8], m[8];
+                tmem_ld8x2(d1 + 8 * j, d2 + TC_BN + 8 * j, p, m);           // Tr Br, Ti Bi
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    accr[16 * j + e] += r[e];
-                    acci[16 * j + e] += im[e];
-                }
+                for (int e = 0; e < 8; ++e) accr[8 * j + e] += p[e] - m[e];
+                tmem_ld8x2(d1 + TC_BN + 8 * j, d2 + 8 * j, p, m);           // Tr Bi, Ti Br
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acci[8 * j + e] += p[e] + m[e];
             }
             tc_fence_before();
             __syncwarp();
@@ -466,7 +495,8 @@ int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a_in, void* scratch, cud
         a.pro = nullptr;
     }
     if (a.sm != -a.sk) return THZ_E_WORKSPACE;                   // the sliding-strip A operand needs T(m, k) = g[off + sm (m - k)]
-    const size_t smem = (size_t)TC_SMEM_BYTES + (size_t)TC_PF * TC_RAW_BYTES + 1024;
+    if (a.L < 64) return THZ_E_WORKSPACE;
+    const size_t smem = (size_t)TC_SMEM_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return thz_set_cuda_error("cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc)", e);
     dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM, a.batch);

@@ -20,15 +20,15 @@ rc = N.lib().thz_debug_tc_timeline(buf.ctypes.data_as(ctypes.c_void_p))
 assert rc == 0, rc
 t0 = buf[0, 0, 0]
 print("producer: stage  wait_data->  [empty wait]  [stores]  [fence+arrive]   stage period")
-for kb in range(40, 60):
+for kb in range(20, 36):
     p = buf[0, kb]
     print("  %3d  t=%7d  empty %5d  stores %5d  fence %5d  period %5d" % (kb, p[0] - t0, p[1] - p[0], p[2] - p[1], p[3] - p[2], buf[0, kb + 1, 0] - p[0]))
 print("mma: stage  [full wait] [issue+commit]  period")
-for kb in range(40, 60):
+for kb in range(20, 36):
     m = buf[1, kb]
     print("  %3d  t=%7d  full %5d  issue %5d  period %5d" % (kb, m[0] - t0, m[1] - m[0], m[2] - m[1], buf[1, kb + 1, 0] - m[0]))
 print("acc: chunk  [tfull wait] [drain]")
-for c in range(10, 16):
+for c in range(8, 14):
     q = buf[2, c]
     print("  %3d  t=%7d  wait %5d  drain %5d" % (c, q[0] - t0, q[1] - q[0], q[2] - q[1]))
-print("first stamps: prod %d mma %d ; last prod %d (total %d clk for 128 stages)" % (0, buf[1, 0, 0] - t0, buf[0, 127, 3] - t0, buf[0, 127, 3] - t0))
+print("first stamps: prod %d mma %d ; last prod %d (total %d clk for 64 stages)" % (0, buf[1, 0, 0] - t0, buf[0, 63, 3] - t0, buf[0, 63, 3] - t0))
