@@ -16,7 +16,8 @@ struct ToeplitzGemmArgs {
     long long sc_b, sc_m, sc_n;
     const cpx* epi;           // optional epilogue factor, same indexing as C
     int conj_epi;
-    int debug_mode;           // 0 normal; 1 producers skip the smem stores; 2 MMA warp skips the MMAs (bottleneck experiments)
+    int debug_mode;           // THZ_CZT_DEBUG: 0 normal; 1 producers skip the smem stores; 2 MMA warp skips the MMAs;
+                              // 3 / 4 clock64 timeline of CTA 0 (tools/tc_timeline.py) -- bottleneck experiments only
 };
 
 // tcgen05 / TMEM implementation (thz_czt_tc.cu)

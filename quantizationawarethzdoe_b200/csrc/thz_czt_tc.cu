@@ -19,7 +19,8 @@
 //
 // Promotion.  The tensor core adds into its fp32 accumulator with truncation, so a single long accumulation
 // drifts linearly with K (measured: 7.8e-6 / 2.7e-5 / 5.3e-5 relative at K = 256 / 1024 / 2048 with one TMEM
-// accumulator -- above the 1e-5 parity bound).  Therefore the K loop is cut into chunks of 64 complex k (48 MMAs)
+// accumulator -- above the 1e-5 parity bound).  Therefore the K loop is cut into chunks of 128 complex k (96 MMAs;
+// 1.9e-6 relative at every K, 1.0e-6 with 64-k chunks at 5 % more time)
 // that each START FROM ZERO in one of two TMEM buffer pairs; 8 accumulate warps drain a finished pair with
 // tcgen05.ld and add it to fp32 register accumulators with IEEE rounding while the MMA warp already works on the
 // other pair (2 x 2 x 128 = all 512 TMEM columns).
@@ -43,7 +44,7 @@
 #define TC_KC 16                      // complex k per k-block = one strip row (16 re | 16 im = 128 bytes)
 #define TC_KS 32                      // complex k per stage = one 128-byte row of the B tile = two k-blocks
 #define TC_STAGES 3
-#define TC_CHUNK 2                    // stages per promotion chunk (64 complex k)
+#define TC_CHUNK 4                    // stages per promotion chunk (128 complex k)
 #define TC_B_BYTES (2 * TC_BN * 128)  // 16 KB: 128 rows ([Br | Bi] of 64 columns) x 128 B (32 k)
 #define TC_STAGE_BYTES (2 * TC_B_BYTES)                    // hi + lo of the B operand: 32 KB per stage
 // Strip window: a row written for k-block kb replaces the row last read by k-block kb - (TC_AW - 128) / 16 - 1; the
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) thz_k_toeplitz_gemm_tc(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_holder;
-    const bool tl = a.debug_mode == 3 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == TC_ACC_WARPS || warp == TC_ACC_WARPS + TC_PROD_WARPS);
+    const bool tl = (a.debug_mode == 3 || (a.debug_mode == 4 && a.epi == nullptr)) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == TC_ACC_WARPS || warp == TC_ACC_WARPS + TC_PROD_WARPS);
     const int NS = (a.K + TC_KS - 1) / TC_KS;               // stages
     const int NC = (NS + TC_CHUNK - 1) / TC_CHUNK;           // promotion chunks
 

@@ -1,6 +1,6 @@
 """Debug: per-stage clock64 timeline of one CTA of the tcgen05 Toeplitz GEMM (THZ_CZT_DEBUG=3)."""
 import ctypes, os, sys
-os.environ["THZ_CZT_DEBUG"] = "3"
+os.environ["THZ_CZT_DEBUG"] = sys.argv[1] if len(sys.argv) > 1 else "3"   # 3: last GEMM launched (GEMM 2), 4: GEMM 1
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from quantizationawarethzdoe_b200 import _native as N
