@@ -26,8 +26,13 @@ def _digest():
         with open(os.path.join(CSRC, n), "rb") as f:
             h.update(n.encode())
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
+
+
+def _extra_flags():
+    """Experiment switches (e.g. THZ_NVCC_EXTRA="-DTHZ_NO_F32X2"); empty in normal builds."""
+    return os.environ.get("THZ_NVCC_EXTRA", "").split()
 
 
 def build(force=False, verbose=False):
@@ -42,7 +47,7 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = s[:-3] + ".o"
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + _extra_flags() + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

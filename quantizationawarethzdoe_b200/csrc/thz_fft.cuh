@@ -57,8 +57,7 @@ THZ_HD cpx mul_root(cpx a, int e) {
     if (4 * e == R) return INV ? cmul_pi(a) : cmul_mi(a);
     if (4 * e == 3 * R) return INV ? cmul_mi(a) : cmul_pi(a);
     const float c = cw_cos<R>(e), s = cw_sin<R>(e);
-    if (INV) return cmake(a.x * c - a.y * s, a.x * s + a.y * c);
-    return cmake(a.x * c + a.y * s, a.y * c - a.x * s);
+    return INV ? cmul(a, cmake(c, s)) : cmulc(a, cmake(c, s));
 }
 
 // ---------------------------------------------------------------- register butterflies
@@ -79,7 +78,7 @@ struct Dft<3, INV> {
     static THZ_HD void run(cpx (&v)[3]) {
         const float S = 0.8660254037844386f;
         cpx t1 = cadd(v[1], v[2]);
-        cpx t2 = cmake(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+        cpx t2 = caxpy(-0.5f, t1, v[0]);
         cpx t3 = cscale(csub(v[1], v[2]), S);
         cpx it3 = INV ? cmul_pi(t3) : cmul_mi(t3);   // -/+ i t3
         v[0] = cadd(v[0], t1);
@@ -108,10 +107,10 @@ struct Dft<5, INV> {
         const float S1 = 0.9510565162951535f, S2 = 0.5877852522924731f;
         cpx t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
         cpx t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
-        cpx a1 = cmake(v[0].x + C1 * t1.x + C2 * t2.x, v[0].y + C1 * t1.y + C2 * t2.y);
-        cpx a2 = cmake(v[0].x + C2 * t1.x + C1 * t2.x, v[0].y + C2 * t1.y + C1 * t2.y);
-        cpx b1 = cmake(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
-        cpx b2 = cmake(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y);
+        cpx a1 = caxpy(C2, t2, caxpy(C1, t1, v[0]));
+        cpx a2 = caxpy(C1, t2, caxpy(C2, t1, v[0]));
+        cpx b1 = caxpy(S2, t4, cscale(t3, S1));
+        cpx b2 = caxpy(-S1, t4, cscale(t3, S2));
         cpx ib1 = INV ? cmul_pi(b1) : cmul_mi(b1);
         cpx ib2 = INV ? cmul_pi(b2) : cmul_mi(b2);
         v[0] = cadd(v[0], cadd(t1, t2));

@@ -1,0 +1,8 @@
+cd $GRAFT_REPO_ROOT
+for v in "-DTHZ_F32X2_MUL_ONLY" "-DTHZ_F32X2_ADD_ONLY"; do
+echo "variant $v"
+THZ_NVCC_EXTRA="$v" python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
+THZ_NVCC_EXTRA="$v" timeout 300 python bench.py --no-cpu-baseline --steps 10 --warmup 3 2>&1 | grep "^{" | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['roofline']['step']['frac'], {k:v['ms_per_step'] for k,v in d['roofline']['kernels'].items()})"
+done
