@@ -58,6 +58,7 @@ static inline uint64_t thz_asm_ws_bytes(const thz_asm_desc* d) {
 static inline bool thz_is_p2_size(int n) { return thz_sp_instantiated(n); }
 
 static inline int thz_p2_row_lines_rt(int n) { return p2_row_lines(n); }
+static inline int thz_p2_tw_count_rt(int n) { return p2_tw_count(n); }
 static inline int thz_p2_row_threads_rt(int n) { return p2_row_threads(n); }
 static inline int thz_p2_col_cols_rt(int n) { return p2_col_cols(n); }
 static inline int thz_p2_col_threads_rt(int n) { return p2_col_threads(n); }
@@ -75,7 +76,8 @@ static inline void thz_asm_apply_p2(const thz_asm_desc* d, int nbc, int sm_count
         L->k1_threads = threads;
         L->k1_grid = (nbc * d->inH + lines - 1) / lines;
         // line buffer + staged raw rows (+ staged height-map rows), see thz_p2_k1
-        L->k1_smem = smem;
+        const size_t tw_bytes = (size_t)thz_p2_tw_count_rt(d->Wp) * sizeof(cpx);   // shared-memory twiddle copy
+        L->k1_smem = smem + tw_bytes;
         if (p2_row_pipelined(d->Wp)) L->k1_smem += (size_t)lines * d->inW * sizeof(cpx) + (size_t)lines * d->inW * sizeof(float);
         L->k3.lines = lines;
         L->k3_threads = threads;
@@ -85,14 +87,14 @@ static inline void thz_asm_apply_p2(const thz_asm_desc* d, int nbc, int sm_count
         gy = thz_imin(gy, nbc);
         L->k3.bc_per_cta = (nbc + gy - 1) / gy;
         L->k3_gridy = (nbc + L->k3.bc_per_cta - 1) / L->k3.bc_per_cta;
-        L->k3_smem = p2_row_pipelined(d->Wp) ? 2 * smem : smem;   // double-buffered line (thz_p2_k3 prefetches the next field)
+        L->k3_smem = (p2_row_pipelined(d->Wp) ? 2 * smem : smem) + tw_bytes;   // double-buffered line (thz_p2_k3 prefetches the next field)
     }
     if (L->p2_h) {
         const int cols = thz_p2_col_cols_rt(d->Hp);
         L->k2.cols = cols;
         L->k2_gridx = (d->Wp + cols - 1) / cols;
         L->k2_threads = thz_p2_col_threads_rt(d->Hp);
-        L->k2_smem = (size_t)cols * (d->Hp + (d->Hp >> 4)) * sizeof(cpx);
+        L->k2_smem = (size_t)cols * (d->Hp + (d->Hp >> 4)) * sizeof(cpx) + (size_t)thz_p2_tw_count_rt(d->Hp) * sizeof(cpx);
     }
 }
 

@@ -43,16 +43,18 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     constexpr int LINES = p2_row_lines(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);
-    cpx* xs = s + LINES * p2_pitch(N);                                   // staged raw rows
+    cpx* tws = s + LINES * p2_pitch(N);                                  // shared-memory copy of the stage twiddles
+    cpx* xs = tws + p2_tw_count(N);                                      // staged raw rows
     float* hs = reinterpret_cast<float*>(xs + (size_t)LINES * a.inW);      // staged height-map rows
     const int tid = threadIdx.x, nt = blockDim.x;
     const int ngroups = (a.nbc * a.inH + LINES - 1) / LINES;
     int grp = blockIdx.x;
+    for (int i = tid; i < p2_tw_count(N); i += nt) tws[i] = a.tw[i];     // visible after the first barrier below
     if constexpr (!p2_row_pipelined(N)) {     // no room for staging: plain load -> transform -> store per group
         for (; grp < ngroups; grp += gridDim.x) {
             p2k1_first<N>(a, s, grp, tid, nt);
             __syncthreads();
-            fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, a.tw);
+            fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, tws);
             p2k1_store<N>(a, s, grp, tid, nt);
             __syncthreads();
         }
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
         __syncthreads();                      // staging consumed
         if (grp + (int)gridDim.x < ngroups) p2k1_prefetch<N>(a, xs, hs, grp + gridDim.x, tid, nt);
         thz_cp_async_commit();
-        fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, a.tw);
+        fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, tws);
         p2k1_store<N>(a, s, grp, tid, nt);
     }
 }
@@ -77,14 +79,16 @@ __global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     constexpr int COLS = p2_col_cols(N), NS = p2_stages(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tws = s + COLS * p2_pitch(N);              // shared-memory copy of the twiddles the in-smem stages use
     const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x, by = blockIdx.y;
+    for (int i = tid; i < p2_tw_count(N); i += nt) tws[i] = a.tw[i];
     p2k2_first<N, COLS>(a, s, bx, by, tid, nt);
     __syncthreads();
-    fwd_cols<N, 1, NS - 1, COLS>(s, tid, nt, a.tw);
+    fwd_cols<N, 1, NS - 1, COLS>(s, tid, nt, tws);
     p2k2_middle<N, COLS>(a, s, bx, by, tid, nt);
     __syncthreads();
-    inv_cols<N, NS - 2, 1, COLS>(s, tid, nt, a.tw);
-    p2k2_last<N, COLS>(a, s, bx, by, tid, nt);
+    inv_cols<N, NS - 2, 1, COLS>(s, tid, nt, tws);
+    p2k2_last<N, COLS>(a, s, tws, bx, by, tid, nt);
 }
 
 template <int N>
@@ -92,7 +96,9 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     constexpr int NACC = p2k3_acc<N>(), LINES = p2_row_lines(N), BUF = LINES * p2_pitch(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);      // two line buffers: [0, BUF) and [BUF, 2 BUF)
+    cpx* tws = s + (p2_row_pipelined(N) ? 2 : 1) * BUF;                  // shared-memory copy of the stage twiddles
     const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x;
+    for (int i = tid; i < p2_tw_count(N); i += nt) tws[i] = a.tw[i];     // visible after the first barrier below
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
@@ -103,8 +109,8 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
         for (int f = f_lo; f < f_hi; ++f) {
             p2k3_load<N>(a, s, bx, f, tid, nt);
             __syncthreads();
-            inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, tid, nt, a.tw);
-            p2k3_last<N, NACC>(a, s, bx, f, tid, nt, acc);
+            inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, tid, nt, tws);
+            p2k3_last<N, NACC>(a, s, tws, bx, f, tid, nt, acc);
             __syncthreads();
         }
         p2k3_flush<N, NACC>(a, bx, tid, nt, acc);
@@ -119,8 +125,8 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
         if (f + 1 < f_hi) p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, tid, nt);
         thz_cp_async_commit();
         p2k3_prefetch_epilogue<N>(a, bx, f, tid, nt);
-        inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, tid, nt, a.tw);
-        p2k3_last<N, NACC>(a, sc, bx, f, tid, nt, acc);
+        inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, tid, nt, tws);
+        p2k3_last<N, NACC>(a, sc, tws, bx, f, tid, nt, acc);
     }
     p2k3_flush<N, NACC>(a, bx, tid, nt, acc);
 }

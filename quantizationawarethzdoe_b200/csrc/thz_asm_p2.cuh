@@ -232,7 +232,7 @@ THZ_HD void p2k2_middle(const ColArgs& a, cpx* s, int bx, int by, int tid, int n
 }
 
 template <int N, int COLS>
-THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, int bx, int by, int tid, int nt) {
+THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, const cpx* tw, int bx, int by, int tid, int nt) {
     constexpr int NB = P2Stage<N, 0>::NB;
     for (int w = tid; w < COLS * NB; w += nt) {
         const int j = w / COLS, l = w % COLS;
@@ -242,7 +242,7 @@ THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, int bx, int by, int tid, i
         st.out_r0 = a.out_r0;
         st.outH = a.outH;
         st.Wp = a.Wp;
-        p2_last_inverse_stage_to<N, COLS>(s + l, j, a.tw, st);
+        p2_last_inverse_stage_to<N, COLS>(s + l, j, tw, st);
     }
 }
 
@@ -329,7 +329,7 @@ THZ_HD void p2k3_prefetch_epilogue(const RowInvArgs& a, int bx, int f, int tid, 
 
 // inverse stage 0 + crop + scale + epilogue for field f; acc has p2k3_acc<N>() entries
 template <int N, int NACC>
-THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, int bx, int f, int tid, int nt, float (&acc)[NACC]) {
+THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, int f, int tid, int nt, float (&acc)[NACC]) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N), R = P2Stage<N, 0>::R;
     K3Storer st;
     st.cf = cmake4(0.f);
@@ -355,7 +355,7 @@ THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, int bx, int f, int tid,
         st.xrow = a.xsaved ? a.xsaved + o : nullptr;
         st.hrow = a.doe.hmap ? a.doe.hmap + (size_t)r * a.outW : nullptr;
         st.acc = &acc[k * R];
-        p2_last_inverse_stage_to<N, 1>(s + line * PITCH, j, a.tw, st);
+        p2_last_inverse_stage_to<N, 1>(s + line * PITCH, j, tw, st);
     }
 }
 

@@ -58,6 +58,18 @@ THZ_HD constexpr bool sp_static_ok(int N) {
     return p2_stages(N) >= 2;
 }
 
+// Twiddles of every stage but the first are read from a shared-memory copy of tw[0 .. p2_tw_count(N)): stage s uses
+// tw[j * N / L_s] with j < L_s / R_s, i.e. indices below N / R_s.  (An inverse stage multiplies BEFORE its butterfly,
+// so nothing hides the load: from L2 it was ~7 % of the column kernel's stall samples, profiles/README.md.)
+THZ_HD constexpr int p2_tw_count(int N) {
+    int n = 1;
+    for (int s = 0; s < p2_stages(N); ++s) {
+        const int L = p2_L(N, s), R = p2_radix(N, s);
+        if (L / R > 1 && N / R > n) n = N / R;
+    }
+    return n;
+}
+
 template <int N, int S>
 struct P2Stage {
     static_assert(sp_static_ok(N), "length cannot use the static-offset FFT path");
@@ -94,7 +106,7 @@ THZ_HD void p2_apply_twiddles(cpx (&v)[R], cpx w1) {
 //   base: pointer to slot 0 of this line (row-major, STRIDE = 1) or to column l of slot 0 (column tile,
 //   STRIDE = number of columns in the tile)
 template <int N, int S, bool INV, int STRIDE>
-THZ_HD void p2_butterfly(cpx* base, int u, const cpx* __restrict__ tw) {
+THZ_HD void p2_butterfly(cpx* base, int u, const cpx* tw) {
     typedef P2Stage<N, S> St;
     constexpr int R = St::R, M = St::M, L = St::L;
     const int b = u / M, j = u % M;       // M is a power of two: shift / mask
@@ -105,9 +117,9 @@ THZ_HD void p2_butterfly(cpx* base, int u, const cpx* __restrict__ tw) {
     for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
     if (!INV) {
         Dft<R, false>::run(v);
-        if (M > 1) p2_apply_twiddles<R>(v, thz_ldg(tw + j * St::WT));
+        if (M > 1) p2_apply_twiddles<R>(v, tw[j * St::WT]);          // tw: shared-memory copy (or the global table)
     } else {
-        if (M > 1) p2_apply_twiddles<R>(v, cconj(thz_ldg(tw + j * St::WT)));
+        if (M > 1) p2_apply_twiddles<R>(v, cconj(tw[j * St::WT]));
         Dft<R, true>::run(v);
     }
 #pragma unroll
@@ -133,14 +145,14 @@ THZ_HD void p2_first_stage_from(cpx* base, int j, const cpx* __restrict__ tw, Lo
 
 // ---------------------------------------------------------------- last inverse stage, outputs to a functor
 template <int N, int STRIDE, typename Store>
-THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* __restrict__ tw, Store store) {
+THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* tw, Store store) {
     typedef P2Stage<N, 0> St;
     constexpr int R = St::R, M = St::M;
     const cpx* p = base + (j + (j >> 4)) * STRIDE;
     cpx v[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
-    p2_apply_twiddles<R>(v, cconj(thz_ldg(tw + j)));
+    p2_apply_twiddles<R>(v, cconj(tw[j]));
     Dft<R, true>::run(v);
 #pragma unroll
     for (int t = 0; t < R; ++t) store(j + t * M, t, v[t]);
@@ -149,7 +161,7 @@ THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* __restri
 // ---------------------------------------------------------------- all butterflies of in-smem stage S
 //   ROWS: LINES lines of pitch PITCH slots (row kernels), work item w -> (line = w / NB, u = w % NB)
 template <int N, int S, bool INV, int LINES>
-THZ_HD void p2_stage_rows(cpx* s, int tid, int nthreads, const cpx* __restrict__ tw) {
+THZ_HD void p2_stage_rows(cpx* s, int tid, int nthreads, const cpx* tw) {
     constexpr int NB = P2Stage<N, S>::NB;
     constexpr int PITCH = N + (N >> 4);
     for (int w = tid; w < LINES * NB; w += nthreads) {
@@ -159,7 +171,7 @@ THZ_HD void p2_stage_rows(cpx* s, int tid, int nthreads, const cpx* __restrict__
 }
 //   COLUMN TILE: COLS lines interleaved (slot * COLS + l), work item w -> (u = w / COLS, l = w % COLS)
 template <int N, int S, bool INV, int COLS>
-THZ_HD void p2_stage_cols(cpx* s, int tid, int nthreads, const cpx* __restrict__ tw) {
+THZ_HD void p2_stage_cols(cpx* s, int tid, int nthreads, const cpx* tw) {
     constexpr int NB = P2Stage<N, S>::NB;
     for (int w = tid; w < COLS * NB; w += nthreads) {
         const int u = w / COLS, l = w % COLS;

@@ -118,7 +118,7 @@ static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
     constexpr int LINES = p2_row_lines(N);
     std::vector<unsigned char> buf(smem);
     cpx* s = (cpx*)buf.data();
-    cpx* xs = s + LINES * p2_pitch(N);
+    cpx* xs = s + LINES * p2_pitch(N) + p2_tw_count(N);
     float* hs = (float*)(xs + (size_t)LINES * a.inW);
     const int ngroups = (a.nbc * a.inH + LINES - 1) / LINES;
     const int g = grid < 5 ? grid : 5;   // a few persistent "CTAs", each walking groups bx, bx+g, ...
@@ -153,7 +153,7 @@ static void run_p2_k2(const ColArgs& a, int gx, int gy, int nt, size_t smem) {
             e_fwd_cols<N, 1, NS - 1, COLS>(s, nt, a.tw);
             for_threads(nt, [&](int t) { p2k2_middle<N, COLS>(a, s, bx, by, t, nt); });
             e_inv_cols<N, NS - 2, 1, COLS>(s, nt, a.tw);
-            for_threads(nt, [&](int t) { p2k2_last<N, COLS>(a, s, bx, by, t, nt); });
+            for_threads(nt, [&](int t) { p2k2_last<N, COLS>(a, s, a.tw, bx, by, t, nt); });
         }
 }
 template <int N>
@@ -172,7 +172,7 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
                 for (int f = f_lo; f < f_hi; ++f) {
                     for_threads(nt, [&](int t) { p2k3_load<N>(a, s, bx, f, t, nt); });
                     e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, nt, a.tw);
-                    for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, s, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                    for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, s, a.tw, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
                 }
                 for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
                 continue;
@@ -182,7 +182,7 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
                 cpx* sc = s + cur * BUF;
                 if (f + 1 < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, t, nt); });
                 e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, nt, a.tw);
-                for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, sc, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, sc, a.tw, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
             }
             for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
         }
