@@ -112,13 +112,50 @@ def tf_vectors(Hp, Wp, spacing, wavelengths, z, bandlimit=True, bandlimit_type="
     return rowvec, colvec, scal
 
 
-def tf_row_thresholds(rowvec, colvec, scal, chunk_rows=512):
+def tf_row_thresholds(rowvec, colvec, scal):
     """Fold the per-bin keep conditions into one threshold per row (natural bin order in and out).
 
     keep(r, c) = (rowvec.y[r] + colvec.y[c] <= 1) & (rowvec.z[r] + colvec.z[c] <= 1) & !(klam^2 - (Kx^2[r] + Ky^2[c]) < 0)
-    is, for a fixed row, monotone non-increasing in Ky^2[c]; tau[r] = the largest Ky^2 that is kept (-1 if none),
-    so that keep(r, c) == (Ky^2[c] <= tau[r]) exactly.  Returns tau [C,Hp] or None if monotonicity fails
-    (never observed; the caller then falls back to the cached-table mode)."""
+    (Props/ASM_Prop.py:262, :290-301, fp32 op order) is, for a fixed row, monotone non-increasing along the columns
+    sorted by Ky^2: the two band-limit quotients are non-decreasing in Ky^2 (checked below) and a rounded fp32 add /
+    subtract with one operand fixed is monotone.  tau[r] = the largest Ky^2 that is kept (-1 if none), so that
+    keep(r, c) == (Ky^2[c] <= tau[r]) exactly; found by a binary search over the sorted columns, vectorised over
+    wavelengths and rows (numpy float32: same IEEE single arithmetic, less per-call overhead than torch) --
+    O((Hp + Wp) log Wp), a depth sweep rebuilds this for every z.  Returns tau [C,Hp], or None if the quotients are
+    not monotone (never observed; the caller then falls back to the cached-table mode)."""
+    import numpy as np
+    rv = rowvec.numpy()
+    cv = colvec.numpy()
+    klam2 = scal[:, 0].numpy().reshape(-1, 1)
+    C, Hp, _ = rv.shape
+    Wp = cv.shape[1]
+    order = np.argsort(cv[:, :, 0], axis=1, kind="stable")
+    ky2 = np.take_along_axis(cv[:, :, 0], order, axis=1)
+    b1 = np.take_along_axis(cv[:, :, 1], order, axis=1)
+    b2 = np.take_along_axis(cv[:, :, 2], order, axis=1)
+    if (b1[:, 1:] < b1[:, :-1]).any() or (b2[:, 1:] < b2[:, :-1]).any():
+        return None
+    r0, r1, r2 = rv[:, :, 0], rv[:, :, 1], rv[:, :, 2]
+    one = np.float32(1)
+    zero = np.float32(0)
+    lo = np.zeros((C, Hp), dtype=np.int64)                # invariant: sorted columns [0, lo) kept, [hi, Wp) dropped
+    hi = np.full((C, Hp), Wp, dtype=np.int64)
+    for _ in range(int(Wp).bit_length() + 1):
+        mid = (lo + hi) >> 1
+        m = np.minimum(mid, Wp - 1)
+        k = np.take_along_axis(ky2, m, axis=1)
+        ok = ((r1 + np.take_along_axis(b1, m, axis=1)) <= one) & ((r2 + np.take_along_axis(b2, m, axis=1)) <= one)
+        ok &= ~((klam2 - (r0 + k)) < zero)
+        ok &= mid < hi
+        lo = np.where(ok, mid + 1, lo)
+        hi = np.where(ok, hi, np.minimum(hi, np.maximum(mid, lo)))
+    t = np.take_along_axis(ky2, np.maximum(lo - 1, 0), axis=1)
+    tau = np.where(lo > 0, t, np.float32(-1.0)).astype(np.float32)
+    return torch.from_numpy(tau)
+
+
+def _tf_row_thresholds_dense(rowvec, colvec, scal, chunk_rows=512):
+    """O(Hp Wp) evaluation of the same thresholds with an explicit monotonicity check (tests compare the two)."""
     C, Hp, _ = rowvec.shape
     tau = torch.empty(C, Hp)
     for c in range(C):

@@ -131,3 +131,19 @@ def test_asm_prop_surface_and_loud_failure_without_cuda():
     with pytest.raises(N.ThzError, match="no CPU path"):   # the product never falls back to the CPU
         a.check_Zc = False
         a(f)
+
+
+def test_row_thresholds_binary_search_equals_dense_evaluation():
+    """The O((Hp+Wp) log Wp) threshold builder a depth sweep calls per z must equal the dense O(Hp Wp) evaluation
+    of the reference's keep mask (Props/ASM_Prop.py:262, :290-301) bit for bit, incl. rows with no kept bin."""
+    from quantizationawarethzdoe_b200 import asm_host as AH
+    cases = [(256, 256, .5e-3, .5e-3, 1e-3, .1, True, 'exact'), (400, 600, 1e-3, .7e-3, 1e-3, .2, True, 'approx'),
+             (300, 300, .3e-3, .3e-3, 1e-3, .05, True, 'exact'), (512, 512, 2e-3, 2e-3, 1e-3, 5.0, True, 'exact'),
+             (64, 96, .5e-3, .5e-3, .9e-3, .01, False, 'exact'), (25, 25, 1e-3, 1e-3, 1e-3, 0.3, True, 'exact'),
+             (1000, 1000, .2e-3, .2e-3, 1e-3, 2.0, True, 'exact')]
+    for Hp, Wp, dx, dy, lam, z, bl, bt in cases:
+        wl = torch.tensor([lam, lam * 1.07, lam * 0.8])
+        rv, cv, sc = AH.tf_vectors(Hp, Wp, torch.tensor([dx, dy]), wl, torch.tensor(z), bl, bt)
+        fast, dense = AH.tf_row_thresholds(rv, cv, sc), AH._tf_row_thresholds_dense(rv, cv, sc)
+        assert fast is not None and dense is not None
+        assert torch.equal(fast, dense), (Hp, Wp, bt)
