@@ -50,6 +50,16 @@ int thz_fft_plan_info(int32_t n, int32_t* radices, int32_t* nstages);
 int thz_fft_slot_to_bin(int32_t n, int32_t* slot_to_bin);
 int thz_fft_twiddles(int32_t n, float* tw);
 
+/* thz_tf_row_thresholds (host-only helper of tf_mode 0): folds the reference's per-bin keep conditions
+ *   (rowvec.y[r] + colvec.y[c] <= 1) && (rowvec.z[r] + colvec.z[c] <= 1) && !(klam2 - (rowvec.x[r] + colvec.x[c]) < 0)
+ * (Props/ASM_Prop.py:262, :297-301, fp32, one rounding per op) into one threshold per row, tau[c][r] = the
+ * largest Ky^2 = colvec.x that is kept (-1 if none), so that keep(r, c) == (colvec.x[c] <= tau[r]) exactly.
+ * rowvec float[C][Hp][4], colvec float[C][Wp][4], scal float[C][2] = {klam2, z}, tau float[C][Hp]; all host
+ * pointers, natural FFT-bin order.  O((Hp + Wp) log Wp) per wavelength: a depth sweep calls it for every z.
+ * Returns THZ_E_UNSUPPORTED if the band-limit quotients are not monotone in Ky^2 (use tf_mode 1 then). */
+int thz_tf_row_thresholds(int32_t C, int32_t Hp, int32_t Wp, const float* rowvec, const float* colvec,
+                          const float* scal, float* tau);
+
 /* ---------------------------------------------------------------------------------------------
  * thz_asm_propagate -- fused band-limited angular-spectrum propagation, optionally fused with the
  * DOE phase modulation in front of it (forward) or its adjoint behind it (backward).

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libthzdoe.so")
 
 THZ_OK = 0
+THZ_E_UNSUPPORTED = -3
 _ERR_EXC = {-1: ValueError, -2: ValueError, -3: NotImplementedError, -4: RuntimeError, -5: RuntimeError, -6: RuntimeError}
 
 
@@ -89,6 +90,7 @@ def _declare(l):
     l.thz_quant_gumbel_v3_fwd.argtypes = [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp, u64, vp]
     l.thz_quant_gumbel_naive_fwd.argtypes = [vp, vp, vp, i32, f32, vp, vp, vp, u64, vp]
     l.thz_toeplitz_gemm.argtypes = [ctypes.POINTER(ToeplitzGemmDesc), vp]
+    l.thz_tf_row_thresholds.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.thz_launch_count.restype = u64
     l.thz_profile_enable.argtypes = [i32]
     l.thz_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
@@ -104,7 +106,7 @@ EXPORTS = [
     "thz_doe_modulate_fwd", "thz_doe_modulate_bwd", "thz_height_fwd", "thz_height_bwd",
     "thz_quant_ste_fwd", "thz_quant_nn_fwd", "thz_quant_nn_bwd", "thz_quant_psq_fwd",
     "thz_quant_gumbel_v3_fwd", "thz_quant_gumbel_naive_fwd",
-    "thz_launch_count", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm",
+    "thz_launch_count", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm", "thz_tf_row_thresholds",
 ]
 
 

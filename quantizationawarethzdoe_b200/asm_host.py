@@ -113,6 +113,22 @@ def tf_vectors(Hp, Wp, spacing, wavelengths, z, bandlimit=True, bandlimit_type="
 
 
 def tf_row_thresholds(rowvec, colvec, scal):
+    """tau [C,Hp] through the library's host helper `thz_tf_row_thresholds` (include/thzdoe.h); None if the
+    band-limit quotients are not monotone (the caller then uses the cached-table mode).  Same result as
+    `_tf_row_thresholds_numpy` / `_tf_row_thresholds_dense` below, which the tests compare it with."""
+    import ctypes
+    rv, cv, sc = rowvec.contiguous(), colvec.contiguous(), scal.contiguous()
+    C, Hp, Wp = rv.shape[0], rv.shape[1], cv.shape[1]
+    tau = torch.empty(C, Hp)
+    rc = N.lib().thz_tf_row_thresholds(C, Hp, Wp, ctypes.c_void_p(rv.data_ptr()), ctypes.c_void_p(cv.data_ptr()),
+                                       ctypes.c_void_p(sc.data_ptr()), ctypes.c_void_p(tau.data_ptr()))
+    if rc == N.THZ_E_UNSUPPORTED:
+        return None
+    N.check(rc, "thz_tf_row_thresholds")
+    return tau
+
+
+def _tf_row_thresholds_numpy(rowvec, colvec, scal):
     """Fold the per-bin keep conditions into one threshold per row (natural bin order in and out).
 
     keep(r, c) = (rowvec.y[r] + colvec.y[c] <= 1) & (rowvec.z[r] + colvec.z[c] <= 1) & !(klam^2 - (Kx^2[r] + Ky^2[c]) < 0)

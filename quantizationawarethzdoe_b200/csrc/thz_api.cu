@@ -132,3 +132,42 @@ extern "C" int thz_profile_read(int32_t nclasses, float* ms_sum, int32_t* count)
     }
     return THZ_OK;
 }
+
+// ------------------------------------------------------------------------------- host helper: row thresholds
+#include <algorithm>
+#include <vector>
+extern "C" int thz_tf_row_thresholds(int32_t C, int32_t Hp, int32_t Wp, const float* rowvec, const float* colvec,
+                                     const float* scal, float* tau) {
+    if (C < 0 || Hp <= 0 || Wp <= 0) return thz_set_error(THZ_E_SHAPE, "thz_tf_row_thresholds: bad sizes");
+    if (!rowvec || !colvec || !scal || !tau) return thz_set_error(THZ_E_NULL, "thz_tf_row_thresholds: null pointer");
+    std::vector<int> order(Wp);
+    std::vector<float> ky2(Wp), b1(Wp), b2(Wp);
+    for (int c = 0; c < C; ++c) {
+        const float* cv = colvec + (size_t)c * Wp * 4;
+        const float* rv = rowvec + (size_t)c * Hp * 4;
+        const float klam2 = scal[2 * c];
+        for (int i = 0; i < Wp; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [cv](int a, int b) { return cv[4 * a] < cv[4 * b]; });
+        for (int i = 0; i < Wp; ++i) {
+            ky2[i] = cv[4 * order[i]];
+            b1[i] = cv[4 * order[i] + 1];
+            b2[i] = cv[4 * order[i] + 2];
+        }
+        for (int i = 1; i < Wp; ++i)
+            if (b1[i] < b1[i - 1] || b2[i] < b2[i - 1])
+                return thz_set_error(THZ_E_UNSUPPORTED, "thz_tf_row_thresholds: band-limit quotients not monotone in Ky^2");
+        for (int r = 0; r < Hp; ++r) {
+            const float r0 = rv[4 * r], r1 = rv[4 * r + 1], r2 = rv[4 * r + 2];
+            int lo = 0, hi = Wp;                       // sorted columns [0, lo) kept, [hi, Wp) dropped
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const bool keep = thz_add_rn(r1, b1[mid]) <= 1.f && thz_add_rn(r2, b2[mid]) <= 1.f &&
+                                  !(thz_sub_rn(klam2, thz_add_rn(r0, ky2[mid])) < 0.f);
+                if (keep) lo = mid + 1;
+                else hi = mid;
+            }
+            tau[(size_t)c * Hp + r] = lo > 0 ? ky2[lo - 1] : -1.f;
+        }
+    }
+    return THZ_OK;
+}

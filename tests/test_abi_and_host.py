@@ -133,7 +133,7 @@ def test_asm_prop_surface_and_loud_failure_without_cuda():
         a(f)
 
 
-def test_row_thresholds_binary_search_equals_dense_evaluation():
+def test_row_thresholds_binary_search_equals_dense_evaluation(lib):
     """The O((Hp+Wp) log Wp) threshold builder a depth sweep calls per z must equal the dense O(Hp Wp) evaluation
     of the reference's keep mask (Props/ASM_Prop.py:262, :290-301) bit for bit, incl. rows with no kept bin."""
     from quantizationawarethzdoe_b200 import asm_host as AH
@@ -146,4 +146,5 @@ def test_row_thresholds_binary_search_equals_dense_evaluation():
         rv, cv, sc = AH.tf_vectors(Hp, Wp, torch.tensor([dx, dy]), wl, torch.tensor(z), bl, bt)
         fast, dense = AH.tf_row_thresholds(rv, cv, sc), AH._tf_row_thresholds_dense(rv, cv, sc)
         assert fast is not None and dense is not None
-        assert torch.equal(fast, dense), (Hp, Wp, bt)
+        assert torch.equal(fast, dense), (Hp, Wp, bt)                                    # C helper (host code of the .so)
+        assert torch.equal(AH._tf_row_thresholds_numpy(rv, cv, sc), dense), (Hp, Wp, bt)  # numpy restatement

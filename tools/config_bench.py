@@ -4,6 +4,7 @@
     python tools/config_bench.py donn    # config 4: 3 x (STE DOE + ASM 200 -> 400), batch 1024, fwd + bwd
     python tools/config_bench.py c2      # config 2: 1000 -> 2000 pad, 8-level DOE, one Adam-style step (fwd + adjoint)
     python tools/config_bench.py czt     # config 3: CZT 2048^2 -> 1024^2, 16 wavelengths
+    python tools/config_bench.py zsweep  # depth sweep: the z setter is moved between forwards (experiment_extend_depth_of_focus)
 Prints one JSON line per config with device-event timings (warm, 10 repetitions)."""
 import json
 import os
@@ -100,6 +101,31 @@ def czt():
     print(json.dumps({"config": "C3 CZT 2048^2 -> 1024^2, 16 wavelengths, forward", **out}))
 
 
+def zsweep():
+    """200 propagation distances through one ASM_prop (z setter, experiment_extend_depth_of_focus.ipynb cell 5): every
+    forward rebuilds the transfer-function vectors on the host, so this measures host + device per z (wall clock)."""
+    import time
+    out = []
+    for n in (100, 1000):
+        torch.manual_seed(0)
+        asm = ASM_prop(z_distance=0.1, device=dev, padding_scale=2 if n == 100 else None)
+        asm.check_Zc = False
+        x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+        f = ElectricField(x, wavelengths=torch.tensor([1 * mm], device=dev), spacing=torch.tensor([1 * mm, 1 * mm], device=dev), device=dev)
+        zs = [0.05 + 0.001 * i for i in range(200)]
+        for z in zs[:5]:
+            asm.z = z
+            asm(f)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for z in zs:
+            asm.z = z
+            y = asm(f).data
+        torch.cuda.synchronize()
+        out.append({"n": n, "padded": asm.compute_padding(n, n)[0], "ms_per_z_wall": (time.perf_counter() - t0) / len(zs) * 1e3})
+    print(json.dumps({"config": "depth sweep, 200 z through the z setter, forward only", "cases": out}))
+
+
 if __name__ == "__main__":
-    for w in (sys.argv[1:] or ["donn", "c2", "czt"]):
-        {"donn": donn, "c2": c2, "czt": czt}[w]()
+    for w in (sys.argv[1:] or ["donn", "c2", "czt", "zsweep"]):
+        {"donn": donn, "c2": c2, "czt": czt, "zsweep": zsweep}[w]()
