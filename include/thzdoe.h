@@ -219,6 +219,26 @@ typedef struct thz_toeplitz_gemm_desc {
 
 int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* desc, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The optimisation loop around the propagation (experiment_four_focal_spots.ipynb cell 8):
+ *     out_amp = normalize(torch.abs(out_field.data) ** 2)     utils/Helper_Functions.py:185-193
+ *     loss = nn.MSELoss()(out_amp, target);  loss.backward();  optimizer.step()   (torch.optim.Adam / AdamW)
+ *
+ * thz_normmse_loss: y complex64 [B, n_per_b], target float32 [B, n_per_b]; normalize divides each batch entry
+ *   by its maximum intensity.  Writes loss float32[1] and, if gy != NULL, gy complex64 [B, n_per_b] = d loss / d y
+ *   exactly as autograd forms it: through the division, through max() into the FIRST maximal element, and
+ *   through abs()**2 (gy = 2 dL/dI y).  scratch: >= 12*B bytes of device memory.  n_per_b <= 2^32.
+ * thz_adam_step: one Adam (decoupled = 0, weight decay added to the gradient) or AdamW (decoupled = 1) update of
+ *   n float32 parameters; m, v are the running moments; step is a device int32 holding the number of updates
+ *   done so far (bias correction uses *step + 1) and is incremented afterwards if `advance` != 0 -- pass
+ *   advance = 1 for the last tensor of a parameter group.  No host-side state, so the launch sequence can be
+ *   captured in a CUDA graph.
+ * ------------------------------------------------------------------------------------------- */
+int thz_normmse_loss(const void* y, const void* target, int32_t B, uint64_t n_per_b, void* scratch, void* loss,
+                     void* gy, void* stream);
+int thz_adam_step(void* p, const void* g, void* m, void* v, void* step, uint64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int32_t decoupled, int32_t advance, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -204,6 +204,29 @@ def gen_czt(R):
              out_dx=np.float64(dxo), out_spacing=y.spacing)
 
 
+def gen_train(R):
+    """Loss / optimizer lines of the notebook loop: the reference's own normalize + nn.MSELoss, torch's own Adam / AdamW."""
+    torch.manual_seed(7)
+    for name, (B, C, H, W) in {"train_loss_single": (1, 1, 40, 40), "train_loss_batch": (3, 2, 24, 16)}.items():
+        y = torch.randn(B, C, H, W, dtype=torch.complex64, requires_grad=True)
+        target = torch.rand(B, C, H, W)
+        out_amp = R.HF.normalize(torch.abs(y) ** 2)
+        loss = torch.nn.MSELoss()(out_amp, target)
+        (gy,) = torch.autograd.grad(loss, y)
+        save(name, y=y, target=target, loss=loss, gy=gy)
+    p0 = torch.randn(50, 30)
+    grads = [torch.randn(50, 30) * (0.5 + 0.1 * i) for i in range(6)]
+    for name, (wd, dec) in {"train_adam": (0.0, False), "train_adam_wd": (0.05, False), "train_adamw": (0.01, True)}.items():
+        p = torch.nn.Parameter(p0.clone())
+        opt = (torch.optim.AdamW if dec else torch.optim.Adam)([p], lr=0.02, weight_decay=wd)
+        hist = []
+        for g in grads:
+            p.grad = g.clone()
+            opt.step()
+            hist.append(p.detach().clone())
+        save(name, p0=p0, grads=torch.stack(grads), hist=torch.stack(hist), weight_decay=np.float64(wd), decoupled=np.int64(dec))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = import_reference()
@@ -211,3 +234,4 @@ if __name__ == "__main__":
     gen_doe(R)
     gen_quant(R)
     gen_czt(R)
+    gen_train(R)

@@ -15,9 +15,7 @@ from .Components.QuantizedDOE import (
     NaiveGumbelQuantizedDOELayer, STEQuantizationFunction, ste_quan,
 )
 
-try:  # CZT lands in a later milestone of this round
-    from .Props.CZT_Prop import CZT_prop
-except ImportError:  # pragma: no cover
-    CZT_prop = None
+from .Props.CZT_Prop import CZT_prop
+from .train import FusedAdam, normalized_intensity_mse
 
 __version__ = "0.1.0"

@@ -91,6 +91,8 @@ def _declare(l):
     l.thz_quant_gumbel_naive_fwd.argtypes = [vp, vp, vp, i32, f32, vp, vp, vp, u64, vp]
     l.thz_toeplitz_gemm.argtypes = [ctypes.POINTER(ToeplitzGemmDesc), vp]
     l.thz_tf_row_thresholds.argtypes = [i32, i32, i32, vp, vp, vp, vp]
+    l.thz_normmse_loss.argtypes = [vp, vp, i32, u64, vp, vp, vp, vp]
+    l.thz_adam_step.argtypes = [vp, vp, vp, vp, vp, u64, f32, f32, f32, f32, f32, i32, i32, vp]
     l.thz_launch_count.restype = u64
     l.thz_profile_enable.argtypes = [i32]
     l.thz_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
@@ -107,6 +109,7 @@ EXPORTS = [
     "thz_quant_ste_fwd", "thz_quant_nn_fwd", "thz_quant_nn_bwd", "thz_quant_psq_fwd",
     "thz_quant_gumbel_v3_fwd", "thz_quant_gumbel_naive_fwd",
     "thz_launch_count", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm", "thz_tf_row_thresholds",
+    "thz_normmse_loss", "thz_adam_step",
 ]
 
 

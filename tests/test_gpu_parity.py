@@ -364,3 +364,97 @@ def test_step_is_cuda_graph_capturable(dev):
     fresh = step()
     assert torch.equal(static_gw, fresh)
     assert not torch.equal(static_gw, eager)
+
+
+# ------------------------------------------------------------------------------- loss + optimizer
+@pytest.mark.parametrize("name", golden_names("train_loss"))
+def test_normalized_intensity_mse_matches_reference(name, dev):
+    """Fused normalize(|y|^2) + MSE loss and its gradient wrt the complex field vs the reference's own lines
+    (utils/Helper_Functions.py:185-193 + nn.MSELoss + autograd, incl. the gradient through max())."""
+    from quantizationawarethzdoe_b200 import normalized_intensity_mse
+    g = golden(name)
+    y = g["y"].to(dev).requires_grad_(True)
+    loss = normalized_intensity_mse(y, g["target"].to(dev))
+    (gy,) = torch.autograd.grad(loss, y)
+    assert abs(float(loss) - g["loss"]) <= 1e-6 * abs(g["loss"])
+    assert rel_l2(gy.cpu(), g["gy"]) <= 1e-6
+
+
+def test_normalized_intensity_mse_large_vs_oracle(dev):
+    from oracle import train_oracle as TO
+    from quantizationawarethzdoe_b200 import normalized_intensity_mse
+    torch.manual_seed(3)
+    y = torch.randn(2, 3, 300, 257, dtype=torch.complex64)
+    t = torch.rand(2, 3, 300, 257)
+    lo, go = TO.normalized_intensity_mse(y, t)
+    yd = y.to(dev).requires_grad_(True)
+    loss = normalized_intensity_mse(yd, t.to(dev))
+    (gy,) = torch.autograd.grad(loss, yd)
+    assert abs(float(loss) - float(lo)) <= 2e-6 * float(lo)
+    assert rel_l2(gy.cpu(), go) <= 2e-6
+    # the same call without a gradient request, and an upstream factor
+    assert abs(float(normalized_intensity_mse(y.to(dev), t.to(dev))) - float(lo)) <= 2e-6 * float(lo)
+    (g3,) = torch.autograd.grad(3.0 * normalized_intensity_mse(yd, t.to(dev)), yd)
+    assert rel_l2(g3.cpu(), 3.0 * go) <= 2e-6
+
+
+@pytest.mark.parametrize("name", golden_names("train_adam"))
+def test_fused_adam_matches_torch(name, dev):
+    """FusedAdam (device-side step counter) vs torch.optim.Adam / AdamW over 6 steps (fp32 bias corrections on the
+    device instead of torch's float64 host scalars: <= 1e-6 relative)."""
+    from quantizationawarethzdoe_b200 import FusedAdam
+    g = golden(name)
+    p = torch.nn.Parameter(g["p0"].to(dev))
+    opt = FusedAdam([p], lr=0.02, weight_decay=g["weight_decay"], decoupled_weight_decay=bool(g["decoupled"]))
+    for i in range(g["grads"].shape[0]):
+        p.grad = g["grads"][i].to(dev)
+        opt.step()
+        assert rel_l2(p.detach().cpu(), g["hist"][i]) <= 1e-6, i
+    assert int(opt.state[p]["step"].item()) == g["grads"].shape[0]
+
+
+def test_whole_iteration_replays_as_one_cuda_graph(dev):
+    """DOE -> ASM -> normalized-intensity MSE -> backward -> FusedAdam captured once and replayed: the weights after
+    three replays equal three eager iterations (same kernels, same order)."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, FusedAdam, STEQuantizedDOELayer, normalized_intensity_mse
+    n = 64
+    params = dict(doe_size=[n, n], doe_dxy=1 * mm, doe_level=4, height_constraint_max=1 * mm, tolerance=None, material=[2.66, 0.003])
+    torch.manual_seed(5)
+    x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+    target = torch.rand(1, 1, n, n, device=dev)
+    lam, sp = torch.tensor([1 * mm], device=dev), torch.tensor([1 * mm, 1 * mm], device=dev)
+
+    def build():
+        torch.manual_seed(11)
+        doe = STEQuantizedDOELayer(params, {}, device=dev)
+        asm = ASM_prop(z_distance=0.05, device=dev)
+        asm.check_Zc = False
+        opt = FusedAdam(doe.parameters(), lr=0.02)
+        return doe, asm, opt
+
+    def iteration(doe, asm, opt):
+        out = asm(doe(ElectricField(x, wavelengths=lam, spacing=sp, device=dev)))
+        loss = normalized_intensity_mse(out.data, target)
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        opt.step()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        doe_e, asm_e, opt_e = build()
+        for _ in range(4):
+            iteration(doe_e, asm_e, opt_e)
+        doe_g, asm_g, opt_g = build()
+        iteration(doe_g, asm_g, opt_g)                       # warm-up: allocates state, builds the plan
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        iteration(doe_g, asm_g, opt_g)                       # capture records, does not execute
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert int(opt_g.state[doe_g.weight_height_map]["step"].item()) == 4
+    assert rel_l2(doe_g.weight_height_map.detach().cpu(), doe_e.weight_height_map.detach().cpu()) <= 1e-6

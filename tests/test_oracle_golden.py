@@ -134,3 +134,21 @@ def test_czt_oracle_matches_reference_vectors(name):
     assert torch.equal(torch.view_as_real(y), torch.view_as_real(g["y"]))            # FFT restatement: bit-exact
     yd = CO.czt_forward_dense(*args)
     assert rel_l2(yd, g["y"]) < 1e-5                                                   # dense separable form the GEMM path uses
+
+
+@pytest.mark.parametrize("name", golden_names("train_loss"))
+def test_loss_oracle_matches_reference_vectors(name):
+    """normalize + MSELoss restatement vs the reference's own normalize (utils/Helper_Functions.py:185-193)."""
+    from oracle import train_oracle as TO
+    g = golden(name)
+    loss, gy = TO.normalized_intensity_mse(g["y"], g["target"])
+    assert abs(float(loss) - g["loss"]) <= 1e-7 * abs(g["loss"])
+    assert rel_l2(gy, g["gy"]) <= 1e-7
+
+
+@pytest.mark.parametrize("name", golden_names("train_adam"))
+def test_adam_oracle_matches_torch_optimizers(name):
+    from oracle import train_oracle as TO
+    g = golden(name)
+    hist = TO.adam_reference(g["p0"], list(g["grads"]), lr=0.02, weight_decay=g["weight_decay"], decoupled=bool(g["decoupled"]))
+    assert torch.equal(torch.stack(hist), g["hist"])

@@ -4,6 +4,7 @@
     python tools/config_bench.py donn    # config 4: 3 x (STE DOE + ASM 200 -> 400), batch 1024, fwd + bwd
     python tools/config_bench.py c2      # config 2: 1000 -> 2000 pad, 8-level DOE, one Adam-style step (fwd + adjoint)
     python tools/config_bench.py czt     # config 3: CZT 2048^2 -> 1024^2, 16 wavelengths
+    python tools/config_bench.py iteration  # configs 1 / 2 as a whole optimisation iteration (loss + Adam), eager and CUDA graph
     python tools/config_bench.py zsweep  # depth sweep: the z setter is moved between forwards (experiment_extend_depth_of_focus)
 Prints one JSON line per config with device-event timings (warm, 10 repetitions)."""
 import json
@@ -101,6 +102,42 @@ def czt():
     print(json.dumps({"config": "C3 CZT 2048^2 -> 1024^2, 16 wavelengths, forward", **out}))
 
 
+def iteration():
+    """One full optimisation iteration of the notebooks' loop (config 1: 512 -> 1024 pad, 4-level STE DOE): DOE -> ASM ->
+    normalize(|y|^2) + MSE -> backward -> Adam, eager and as one replayed CUDA graph."""
+    from quantizationawarethzdoe_b200 import FusedAdam, normalized_intensity_mse
+    out = []
+    for n, levels in ((512, 4), (1000, 8)):
+        torch.manual_seed(0)
+        doe = STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=0.5 * mm, doe_level=levels, height_constraint_max=1 * mm, tolerance=None,
+                                        material=[2.66, 0.003]), {}, device=dev)
+        asm = ASM_prop(z_distance=0.1, device=dev)
+        asm.check_Zc = False
+        opt = FusedAdam(doe.parameters(), lr=0.02)
+        x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+        target = torch.rand(1, 1, n, n, device=dev)
+        lam_t, sp_t = torch.tensor([1 * mm], device=dev), torch.tensor([0.5 * mm, 0.5 * mm], device=dev)
+
+        def it():
+            y = asm(doe(ElectricField(x, wavelengths=lam_t, spacing=sp_t, device=dev))).data
+            loss = normalized_intensity_mse(y, target)
+            opt.zero_grad(set_to_none=False)
+            loss.backward()
+            opt.step()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ms = timeit(it, reps=50)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            it()
+        ms_graph = timeit(graph.replay, reps=200)
+        out.append({"n": n, "levels": levels, "eager_ms": ms, "cuda_graph_ms": ms_graph, "iterations_per_s_graph": 1e3 / ms_graph})
+    print(json.dumps({"config": "full iteration: STE DOE + ASM + normalized-intensity MSE + backward + FusedAdam", "cases": out}))
+
+
 def zsweep():
     """200 propagation distances through one ASM_prop (z setter, experiment_extend_depth_of_focus.ipynb cell 5): every
     forward rebuilds the transfer-function vectors on the host, so this measures host + device per z (wall clock)."""
@@ -128,4 +165,4 @@ def zsweep():
 
 if __name__ == "__main__":
     for w in (sys.argv[1:] or ["donn", "c2", "czt", "zsweep"]):
-        {"donn": donn, "c2": c2, "czt": czt, "zsweep": zsweep}[w]()
+        {"donn": donn, "c2": c2, "czt": czt, "zsweep": zsweep, "iteration": iteration}[w]()
