@@ -140,50 +140,40 @@ static int set_smem_p2(K kernel, size_t bytes) {
     return THZ_OK;
 }
 
-#define THZ_P2_CASE(KERN, NN, cls, grid, block, smem, stream, args)                      \
-    case NN: {                                                                           \
-        int rc_ = set_smem_p2(KERN<NN>, smem);                                           \
-        if (rc_ != THZ_OK) return rc_;                                                   \
-        thz_launch_begin(stream, cls);                                                   \
-        KERN<NN><<<grid, block, smem, stream>>>(args);                                   \
-        thz_launch_end(stream, cls);                                                     \
-        break;                                                                           \
-    }
-#define THZ_P2_SWITCH(KERN, n, cls, grid, block, smem, stream, args)                     \
-    switch (n) {                                                                         \
-        THZ_P2_CASE(KERN, 256, cls, grid, block, smem, stream, args)                     \
-        THZ_P2_CASE(KERN, 512, cls, grid, block, smem, stream, args)                     \
-        THZ_P2_CASE(KERN, 1024, cls, grid, block, smem, stream, args)                    \
-        THZ_P2_CASE(KERN, 2048, cls, grid, block, smem, stream, args)                    \
-        THZ_P2_CASE(KERN, 4096, cls, grid, block, smem, stream, args)                    \
-        THZ_P2_CASE(KERN, 8192, cls, grid, block, smem, stream, args)                    \
-        THZ_P2_CASE(KERN, 16384, cls, grid, block, smem, stream, args)                   \
-        THZ_P2_CASE(KERN, 400, cls, grid, block, smem, stream, args)                     \
-        THZ_P2_CASE(KERN, 800, cls, grid, block, smem, stream, args)                     \
-        THZ_P2_CASE(KERN, 1600, cls, grid, block, smem, stream, args)                    \
-        THZ_P2_CASE(KERN, 2000, cls, grid, block, smem, stream, args)                    \
-        THZ_P2_CASE(KERN, 3200, cls, grid, block, smem, stream, args)                    \
-        THZ_P2_CASE(KERN, 4000, cls, grid, block, smem, stream, args)                    \
-    default:                                                                             \
-        return thz_set_error(THZ_E_UNSUPPORTED, "power-of-two fast path: size not instantiated"); \
-    }                                                                                    \
-    {                                                                                    \
-        cudaError_t e_ = cudaGetLastError();                                             \
-        if (e_ != cudaSuccess) return thz_set_cuda_error(#KERN, e_);                     \
+template <typename K, typename A>
+static int launch_p2(K kernel, const char* name, int cls, dim3 grid, int block, size_t smem, cudaStream_t stream, const A& args) {
+    int rc = set_smem_p2(kernel, smem);
+    if (rc != THZ_OK) return rc;
+    thz_launch_begin(stream, cls);
+    kernel<<<grid, block, smem, stream>>>(args);
+    thz_launch_end(stream, cls);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return thz_set_cuda_error(name, e);
+    return THZ_OK;
+}
+// one case per entry of THZ_SP_SIZES (thz_asm_p2.cuh), so that thz_sp_instantiated() and the dispatch cannot disagree
+#define THZ_P2_SWITCH(KERN, n, cls, grid, block, smem, stream, args)                                        \
+    switch (n) {                                                                                            \
+        THZ_SP_SIZES(THZ_P2_X)                                                                              \
+    default:                                                                                                \
+        return thz_set_error(THZ_E_UNSUPPORTED, "static fast path: size not instantiated");                 \
     }
 
 int thz_p2_launch_k1(const RowFwdArgs& a, int grid, int threads, size_t smem, cudaStream_t stream) {
     // persistent CTAs: a few per SM, each walking line groups bx, bx + grid, ... (software pipeline inside)
     const int resident = thz_sm_count() * (a.Wp >= 8192 ? 1 : 3);
     if (grid > resident) grid = resident;
+#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k1<NN>, "thz_p2_k1", THZ_KC_ROW_FWD, dim3(grid), threads, smem, stream, a);
     THZ_P2_SWITCH(thz_p2_k1, a.Wp, THZ_KC_ROW_FWD, grid, threads, smem, stream, a)
-    return THZ_OK;
+#undef THZ_P2_X
 }
 int thz_p2_launch_k2(const ColArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream) {
+#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k2<NN>, "thz_p2_k2", THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a);
     THZ_P2_SWITCH(thz_p2_k2, a.Hp, THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a)
-    return THZ_OK;
+#undef THZ_P2_X
 }
 int thz_p2_launch_k3(const RowInvArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream) {
+#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k3<NN>, "thz_p2_k3", THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a);
     THZ_P2_SWITCH(thz_p2_k3, a.Wp, THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a)
-    return THZ_OK;
+#undef THZ_P2_X
 }

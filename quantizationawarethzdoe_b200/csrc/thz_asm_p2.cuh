@@ -15,7 +15,7 @@
 
 // lengths with a compiled static path: powers of two 256 .. 16384 and the multiples of 16 of the form 25*16*2^a / 25*20*4*2^a
 // that the BASELINE configs and the reference notebooks produce (200 -> 400, 1000 -> 2000, ...)
-#define THZ_SP_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384) X(400) X(800) X(1600) X(2000) X(3200) X(4000)
+#define THZ_SP_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384) X(400) X(800) X(1600) X(2000) X(3200) X(4000) X(768) X(1536) X(3072) X(6144)
 THZ_HD constexpr bool thz_sp_instantiated(int n) {
 #define THZ_SP_CMP(NN) if (n == NN) return true;
     THZ_SP_SIZES(THZ_SP_CMP)

@@ -188,21 +188,11 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
         }
 }
 
-#define P2_DISPATCH(FN, n, ...)                      \
+// one case per entry of THZ_SP_SIZES, like the library's own dispatch
+#define P2_CASE_X(NN) case NN: P2_FN<NN> P2_ARGS; break;
+#define P2_DISPATCH(n)                               \
     switch (n) {                                     \
-    case 256: FN<256>(__VA_ARGS__); break;           \
-    case 512: FN<512>(__VA_ARGS__); break;           \
-    case 1024: FN<1024>(__VA_ARGS__); break;         \
-    case 2048: FN<2048>(__VA_ARGS__); break;         \
-    case 4096: FN<4096>(__VA_ARGS__); break;         \
-    case 8192: FN<8192>(__VA_ARGS__); break;         \
-    case 16384: FN<16384>(__VA_ARGS__); break;       \
-    case 400: FN<400>(__VA_ARGS__); break;           \
-    case 800: FN<800>(__VA_ARGS__); break;           \
-    case 1600: FN<1600>(__VA_ARGS__); break;         \
-    case 2000: FN<2000>(__VA_ARGS__); break;         \
-    case 3200: FN<3200>(__VA_ARGS__); break;         \
-    case 4000: FN<4000>(__VA_ARGS__); break;         \
+        THZ_SP_SIZES(P2_CASE_X)                      \
     default: return THZ_E_UNSUPPORTED;               \
     }
 
@@ -227,17 +217,29 @@ extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
         }
         if (!(stages & 1)) {
         } else if (L.p2_w) {
-            P2_DISPATCH(run_p2_k1, d->Wp, L.k1, L.k1_grid, L.k1_threads, L.k1_smem)
+#define P2_FN run_p2_k1
+#define P2_ARGS (L.k1, L.k1_grid, L.k1_threads, L.k1_smem)
+            P2_DISPATCH(d->Wp)
+#undef P2_FN
+#undef P2_ARGS
         } else if (L.mixed_w) run_k1<true>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
         else run_k1<false>(L.k1, L.k1_grid, L.k1_threads, L.k1_smem);
         if (!(stages & 2)) {
         } else if (L.p2_h) {
-            P2_DISPATCH(run_p2_k2, d->Hp, L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem)
+#define P2_FN run_p2_k2
+#define P2_ARGS (L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem)
+            P2_DISPATCH(d->Hp)
+#undef P2_FN
+#undef P2_ARGS
         } else if (L.mixed_h) run_k2<true>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
         else run_k2<false>(L.k2, L.k2_gridx, nbc, L.k2_threads, L.k2_smem);
         if (!(stages & 4)) {
         } else if (L.p2_w) {
-            P2_DISPATCH(run_p2_k3, d->Wp, L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem)
+#define P2_FN run_p2_k3
+#define P2_ARGS (L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem)
+            P2_DISPATCH(d->Wp)
+#undef P2_FN
+#undef P2_ARGS
         } else if (L.mixed_w) run_k3<true>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
         else run_k3<false>(L.k3, L.k3_gridx, L.k3_gridy, L.k3_threads, L.k3_smem);
     }

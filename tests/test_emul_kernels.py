@@ -63,6 +63,8 @@ CASES = [
     (2, 1, 200, 200, None, [1e-3], 0.5e-3, 0.05, {}),                                    # 400 x 400 = (25*16)^2, in-register H
     (1, 1, 1000, 128, None, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                          # 2000 (25*20*4) x 256
     (1, 2, 128, 400, None, [1e-3, 1.1e-3], 0.5e-3, 0.1, dict(mode=1)),                   # 256 x 800 (25*16*2)
+    (1, 1, 256, 128, 2, [1e-3], 0.5e-3, 0.1, dict(mode=1)),                              # padding_scale 2: 768 (12*8*8) x 384 (generic)
+    (1, 1, 512, 256, 2, [1e-3], 0.5e-3, 0.1, {}),                                        # 1536 (12*16*8) x 768, in-register H
 ]
 
 

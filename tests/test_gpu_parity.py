@@ -242,20 +242,27 @@ def test_errors_cross_the_abi_as_python_exceptions(dev):
         a(ElectricField(torch.zeros(1, 1, 16, 16, dtype=torch.complex128, device=dev), 1e-3, 1e-3, device=dev))
 
 
-def test_power_of_two_fast_path_agrees_with_generic_engine(dev, monkeypatch):
-    """The compile-time specialised kernels and the runtime-planned engine must give the same field
-    (same algorithm, same twiddles): run both on one input (THZ_NO_P2=1 selects the generic engine)."""
+@pytest.mark.parametrize("H,W,scale", [(512, 1024, None),      # 1024 x 2048
+                                       (256, 512, 2),          # padding_scale 2 (the notebooks): 768 x 1536
+                                       (1024, 200, 2)])        # 3072 x 600 (600 = generic engine)
+def test_static_fast_path_agrees_with_generic_engine(H, W, scale, dev, monkeypatch):
+    """The compile-time specialised kernels and the runtime-planned engine must give the same field and the same
+    adjoint (same algorithm, same twiddles): run both on one input (THZ_NO_P2=1 selects the generic engine)."""
     from quantizationawarethzdoe_b200 import ASM_prop, ElectricField
     torch.manual_seed(5)
-    x = torch.randn(2, 2, 512, 1024, dtype=torch.complex64, device=dev)
+    x = torch.randn(2, 2, H, W, dtype=torch.complex64, device=dev)
     lams = [1 * mm, 1.02 * mm]
     outs = []
     for flag in ("0", "1"):
         monkeypatch.setenv("THZ_NO_P2", flag)
-        a = ASM_prop(z_distance=0.1, device=dev)
+        a = ASM_prop(z_distance=0.1, device=dev, padding_scale=scale)
         a.check_Zc = False
-        outs.append(a(ElectricField(x, wavelengths=lams, spacing=0.5 * mm, device=dev)).data)
-    assert rel_l2(outs[0].cpu(), outs[1].cpu()) < 1e-6
+        xr = x.clone().requires_grad_(True)
+        y = a(ElectricField(xr, wavelengths=lams, spacing=0.5 * mm, device=dev)).data
+        (gx,) = torch.autograd.grad(y, xr, y.detach())
+        outs.append((y.detach().cpu(), gx.cpu()))
+    assert rel_l2(outs[0][0], outs[1][0]) < 1e-6
+    assert rel_l2(outs[0][1], outs[1][1]) < 1e-6
 
 
 @pytest.fixture(params=["tc", "simt"])
