@@ -50,11 +50,17 @@ def emul_lib():
     csrc = os.path.join(ROOT, "quantizationawarethzdoe_b200", "csrc")
     deps = [EMUL_SRC, os.path.join(ROOT, "include", "thzdoe.h")] + [
         os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
-    stale = not os.path.isfile(EMUL_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMUL_SO) for d in deps)
+    # THZ_EMUL_ASAN=1: AddressSanitizer build of the replay (shared memory and workspaces are heap buffers there, so every
+    # out-of-bounds access of a kernel body is caught).  Needs LD_PRELOAD=$(gcc -print-file-name=libasan.so) and
+    # ASAN_OPTIONS=detect_leaks=0 on the pytest command line; compute-sanitizer is not available on the GPU pool.
+    asan = os.environ.get("THZ_EMUL_ASAN") == "1"
+    so = EMUL_SO.replace(".so", "_asan.so") if asan else EMUL_SO
+    stale = not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps)
     if stale:
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-I/usr/local/cuda/include", "-o", EMUL_SO, EMUL_SRC])
-    E = ctypes.CDLL(EMUL_SO)
+        extra = ["-fsanitize=address", "-fno-omit-frame-pointer", "-O1", "-g"] if asan else ["-O2"]
+        subprocess.check_call(["g++", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared"] + extra +
+                              ["-I/usr/local/cuda/include", "-o", so, EMUL_SRC])
+    E = ctypes.CDLL(so)
     E.thz_emul_asm_propagate.argtypes = [ctypes.POINTER(N.AsmDesc), ctypes.c_int]
     E.thz_emul_slot_to_bin.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     E.thz_emul_plan_info.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
