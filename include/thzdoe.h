@@ -49,6 +49,8 @@ const char* thz_last_error(void);
 int thz_fft_plan_info(int32_t n, int32_t* radices, int32_t* nstages);
 int thz_fft_slot_to_bin(int32_t n, int32_t* slot_to_bin);
 int thz_fft_twiddles(int32_t n, float* tw);
+/* 1 if length n is served by the compile-time specialised ("static") kernels, else 0 (runtime-planned engine). */
+int thz_fft_is_static(int32_t n);
 
 /* thz_tf_row_thresholds (host-only helper of tf_mode 0): folds the reference's per-bin keep conditions
  *   (rowvec.y[r] + colvec.y[c] <= 1) && (rowvec.z[r] + colvec.z[c] <= 1) && !(klam2 - (rowvec.x[r] + colvec.x[c]) < 0)
@@ -116,6 +118,18 @@ typedef struct thz_asm_desc {
     int32_t stages;            /* 0 = whole pipeline; else bit mask 1 = row FFT (x -> ws), 2 = column pass (ws in
                                   place), 4 = row iFFT + epilogue (ws -> y): the slab-decomposed multi-GPU FFT runs
                                   the three stages separately around its all-to-all transposes                 */
+    /* Slab-decomposed FFT over peer memory (NVLink P2P), slab_parts > 1, stages == 1 or stages == 4 only:
+       the intermediate lives as COLUMN slabs, one per GPU: slab_ptrs[d] = complex64 [B*C][slab_rows][Wp/slab_parts] on
+       GPU d (peer-mapped pointers; d == own rank is the local buffer).  stages == 1: the row-FFT kernel writes segment d
+       of each of its rows (local row r = global row slab_row0 + r) straight into slab_ptrs[d] -- the transpose happens
+       in the kernel's stores, no all-to-all.  stages == 4: the row-iFFT kernel gathers segment d of its rows from
+       slab_ptrs[d].  ws is not used.  The caller orders the stages across GPUs (a barrier after stage 1 and one after
+       stage 2).  Static-path widths only (THZ_E_UNSUPPORTED otherwise).                                              */
+    int32_t slab_parts;        /* 0 or 1: off                                                               */
+    int32_t slab_row0;         /* global row index of this GPU's first row                                  */
+    int32_t slab_rows;         /* rows per field in every column slab                                       */
+    int32_t slab_reserved;
+    void* slab_ptrs[8];
 } thz_asm_desc;
 
 uint64_t thz_asm_workspace_bytes(const thz_asm_desc* desc);

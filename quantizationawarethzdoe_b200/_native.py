@@ -43,6 +43,9 @@ class AsmDesc(ctypes.Structure):
         ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_uint64),
         ("bc_chunk", ctypes.c_int32), ("tune_k2_cols", ctypes.c_int32),
         ("tune_lines", ctypes.c_int32), ("stages", ctypes.c_int32),
+        ("slab_parts", ctypes.c_int32), ("slab_row0", ctypes.c_int32),
+        ("slab_rows", ctypes.c_int32), ("slab_reserved", ctypes.c_int32),
+        ("slab_ptrs", ctypes.c_void_p * 8),
     ]
 
 
@@ -74,6 +77,7 @@ def _declare(l):
     l.thz_fft_plan_info.argtypes = [i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     l.thz_fft_slot_to_bin.argtypes = [i32, ctypes.POINTER(i32)]
     l.thz_fft_twiddles.argtypes = [i32, ctypes.POINTER(ctypes.c_float)]
+    l.thz_fft_is_static.argtypes = [i32]
     l.thz_asm_workspace_bytes.argtypes = [ctypes.POINTER(AsmDesc)]
     l.thz_asm_workspace_bytes.restype = u64
     l.thz_asm_propagate.argtypes = [ctypes.POINTER(AsmDesc), vp]
@@ -109,7 +113,7 @@ EXPORTS = [
     "thz_quant_ste_fwd", "thz_quant_nn_fwd", "thz_quant_nn_bwd", "thz_quant_psq_fwd",
     "thz_quant_gumbel_v3_fwd", "thz_quant_gumbel_naive_fwd",
     "thz_launch_count", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm", "thz_tf_row_thresholds",
-    "thz_normmse_loss", "thz_adam_step",
+    "thz_normmse_loss", "thz_adam_step", "thz_fft_is_static",
 ]
 
 

@@ -248,7 +248,7 @@ def doe_coefficients(wavelengths, epsilon, tand):
 
 def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, out_c0, tf_mode, tf_conj,
                rowvec, colvec, scal, table, doe_mode, doe_base, hmap, coef, xsaved, gh, tw_h, tw_w, ws,
-               bc_chunk=0, tune_k2_cols=0, tune_lines=0, stages=0):
+               bc_chunk=0, tune_k2_cols=0, tune_lines=0, stages=0, slab=None):
     """Fill a thz_asm_desc from tensors (device or, in the CPU replay tests, host tensors)."""
     d = N.AsmDesc()
     d.B, d.C, d.inH, d.inW, d.Hp, d.Wp = B, C, inH, inW, Hp, Wp
@@ -261,6 +261,10 @@ def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, o
     d.tw_h, d.tw_w = N.ptr(tw_h), N.ptr(tw_w)
     d.ws = N.ptr(ws)
     d.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
+    if slab is not None:          # (parts, row0, rows, [pointer of every rank's column slab]); see thz_asm_desc.slab_*
+        d.slab_parts, d.slab_row0, d.slab_rows = int(slab[0]), int(slab[1]), int(slab[2])
+        for i, q in enumerate(slab[3]):
+            d.slab_ptrs[i] = int(q)
     d.bc_chunk, d.tune_k2_cols, d.tune_lines, d.stages = bc_chunk, tune_k2_cols, tune_lines, stages
     return d
 

@@ -133,6 +133,12 @@ extern "C" int thz_profile_read(int32_t nclasses, float* ms_sum, int32_t* count)
     return THZ_OK;
 }
 
+#include "thz_asm_p2.cuh"
+extern "C" int thz_fft_is_static(int32_t n) {
+    const char* off = getenv("THZ_NO_P2");
+    return (off && off[0] == '1') ? 0 : (thz_sp_instantiated(n) ? 1 : 0);
+}
+
 // ------------------------------------------------------------------------------- host helper: row thresholds
 #include <algorithm>
 #include <vector>

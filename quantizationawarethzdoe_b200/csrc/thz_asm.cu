@@ -116,7 +116,8 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = thz_asm_validate(d);
     if (rc != THZ_OK) return thz_set_error(rc, "thz_asm_propagate: invalid descriptor");
-    if (d->ws_bytes < thz_asm_ws_bytes(d)) return thz_set_error(THZ_E_WORKSPACE, "thz_asm_propagate: workspace too small");
+    if (d->slab_parts <= 1 && d->ws_bytes < thz_asm_ws_bytes(d))
+        return thz_set_error(THZ_E_WORKSPACE, "thz_asm_propagate: workspace too small");
     const int nbc_all = d->B * d->C;
     const int chunk = (int)thz_asm_chunk_fields(d);
     const int sm_count = thz_sm_count();

@@ -66,6 +66,17 @@ THZ_HD cpx thz_tf_value(float2 rv, float ky2, float2 sc, int conj) {
 }
 
 // =============================================================================== K1: row forward
+// Column slabs of a multi-GPU slab FFT (see thz_asm_desc.slab_*): element p of global row (row0 + r) of field f lives in
+// slab d = p / Wc at ptr[d][(f * rows + row0 + r) * Wc + p % Wc]; ptr[d] may be peer memory.
+struct SlabArgs {
+    int parts, row0, rows, Wc;
+    cpx* ptr[8];
+};
+THZ_HD cpx* thz_slab_addr(const SlabArgs& sl, int f, int r, int p) {
+    const int d = p / sl.Wc;
+    return sl.ptr[d] + ((size_t)f * sl.rows + (sl.row0 + r)) * sl.Wc + (p - d * sl.Wc);
+}
+
 struct RowFwdArgs {
     const cpx* x;             // [nbc][inH][inW] (already offset to the chunk)
     cpx* T;                   // [nbc][rowsT][Wp]
@@ -78,6 +89,7 @@ struct RowFwdArgs {
     const cpx* tw;
     DoeArgs doe;
     int conj_in;              // conjugate on load (inverse transforms via conj . FFT . conj)
+    SlabArgs slab;            // parts > 1: scatter the output rows into column slabs instead of T
 };
 
 THZ_HD void k1_load(const RowFwdArgs& a, cpx* s, int bx, int tid, int nthreads) {
@@ -250,6 +262,7 @@ struct RowInvArgs {
     const cpx* xsaved;        // [nbc][outH][outW] field that entered the DOE
     float* gh;                // [outH][outW]
     int gh_atomic;            // 1: several CTAs contribute to one gh element -> atomicAdd
+    SlabArgs slab;            // parts > 1: gather the input rows from column slabs instead of T
 };
 
 THZ_HD void k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nthreads) {

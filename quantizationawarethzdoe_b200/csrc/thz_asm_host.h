@@ -29,7 +29,7 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     const int st = d->stages ? d->stages : 7;
     if (st < 0 || st > 7) return THZ_E_SHAPE;
     if (st != 7 && d->bc_chunk > 0 && d->bc_chunk < d->B * d->C) return THZ_E_SHAPE;   // staged runs keep all fields in ws
-    if (((st & 1) && !d->x) || !d->tw_h || !d->tw_w || !d->ws) return THZ_E_NULL;
+    if (((st & 1) && !d->x) || !d->tw_h || !d->tw_w || (!d->ws && d->slab_parts <= 1)) return THZ_E_NULL;
     if (d->B < 1 || d->C < 1 || d->inH < 1 || d->inW < 1 || d->outH < 1 || d->outW < 1) return THZ_E_SHAPE;
     if (d->in_r0 < 0 || d->in_c0 < 0 || d->out_r0 < 0 || d->out_c0 < 0) return THZ_E_SHAPE;
     if (d->in_r0 + d->inH > d->Hp || d->in_c0 + d->inW > d->Wp) return THZ_E_SHAPE;
@@ -41,6 +41,12 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     if (d->doe_mode != 0 && (!d->doe_hmap || !d->doe_coef)) return THZ_E_NULL;
     if ((st & 4) && d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
     if ((st & 4) && d->doe_mode != 2 && !d->y) return THZ_E_NULL;
+    if (d->slab_parts > 1) {
+        if (d->slab_parts > 8 || (st != 1 && st != 4) || d->Wp % d->slab_parts || d->slab_rows < 1 || d->slab_row0 < 0) return THZ_E_SHAPE;
+        if (d->slab_row0 + (st == 1 ? d->inH : d->outH) > d->slab_rows) return THZ_E_SHAPE;
+        for (int i = 0; i < d->slab_parts; ++i)
+            if (!d->slab_ptrs[i]) return THZ_E_NULL;
+    }
     return THZ_OK;
 }
 
@@ -128,6 +134,18 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a1.doe.coef = (const float4*)d->doe_coef;
     a1.doe.base = d->doe_base;
     a1.conj_in = 0;
+    memset(&a1.slab, 0, sizeof(a1.slab));
+    memset(&L->k3.slab, 0, sizeof(L->k3.slab));
+    if (d->slab_parts > 1) {
+        SlabArgs sl;
+        sl.parts = d->slab_parts;
+        sl.row0 = d->slab_row0;
+        sl.rows = d->slab_rows;
+        sl.Wc = d->Wp / d->slab_parts;
+        for (int i = 0; i < 8; ++i) sl.ptr[i] = i < d->slab_parts ? (cpx*)d->slab_ptrs[i] : nullptr;
+        a1.slab = sl;
+        L->k3.slab = sl;
+    }
     {
         // enough lines per CTA to give 256 threads at least one radix-16 butterfly each
         int lines = thz_imax(1, 4096 / d->Wp);
@@ -220,5 +238,6 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k3_smem = lines * line_bytes_w;
     }
     thz_asm_apply_p2(d, nbc, sm_count, L);
+    if (d->slab_parts > 1 && !L->p2_w) return THZ_E_UNSUPPORTED;   // only the static row kernels scatter / gather slabs
     return THZ_OK;
 }

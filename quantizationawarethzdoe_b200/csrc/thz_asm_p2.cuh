@@ -139,8 +139,12 @@ THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int n
         const int gl = bx * LINES + l;
         if (gl >= total_lines) break;
         const int f = gl / a.inH, r = gl - f * a.inH;
-        cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         const cpx* sl = s + l * PITCH;
+        if (a.slab.parts > 1) {           // slab FFT: the transpose happens here, segment d of the row goes to GPU d
+            for (int p = tid; p < N; p += nt) *thz_slab_addr(a.slab, f, r, p) = sl[p + (p >> 4)];
+            continue;
+        }
+        cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         for (int p = tid; p < N; p += nt) tr[p] = sl[p + (p >> 4)];
     }
 }
@@ -254,8 +258,12 @@ THZ_HD void p2k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int n
     for (int l = 0; l < LINES; ++l) {
         const int r = bx * LINES + l;
         if (r >= a.outH) break;
-        const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         cpx* sl = s + l * PITCH;
+        if (a.slab.parts > 1) {           // slab FFT: gather the row from the column slabs of all GPUs
+            for (int p = tid; p < N; p += nt) sl[p + (p >> 4)] = *thz_slab_addr(a.slab, f, r, p);
+            continue;
+        }
+        const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         for (int p = tid; p < N; p += nt) sl[p + (p >> 4)] = tr[p];
     }
 }
@@ -269,8 +277,12 @@ THZ_HD void p2k3_prefetch(const RowInvArgs& a, cpx* s, int bx, int f, int tid, i
     for (int l = 0; l < LINES; ++l) {
         const int r = bx * LINES + l;
         if (r >= a.outH) break;
-        const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         cpx* sl = s + l * PITCH;
+        if (a.slab.parts > 1) {
+            for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), thz_slab_addr(a.slab, f, r, p));
+            continue;
+        }
+        const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), tr + p);
     }
 }

@@ -14,7 +14,9 @@ from . import asm_host as AH
 BASE_PLANE_THICKNESS = 2 * 1e-3   # Components/QuantizedDOE.py:23
 
 # tuning knobs (bench.py / tests may override): fields per kernel group, K2 tile width, rows per CTA
-TUNE = {"bc_chunk": 0, "k2_cols": 0, "lines": 0}
+import os as _os
+
+TUNE = {"bc_chunk": int(_os.environ.get("THZ_BC_CHUNK", "0")), "k2_cols": 0, "lines": 0}   # 0 = library defaults
 
 _ws_cache = {}
 

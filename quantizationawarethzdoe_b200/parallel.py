@@ -92,6 +92,16 @@ class _SlabPlan:
         self.tw_h, self.tw_w, self.tw_c = N.twiddles(Hp, device), N.twiddles(Wp, device), N.twiddles(self.Wc, device)
 
 
+SLAB_TIMINGS = None     # debug: set to a list to collect (label, cuda event) marks of the next _slab_run calls
+
+
+def _mark(label):
+    if SLAB_TIMINGS is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        SLAB_TIMINGS.append((label, e))
+
+
 def _slab_run(x_local, p, conj, group):
     """One slab-decomposed propagation.  x_local [B,C,rows_local,cols] -> y_local [B,C,out_rows_local,out_cols]."""
     G, B, C = p.G, x_local.shape[0], p.C
@@ -105,39 +115,142 @@ def _slab_run(x_local, p, conj, group):
     assert x_local.shape[2] == Hl and x_local.shape[3] == inW, "local slab has the wrong shape"
     common = dict(B=B, C=C, Hp=p.Hp, tf_mode=p.tf_mode, tf_conj=1 if conj else 0, rowvec=p.rowvec, scal=p.scal,
                   doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h)
+    _mark("start")
     # ---- stage 1: row FFT of the local rows -> t1 [nbc, Hl, Wp]
     t1 = torch.empty(nbc * Hl * Wp, dtype=torch.complex64, device=dev)
     Fn._asm_call(AH.build_desc(x=x_local, y=None, inH=Hl, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Hl, outW=outW, out_r0=0,
                                out_c0=out_c0, colvec=p.colvec, table=p.table, tw_w=p.tw_w, ws=t1, stages=1, **common), dev)
+    _mark("row fft")
     # ---- transpose 1: rank j receives my rows of ITS column block
     send = t1.view(nbc, Hl, G, Wc).permute(2, 0, 1, 3).contiguous()               # [G, nbc, Hl, Wc]
     recv = _all_to_all(send, group)                                               # recv[i] = rows of rank i, my columns
     rowsT = max(inH, outH)
     t2 = torch.zeros(nbc, rowsT, Wc, dtype=torch.complex64, device=dev) if rowsT > inH else torch.empty(nbc, inH, Wc, dtype=torch.complex64, device=dev)
     t2[:, :inH] = recv.permute(1, 0, 2, 3).reshape(nbc, inH, Wc)
+    _mark("transpose 1")
     # ---- stage 2: column FFT . H . column iFFT on the local columns (in place)
     Fn._asm_call(AH.build_desc(x=None, y=None, inH=inH, inW=min(inW, Wc), Wp=Wc, in_r0=in_r0, in_c0=0, outH=outH, outW=min(outW, Wc),
                                out_r0=out_r0, out_c0=0, colvec=p.colvec, table=p.table, tw_w=p.tw_c, ws=t2, stages=2, **common), dev)
+    _mark("column pass")
     # ---- transpose 2: rank j receives its output rows of my column block
     send = t2[:, :outH].reshape(nbc, G, Ol, Wc).permute(1, 0, 2, 3).contiguous()  # [G, nbc, Ol, Wc]
     recv = _all_to_all(send, group)                                               # recv[i] = my rows, columns of rank i
     t3 = recv.permute(1, 2, 0, 3).reshape(nbc * Ol * Wp).contiguous()             # [nbc, Ol, Wp]
+    _mark("transpose 2")
     # ---- stage 3: row iFFT + crop of the local output rows
     y = torch.empty(B, C, Ol, outW, dtype=torch.complex64, device=dev)
     Fn._asm_call(AH.build_desc(x=None, y=y, inH=Ol, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Ol, outW=outW, out_r0=0,
                                out_c0=out_c0, colvec=p.colvec, table=p.table, tw_w=p.tw_w, ws=t3, stages=4, **common), dev)
+    _mark("row ifft")
     return y
+
+
+# ----------------------------------------------------------------------------- slab FFT over peer memory (NVLink P2P)
+class _PeerSlabs:
+    """One column slab [nbc, rows, Wc] per rank in symmetric memory: every rank holds peer-mapped pointers to all of
+    them, so the row-FFT kernel can store each row segment straight into its owner's slab and the row-iFFT kernel can
+    read its rows straight out of the peers' slabs -- the two transposes of the slab FFT happen inside the kernels'
+    stores / loads and overlap with the butterflies; no pack / all-to-all / unpack passes.  torch's symmetric-memory
+    allocator provides the mapping and a stream-ordered cross-GPU barrier (plumbing); the data path is ours."""
+
+    def __init__(self, numel, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.buf = symm.empty(2 * numel, dtype=torch.float32, device=device)      # complex64 as float pairs
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(q) for q in self.hdl.buffer_ptrs]
+        self.numel = numel
+
+    def local(self, nbc, rows, Wc):
+        return torch.view_as_complex(self.buf.view(-1, 2))[:nbc * rows * Wc].view(nbc, rows, Wc)
+
+    def barrier(self):
+        self.hdl.barrier()
+
+
+def _slab_stage_descs(p, x_local, y_local, rank, ptrs, conj):
+    """The three descriptors of one rank's part of a peer-memory slab propagation (stage 1 scatter, stage 2 on the local
+    column slab, stage 4 gather).  ptrs[d] = address of rank d's column slab [nbc, rowsT, Wc]."""
+    G, B, C = p.G, x_local.shape[0], p.C
+    if not conj:
+        inH, inW, in_r0, in_c0, outH, outW, out_r0, out_c0 = p.H, p.W, p.pad_h, p.pad_w, p.outH, p.outW, p.out_r0, p.out_c0
+    else:
+        inH, inW, in_r0, in_c0, outH, outW, out_r0, out_c0 = p.outH, p.outW, p.out_r0, p.out_c0, p.H, p.W, p.pad_h, p.pad_w
+    Hl, Ol, Wc, Wp = inH // G, outH // G, p.Wc, p.Wp
+    rowsT = max(inH, outH)
+    common = dict(B=B, C=C, Hp=p.Hp, tf_mode=p.tf_mode, tf_conj=1 if conj else 0, rowvec=p.rowvec, scal=p.scal,
+                  doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h, colvec=p.colvec, table=p.table)
+    d1 = AH.build_desc(x=x_local, y=None, inH=Hl, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Hl, outW=outW, out_r0=0, out_c0=out_c0,
+                       tw_w=p.tw_w, ws=None, stages=1, slab=(G, rank * Hl, rowsT, ptrs), **common)
+    d3 = AH.build_desc(x=None, y=y_local, inH=Ol, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Ol, outW=outW, out_r0=0, out_c0=out_c0,
+                       tw_w=p.tw_w, ws=None, stages=4, slab=(G, rank * Ol, rowsT, ptrs), **common)
+
+    def d2(t2):
+        return AH.build_desc(x=None, y=None, inH=inH, inW=min(inW, Wc), Wp=Wc, in_r0=in_r0, in_c0=0, outH=outH, outW=min(outW, Wc),
+                             out_r0=out_r0, out_c0=0, tw_w=p.tw_c, ws=t2, stages=2, **common)
+    return d1, d2, d3, (Ol, outW, rowsT)
+
+
+def _slab_run_peer(x_local, p, conj, slabs):
+    """Slab-decomposed propagation with the transposes fused into the row kernels (see _PeerSlabs)."""
+    B, C, dev = x_local.shape[0], p.C, x_local.device
+    outH, outW = (p.outH, p.outW) if not conj else (p.H, p.W)
+    inH = p.H if not conj else p.outH
+    y = torch.empty(B, C, outH // p.G, outW, dtype=torch.complex64, device=dev)
+    d1, d2, d3, (_, _, rowsT) = _slab_stage_descs(p, x_local, y, p.rank, slabs.ptrs, conj)
+    t2 = slabs.local(B * C, rowsT, p.Wc)
+    _mark("start")
+    slabs.barrier()                      # every rank has finished reading the slabs of the previous call
+    Fn._asm_call(d1, dev)                # row FFT; stores go to the owners of the column blocks
+    _mark("row fft + scatter")
+    slabs.barrier()                      # all row segments have landed in my column slab
+    Fn._asm_call(d2(t2), dev)            # column FFT . H . column iFFT in place
+    _mark("column pass")
+    slabs.barrier()                      # every column slab is final
+    Fn._asm_call(d3, dev)                # row iFFT; loads come from the owners of the column blocks
+    _mark("gather + row ifft")
+    return y
+
+
+def slab_emulate_ranks(x_full, plans, conj=False):
+    """Test helper: run the G ranks of a peer-memory slab propagation one after the other in THIS process (all column
+    slabs on one device), exercising exactly the descriptors and kernels of `_slab_run_peer`.  x_full [B,C,H,W]."""
+    G, p0 = len(plans), plans[0]
+    B, dev = x_full.shape[0], x_full.device
+    inH = p0.H if not conj else p0.outH
+    outH, outW = (p0.outH, p0.outW) if not conj else (p0.H, p0.W)
+    rowsT = max(p0.H, p0.outH)
+    slabs = [torch.zeros(B * p0.C, rowsT, p0.Wc, dtype=torch.complex64, device=dev) for _ in range(G)]
+    ptrs = [t.data_ptr() for t in slabs]
+    Hl = inH // G
+    ys = [torch.empty(B, p0.C, outH // G, outW, dtype=torch.complex64, device=dev) for _ in range(G)]
+    xs = [x_full[:, :, r * Hl:(r + 1) * Hl].contiguous() for r in range(G)]
+    descs = [_slab_stage_descs(plans[r], xs[r], ys[r], r, ptrs, conj) for r in range(G)]
+    for r in range(G):
+        Fn._asm_call(descs[r][0], dev)
+    for r in range(G):
+        Fn._asm_call(descs[r][1](slabs[r]), dev)
+    for r in range(G):
+        Fn._asm_call(descs[r][2], dev)
+    return torch.cat(ys, dim=2)
+
+
+def _peer_transport_possible(plan, device):
+    from . import _native
+    return device.type == "cuda" and dist.get_backend() == "nccl" and plan.G <= 8 and bool(_native.lib().thz_fft_is_static(plan.Wp))
 
 
 class _SlabFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, plan, group):
-        ctx.plan, ctx.group = plan, group
-        return _slab_run(Fn._c64(x_local, "field.data"), plan, False, group)
+    def forward(ctx, x_local, plan, group, slabs):
+        ctx.plan, ctx.group, ctx.slabs = plan, group, slabs
+        x_local = Fn._c64(x_local, "field.data")
+        return _slab_run_peer(x_local, plan, False, slabs) if slabs is not None else _slab_run(x_local, plan, False, group)
 
     @staticmethod
     def backward(ctx, g):
-        return _slab_run(Fn._c64(g, "grad_output"), ctx.plan, True, ctx.group), None, None
+        g = Fn._c64(g, "grad_output")
+        gx = _slab_run_peer(g, ctx.plan, True, ctx.slabs) if ctx.slabs is not None else _slab_run(g, ctx.plan, True, ctx.group)
+        return gx, None, None, None
 
 
 class SlabAsm(torch.nn.Module):
@@ -147,21 +260,52 @@ class SlabAsm(torch.nn.Module):
     slab of the propagated field.  Constructor arguments as ASM_prop (Props/ASM_Prop.py:19-27)."""
 
     def __init__(self, z_distance=0.0, do_padding=True, do_unpad_after_pad=True, padding_scale=None, bandlimit_kernel=True,
-                 bandlimit_type="exact", group=None, kernel_mode="inregister"):
+                 bandlimit_type="exact", group=None, kernel_mode="inregister", transport="auto"):
         super().__init__()
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        # 'peer': transposes fused into the row kernels over NVLink peer memory (_PeerSlabs); 'nccl': pack + all_to_all +
+        # unpack around the kernels (also the CPU / gloo test path); 'auto': peer when it can be set up, else nccl.
+        self.transport = transport
+        self._slabs = None
         self.z = torch.as_tensor(z_distance, dtype=torch.float32)
         self.do_padding, self.do_unpad_after_pad = do_padding, do_unpad_after_pad
         self.padding_scale = AH.normalise_padding_scale(padding_scale, do_padding)
         self.bandlimit_kernel, self.bandlimit_type = bandlimit_kernel, bandlimit_type
         self.group, self.kernel_mode = group, kernel_mode
-        self._key, self._plan = None, None
+        self._key, self._plan, self._fast = None, None, None
+
+    def _make_slabs(self, nbc, device):
+        """Symmetric-memory column slabs for the peer transport (collective: every rank calls it with the same sizes)."""
+        p = self._plan
+        if self.transport == "nccl" or not _peer_transport_possible(p, device):
+            if self.transport == "peer":
+                raise RuntimeError("SlabAsm(transport='peer') needs CUDA + NCCL, <= 8 ranks and a static-path padded width")
+            return None
+        try:
+            return _PeerSlabs(nbc * max(p.H, p.outH) * p.Wc, device, self.group)
+        except Exception as e:          # no P2P mapping on this system: the NCCL transport still works
+            if self.transport == "peer":
+                raise
+            import warnings
+            warnings.warn("SlabAsm: peer-memory transport unavailable (%s); using all_to_all" % (e,))
+            return None
 
     def forward(self, field):
         G, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         data = field.data
         B, C, Hl, W = data.shape
         H = Hl * G
-        key = (C, H, W, tuple(field.spacing.detach().cpu().tolist()), tuple(field.wavelengths.detach().cpu().tolist()), float(self.z), G, rank)
+        # same tensor objects (unchanged in place) as last time -> same plan, no device->host reads (they would serialise
+        # the host with the GPU on every call)
+        fast = (id(field.spacing), field.spacing._version, id(field.wavelengths), field.wavelengths._version, C, H, W,
+                float(self.z), G, rank, str(data.device))
+        if self._plan is not None and self._fast == fast:
+            key = self._key
+        else:
+            key = (C, H, W, tuple(field.spacing.detach().cpu().tolist()), tuple(field.wavelengths.detach().cpu().tolist()),
+                   float(self.z), G, rank)
+            self._fast, self._fast_refs = fast, (field.spacing, field.wavelengths)
         if key != self._key:
             pad_h, pad_w, Hp, Wp = AH.compute_padding(H, W, self.padding_scale, self.do_padding)
             rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type)
@@ -175,5 +319,8 @@ class SlabAsm(torch.nn.Module):
             self._plan = _SlabPlan(G, rank, C, H, W, pad_h, pad_w, Hp, Wp, bool(self.do_padding and self.do_unpad_after_pad),
                                    data.device, rowvec, colvec, scal, table, mode)
             self._key = key
-        out = _SlabFn.apply(data, self._plan, self.group)
+            self._slabs = self._make_slabs(B * C, data.device)
+        elif self._slabs is not None and self._slabs.numel < B * C * max(self._plan.H, self._plan.outH) * self._plan.Wc:
+            self._slabs = self._make_slabs(B * C, data.device)
+        out = _SlabFn.apply(data, self._plan, self.group, self._slabs)
         return ElectricField(out, wavelengths=field.wavelengths, spacing=field.spacing, device=data.device)

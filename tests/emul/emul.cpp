@@ -199,7 +199,7 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
 extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
     int rc = thz_asm_validate(d);
     if (rc != THZ_OK) return rc;
-    if (d->ws_bytes < thz_asm_ws_bytes(d)) return THZ_E_WORKSPACE;
+    if (d->slab_parts <= 1 && d->ws_bytes < thz_asm_ws_bytes(d)) return THZ_E_WORKSPACE;
     const int nbc_all = d->B * d->C;
     const int chunk = (int)thz_asm_chunk_fields(d);
     const int nchunks = (nbc_all + chunk - 1) / chunk;

@@ -2,6 +2,7 @@
 planning helpers) and of the host-side logic mirrored from the reference (padding, validation, errors).
 No compute call is made: there is no GPU here."""
 import ctypes
+import subprocess
 import os
 import re
 
@@ -33,9 +34,20 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.thz_version() >= 100
 
 
-def test_descriptor_layout_matches_header():
-    # thz_asm_desc: 12 int32, 2 ptr, 2 int32, 4 ptr, int32+float, 4 ptr, 2 ptr, ptr, u64, 4 int32
-    assert ctypes.sizeof(N.AsmDesc) == 12 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 4 * 4
+def test_descriptor_layout_matches_header(tmp_path):
+    """ctypes mirrors vs the C header: sizes and field offsets as gcc lays the structs out."""
+    # thz_asm_desc: 12 int32, 2 ptr, 2 int32, 4 ptr, int32+float, 4 ptr, 2 ptr, ptr, u64, 4 int32, 4 int32, 8 ptr
+    assert ctypes.sizeof(N.AsmDesc) == 12 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 4 * 4 + 4 * 4 + 8 * 8
+    fields = ["x", "tf_mode", "tf_table", "doe_base", "doe_gh", "ws_bytes", "stages", "slab_parts", "slab_ptrs"]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "thzdoe.h"\nint main(void) {\n'
+                   '  printf("%zu %zu", sizeof(thz_asm_desc), sizeof(thz_toeplitz_gemm_desc));\n' +
+                   "".join('  printf(" %%zu", offsetof(thz_asm_desc, %s));\n' % f for f in fields) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert got[0] == ctypes.sizeof(N.AsmDesc) and got[1] == ctypes.sizeof(N.ToeplitzGemmDesc)
+    assert got[2:] == [getattr(N.AsmDesc, f).offset for f in fields]
 
 
 def test_plan_helpers(lib):

@@ -155,3 +155,59 @@ def test_unsupported_length_is_reported():
     assert E.thz_emul_plan_info(26, radices, ctypes.byref(ns)) == -3      # 13 is not a supported radix
     assert E.thz_emul_plan_info(4096, radices, ctypes.byref(ns)) == 0 and list(radices)[:3] == [16, 16, 16]
     assert E.thz_emul_plan_info(2000, radices, ctypes.byref(ns)) == 0 and list(radices)[:3] == [25, 20, 4]
+
+
+# ------------------------------------------------------------------------------- slab FFT over peer memory
+def _slab_plans(G, C, H, W, lams, dxy, z, device, mode="inregister"):
+    from quantizationawarethzdoe_b200 import parallel as P
+    pad_h, pad_w, Hp, Wp = AH.compute_padding(H, W, AH.normalise_padding_scale(None, True), True)
+    sp, wl = torch.tensor([dxy, dxy]), torch.tensor(lams)
+    rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, sp, wl, torch.tensor(z), True, "exact")
+    table, tf_mode = None, 0
+    if mode == "inregister":
+        rowvec, colvec, scal = AH.tf_device_vectors(rowvec, colvec, scal)
+    else:
+        table, tf_mode = AH.tf_table_slot_order(AH.tf_centred_reference_order(Hp, Wp, sp, wl, torch.tensor(z), True, "exact")), 1
+    return [P._SlabPlan(G, r, C, H, W, pad_h, pad_w, Hp, Wp, True, device, rowvec, colvec, scal, table, tf_mode) for r in range(G)]
+
+
+@pytest.mark.parametrize("G,mode", [(2, "cached"), (4, "inregister")])
+def test_peer_memory_slab_schedule_replay(G, mode, monkeypatch):
+    """The peer-memory slab FFT (row kernels scatter / gather column slabs, thz_asm_desc.slab_*): the G ranks are
+    replayed one after the other in this process, with all column slabs in host memory, and must reproduce the
+    oracle's full-grid propagation and adjoint."""
+    from quantizationawarethzdoe_b200 import functional as Fn, parallel as P
+
+    def call(desc, device):
+        rc = E.thz_emul_asm_propagate(ctypes.byref(desc), 148)
+        assert rc == 0, rc
+
+    monkeypatch.setattr(Fn, "_asm_call", call)
+    H = W = 128
+    lams, dxy, z = [1e-3, 1.04e-3], 0.5e-3, 0.1
+    torch.manual_seed(0)
+    x = torch.randn(1, 2, H, W, dtype=torch.complex64)
+    g = torch.randn(1, 2, H, W, dtype=torch.complex64)
+    plans = _slab_plans(G, 2, H, W, lams, dxy, z, torch.device("cpu"), mode)
+    y = P.slab_emulate_ranks(x, plans)
+    gx = P.slab_emulate_ranks(g, plans, conj=True)
+    xo = x.clone().requires_grad_(True)
+    yo = AO.asm_forward(xo, lams, dxy, z)
+    (gxo,) = torch.autograd.grad(yo, xo, g)
+    tol = TOL_TABLE if mode == "cached" else TOL
+    assert rel_l2(y, yo.detach()) < tol
+    assert rel_l2(gx, gxo) < tol
+
+
+def test_slab_descriptor_is_validated():
+    """slab_parts > 1 needs stages 1 or 4, a width divisible by the parts, rows inside the slab and all pointers."""
+    base, _ = _setup(1, 1, 128, 128, None, [1e-3], 0.5e-3, 0.1)
+    x = torch.zeros(1, 1, 64, 128, dtype=torch.complex64)
+    slab = torch.zeros(128 * 128, dtype=torch.complex64)
+    kw = dict(base, x=x, y=None, inH=64, outH=64, in_r0=0, out_r0=0, ws=None)
+    ok = AH.build_desc(**dict(kw, stages=1, slab=(2, 64, 128, [slab.data_ptr(), slab.data_ptr()])))
+    assert E.thz_emul_asm_propagate(ctypes.byref(ok), 148) == 0
+    for bad in (dict(stages=2), dict(stages=1, slab=(3, 0, 128, [slab.data_ptr()] * 3)), dict(stages=1, slab=(2, 100, 128, [slab.data_ptr()] * 2)),
+                dict(stages=1, slab=(2, 0, 128, [slab.data_ptr(), 0]))):
+        d = AH.build_desc(**dict(dict(kw, stages=1, slab=(2, 64, 128, [slab.data_ptr(), slab.data_ptr()])), **bad))
+        assert E.thz_emul_asm_propagate(ctypes.byref(d), 148) in (-1, -2), bad

@@ -465,3 +465,27 @@ def test_whole_iteration_replays_as_one_cuda_graph(dev):
     torch.cuda.synchronize()
     assert int(opt_g.state[doe_g.weight_height_map]["step"].item()) == 4
     assert rel_l2(doe_g.weight_height_map.detach().cpu(), doe_e.weight_height_map.detach().cpu()) <= 1e-6
+
+
+@pytest.mark.parametrize("G,n", [(2, 512), (4, 1024)])
+def test_peer_memory_slab_kernels_on_one_gpu(G, n, dev):
+    """The scatter / gather row kernels of the peer-memory slab FFT, with the G ranks run one after the other on this
+    GPU (all column slabs local): identical arithmetic to the single-GPU pipeline, so the result is bit-identical."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_emul_kernels import _slab_plans
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, parallel as P
+    lams = [1 * mm, 1.04 * mm]
+    torch.manual_seed(0)
+    x = torch.randn(1, 2, n, n, dtype=torch.complex64, device=dev)
+    g = torch.randn(1, 2, n, n, dtype=torch.complex64, device=dev)
+    plans = _slab_plans(G, 2, n, n, lams, 0.5 * mm, 0.1, dev)
+    y = P.slab_emulate_ranks(x, plans)
+    gx = P.slab_emulate_ranks(g, plans, conj=True)
+    asm = ASM_prop(z_distance=0.1, device=dev)
+    asm.check_Zc = False
+    xr = x.clone().requires_grad_(True)
+    yr = asm(ElectricField(xr, wavelengths=lams, spacing=0.5 * mm, device=dev)).data
+    (gxr,) = torch.autograd.grad(yr, xr, g)
+    assert torch.equal(y, yr.detach())
+    assert torch.equal(gx, gxr)

@@ -32,7 +32,8 @@ torch.manual_seed(0)
 x = torch.randn(1, len(lams), n, n, dtype=torch.complex64, device=dev)
 g = torch.randn(1, len(lams), n, n, dtype=torch.complex64, device=dev)
 lo, hi = P.shard_range(n, rank, world)
-slab = P.SlabAsm(z_distance=0.1)
+transport = os.environ.get("THZ_SLAB_TRANSPORT", "auto")     # auto / peer / nccl
+slab = P.SlabAsm(z_distance=0.1, transport=transport)
 xl = x[:, :, lo:hi].contiguous().requires_grad_(True)
 yl = slab(ElectricField(xl, wavelengths=lams, spacing=0.5 * mm, device=dev)).data
 (gxl,) = torch.autograd.grad(yl, xl, g[:, :, lo:hi].contiguous())
@@ -40,23 +41,42 @@ yl = slab(ElectricField(xl, wavelengths=lams, spacing=0.5 * mm, device=dev)).dat
 torch.cuda.synchronize()
 dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+fl = ElectricField(xl.detach(), wavelengths=lams, spacing=0.5 * mm, device=dev)   # one field object: plan lookups stay on the fast path
+slab(fl)
+torch.cuda.synchronize()
+dist.barrier()
 e0.record()
-for _ in range(3):
-    slab(ElectricField(xl.detach(), wavelengths=lams, spacing=0.5 * mm, device=dev))
+for _ in range(10):
+    slab(fl)
 e1.record()
 torch.cuda.synchronize()
-tms = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+tms = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
 dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+P.SLAB_TIMINGS = []
+slab(fl)
+torch.cuda.synchronize()
+marks, P.SLAB_TIMINGS = P.SLAB_TIMINGS, None
+stage_ms = ", ".join("%s %.2f" % (marks[i][0], marks[i - 1][1].elapsed_time(marks[i][1])) for i in range(1, len(marks)))
 asm = ASM_prop(z_distance=0.1, device=dev)
 asm.check_Zc = False
+ff = ElectricField(x, wavelengths=lams, spacing=0.5 * mm, device=dev)
+asm(ff)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    asm(ff)
+e1.record()
+torch.cuda.synchronize()
+single_ms = e0.elapsed_time(e1) / 10
 xf = x.clone().requires_grad_(True)
 yf = asm(ElectricField(xf, wavelengths=lams, spacing=0.5 * mm, device=dev)).data
 (gxf,) = torch.autograd.grad(yf, xf, g)
 e = torch.tensor([rel(yl.detach(), yf.detach()[:, :, lo:hi]), rel(gxl, gxf[:, :, lo:hi])], device=dev)
 dist.all_reduce(e, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("slab %d^2 (padded %d^2) over %d GPUs vs single GPU: fwd %.2e adjoint %.2e; slab forward %.2f ms" % (
-        n, 2 * n, world, e[0], e[1], float(tms)))
+    print("slab %d^2 (padded %d^2) over %d GPUs [%s transport] vs single GPU: fwd %.2e adjoint %.2e; slab forward %.2f ms, single-GPU forward %.2f ms" % (
+        n, 2 * n, world, "peer" if slab._slabs is not None else "nccl", e[0], e[1], float(tms), single_ms))
+    print("  rank 0 stages (ms):", stage_ms)
 ok &= bool(e.max() < 2e-6)
 
 # ---- data parallel over wavelengths
