@@ -40,7 +40,7 @@ struct K1Loader {
     int in_c0, inW, conj_in;
     THZ_HD cpx operator()(int pos) const {
         const int c = pos - in_c0;
-        if (xr == nullptr || c < 0 || c >= inW) return cmake(0.f, 0.f);
+        if (xr == nullptr || (unsigned)c >= (unsigned)inW) return cmake(0.f, 0.f);   // one compare: c < 0 wraps
         cpx v = xr[c];
         if (conj_in) v.y = -v.y;
         if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
@@ -155,7 +155,7 @@ struct K2Loader {
     int in_r0, inH, Wp;
     THZ_HD cpx operator()(int pos) const {
         const int r = pos - in_r0;
-        if (col == nullptr || r < 0 || r >= inH) return cmake(0.f, 0.f);
+        if (col == nullptr || (unsigned)r >= (unsigned)inH) return cmake(0.f, 0.f);  // one compare: r < 0 wraps
         return col[(size_t)r * Wp];
     }
 };
@@ -164,7 +164,7 @@ struct K2Storer {
     int out_r0, outH, Wp;
     THZ_HD void operator()(int pos, int, cpx v) const {
         const int r = pos - out_r0;
-        if (col != nullptr && r >= 0 && r < outH) col[(size_t)r * Wp] = v;
+        if (col != nullptr && (unsigned)r < (unsigned)outH) col[(size_t)r * Wp] = v;
     }
 };
 
@@ -304,7 +304,7 @@ struct K3Storer {
     float* acc;           // this butterfly's R accumulators
     THZ_HD void operator()(int pos, int t, cpx v) const {
         const int c = pos - out_c0;
-        if (c < 0 || c >= outW) return;
+        if ((unsigned)c >= (unsigned)outW) return;
         v = cscale(v, scale);
         if (hrow == nullptr) {
             yrow[c] = v;
@@ -332,7 +332,7 @@ THZ_HD void p2k3_prefetch_epilogue(const RowInvArgs& a, int bx, int f, int tid, 
 #pragma unroll
         for (int t = 0; t < R; ++t) {
             const int c = j + t * M - a.out_c0;
-            if (c < 0 || c >= a.outW) continue;
+            if ((unsigned)c >= (unsigned)a.outW) continue;
             if ((c & 3) == 0) thz_prefetch_l2(xrow + c);
             if ((c & 7) == 0) thz_prefetch_l2(hrow + c);
         }
@@ -386,7 +386,7 @@ THZ_HD void p2k3_flush(const RowInvArgs& a, int bx, int tid, int nt, const float
 #pragma unroll
         for (int t = 0; t < R; ++t) {
             const int c = j + t * M - a.out_c0;
-            if (c < 0 || c >= a.outW) continue;
+            if ((unsigned)c >= (unsigned)a.outW) continue;
             float* g = a.gh + (size_t)r * a.outW + c;
             if (a.gh_atomic) thz_atomic_add(g, acc[k * R + t]);
             else *g = acc[k * R + t];
