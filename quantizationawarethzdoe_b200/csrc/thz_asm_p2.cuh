@@ -293,7 +293,9 @@ THZ_HD constexpr int p2k3_acc() {
     return ((p2_row_lines(N) * P2Stage<N, 0>::NB + p2_row_threads(N) - 1) / p2_row_threads(N)) * P2Stage<N, 0>::R;
 }
 
+template <int PF_>
 struct K3Storer {
+    static constexpr int PF = PF_;   // epilogue loads (saved field, height map) run this many outputs ahead
     cpx* yrow;            // output row (forward output or grad wrt field; may be NULL in DOE mode)
     const cpx* xrow;      // saved input row (DOE mode)
     const float* hrow;    // height-map row (DOE mode; NULL = plain forward)
@@ -302,7 +304,15 @@ struct K3Storer {
     float base, scale;
     int out_c0, outW;
     float* acc;           // this butterfly's R accumulators
-    THZ_HD void operator()(int pos, int t, cpx v) const {
+    cpx xq[PF];           // prefetch ring (registers after unrolling)
+    float hq[PF];
+    THZ_HD void prefetch(int pos, int t) {
+        const int c = pos - out_c0;
+        if (hrow == nullptr || (unsigned)c >= (unsigned)outW) return;
+        hq[t % PF] = thz_ldg(hrow + c);
+        xq[t % PF] = thz_ldg(xrow + c);
+    }
+    THZ_HD void operator()(int pos, int t, cpx v) {
         const int c = pos - out_c0;
         if ((unsigned)c >= (unsigned)outW) return;
         v = cscale(v, scale);
@@ -310,10 +320,12 @@ struct K3Storer {
             yrow[c] = v;
             return;
         }
-        const cpx p = thz_doe_phase(thz_ldg(hrow + c), cf, base);
-        if (yrow) yrow[c] = cmulc(v, p);
-        const cpx xp = cmul(cmul(xrow[c], p), gamma);
-        acc[t] += v.x * xp.x + v.y * xp.y;
+        const cpx p = thz_doe_phase(hq[t % PF], cf, base);
+        const cpx q = cmulc(v, p);                 // grad wrt the field that entered the DOE
+        if (yrow) yrow[c] = q;
+        // gh += Re(conj(v) x p gamma) = Re(conj(q) x gamma)
+        const cpx xg = cmul(xq[t % PF], gamma);
+        acc[t] += q.x * xg.x + q.y * xg.y;
     }
 };
 
@@ -343,7 +355,7 @@ THZ_HD void p2k3_prefetch_epilogue(const RowInvArgs& a, int bx, int f, int tid, 
 template <int N, int NACC>
 THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, int f, int tid, int nt, float (&acc)[NACC]) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N), R = P2Stage<N, 0>::R;
-    K3Storer st;
+    K3Storer<(R <= 16 ? 4 : 1)> st;     // radix-25 butterflies have no registers to spare for a deeper ring
     st.cf = cmake4(0.f);
     st.gamma = cmake(0.f, 0.f);
     if (a.doe.hmap) {

@@ -144,18 +144,38 @@ THZ_HD void p2_first_stage_from(cpx* base, int j, const cpx* __restrict__ tw, Lo
 }
 
 // ---------------------------------------------------------------- last inverse stage, outputs to a functor
+//   A store functor with an epilogue that READS global memory (the DOE adjoint) may define PF > 0 and prefetch(pos, t):
+//   the loads of output t + PF are then issued while output t is being finished (software pipeline over the R outputs;
+//   after unrolling the functor's PF-deep ring lives in registers).
+template <typename Store>
+struct P2StorePF {
+    template <typename S>
+    static constexpr auto get(int) -> decltype(S::PF) { return S::PF; }
+    template <typename S>
+    static constexpr int get(...) { return 0; }
+    static constexpr int value = get<Store>(0);
+};
 template <int N, int STRIDE, typename Store>
 THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* tw, Store store) {
     typedef P2Stage<N, 0> St;
-    constexpr int R = St::R, M = St::M;
+    constexpr int R = St::R, M = St::M, PF = P2StorePF<Store>::value;
     const cpx* p = base + (j + (j >> 4)) * STRIDE;
     cpx v[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
+    if constexpr (PF > 0) {
+#pragma unroll
+        for (int t = 0; t < PF && t < R; ++t) store.prefetch(j + t * M, t);
+    }
     p2_apply_twiddles<R>(v, cconj(tw[j]));
     Dft<R, true>::run(v);
 #pragma unroll
-    for (int t = 0; t < R; ++t) store(j + t * M, t, v[t]);
+    for (int t = 0; t < R; ++t) {
+        store(j + t * M, t, v[t]);
+        if constexpr (PF > 0) {
+            if (t + PF < R) store.prefetch(j + (t + PF) * M, t + PF);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- all butterflies of in-smem stage S
