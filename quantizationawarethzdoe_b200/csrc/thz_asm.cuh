@@ -55,14 +55,16 @@ THZ_HD cpx thz_doe_phase(float h, float4 cf, float base) {
 // The evanescent cut (:262) and both band-limit constraints (:297-306) are monotone in Ky^2 for a fixed row,
 // so the host folds them, evaluated with the reference's exact fp32 expressions, into one threshold tau per
 // row: the kept set is exactly {Ky^2 <= tau}.  The phase follows the reference's rounding order.
+// Branch-free: dropped bins are computed too (their d may be negative -> NaN) and replaced by 0 with a select at the end,
+// which costs less than a divergent early return around the sqrt / sincos sequence.
 THZ_HD cpx thz_tf_value(float2 rv, float ky2, float2 sc, int conj) {
-    if (!(ky2 <= rv.y)) return cmake(0.f, 0.f);
     const float K2 = thz_add_rn(rv.x, ky2);
     const float d = thz_sub_rn(sc.x, K2);
-    const float ang = thz_mul_rn(sc.y, thz_sqrt_rn(d));
+    const float ang = thz_mul_rn(sc.y, thz_sqrt_pos(d));
     float sn, cs;
     thz_sincos_fast(ang, &sn, &cs);
-    return cmake(cs, conj ? -sn : sn);
+    const bool keep = ky2 <= rv.y;
+    return cmake(keep ? cs : 0.f, keep ? (conj ? -sn : sn) : 0.f);
 }
 
 // =============================================================================== K1: row forward
