@@ -23,7 +23,7 @@ __device__ __forceinline__ void inv_rows(cpx* s, int tid, int nt, const cpx* tw)
 template <int N, int S, int S1, int COLS>
 __device__ __forceinline__ void fwd_cols(cpx* s, int tid, int nt, const cpx* tw) {
     if constexpr (S < S1) {
-        p2_stage_cols<N, S, false, COLS>(s, tid, nt, tw);
+        p2_stage_cols<N, S, false, COLS, p2_col_threads(N)>(s, tid, nt, tw);
         __syncthreads();
         fwd_cols<N, S + 1, S1, COLS>(s, tid, nt, tw);
     }
@@ -31,7 +31,7 @@ __device__ __forceinline__ void fwd_cols(cpx* s, int tid, int nt, const cpx* tw)
 template <int N, int S, int S0, int COLS>
 __device__ __forceinline__ void inv_cols(cpx* s, int tid, int nt, const cpx* tw) {
     if constexpr (S >= S0) {
-        p2_stage_cols<N, S, true, COLS>(s, tid, nt, tw);
+        p2_stage_cols<N, S, true, COLS, p2_col_threads(N)>(s, tid, nt, tw);
         __syncthreads();
         inv_cols<N, S - 1, S0, COLS>(s, tid, nt, tw);
     }

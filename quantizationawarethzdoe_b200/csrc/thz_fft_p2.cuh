@@ -126,6 +126,31 @@ THZ_HD void p2_butterfly(cpx* base, int u, const cpx* tw) {
     for (int t = 0; t < R; ++t) p[p2_coff(M, t) * STRIDE] = v[t];
 }
 
+// Same butterfly with the twiddle powers w[q] = w1^q (already conjugated for INV) supplied by the caller: when the
+// butterflies a thread runs in one stage all share their sub-block offset j, the power tree is built once per stage.
+template <int N, int S, bool INV, int STRIDE>
+THZ_HD void p2_butterfly_w(cpx* base, int u, const cpx (&w)[P2Stage<N, S>::R]) {
+    typedef P2Stage<N, S> St;
+    constexpr int R = St::R, M = St::M, L = St::L;
+    const int b = u / M, j = u % M;
+    const int p0 = b * L + j;
+    cpx* p = base + (p0 + (p0 >> 4)) * STRIDE;
+    cpx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
+    if (!INV) {
+        Dft<R, false>::run(v);
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+    } else {
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+        Dft<R, true>::run(v);
+    }
+#pragma unroll
+    for (int t = 0; t < R; ++t) p[p2_coff(M, t) * STRIDE] = v[t];
+}
+
 // ---------------------------------------------------------------- first forward stage, inputs from a functor
 //   load(pos) returns the input at logical position pos in [0, N).  Stage 0 has a single block (L = N), so
 //   butterfly j touches positions j + t*M.
@@ -190,11 +215,22 @@ THZ_HD void p2_stage_rows(cpx* s, int tid, int nthreads, const cpx* tw) {
     }
 }
 //   COLUMN TILE: COLS lines interleaved (slot * COLS + l), work item w -> (u = w / COLS, l = w % COLS)
-template <int N, int S, bool INV, int COLS>
+//   NT = the kernel's compile-time block size (0: unknown).  A thread's work items are w = tid + k NT, i.e. u = u0 +
+//   k NT / COLS: if NT / COLS is a multiple of the sub-block length M, all of them have the same j = u % M and hence
+//   the same twiddle powers -- computed once here instead of once per butterfly (14 complex multiplies for radix 16).
+template <int N, int S, bool INV, int COLS, int NT = 0>
 THZ_HD void p2_stage_cols(cpx* s, int tid, int nthreads, const cpx* tw) {
-    constexpr int NB = P2Stage<N, S>::NB;
-    for (int w = tid; w < COLS * NB; w += nthreads) {
-        const int u = w / COLS, l = w % COLS;
-        p2_butterfly<N, S, INV, COLS>(s + l, u, tw);
+    typedef P2Stage<N, S> St;
+    constexpr int NB = St::NB, M = St::M, R = St::R;
+    if constexpr (NT > 0 && M > 1 && NT % COLS == 0 && (NT / COLS) % M == 0 && (COLS * NB) > NT) {
+        const cpx w1 = tw[((tid / COLS) % M) * St::WT];
+        cpx w[R];
+        twiddle_powers<R>(INV ? cconj(w1) : w1, w);
+        for (int w_ = tid; w_ < COLS * NB; w_ += NT) p2_butterfly_w<N, S, INV, COLS>(s + w_ % COLS, w_ / COLS, w);
+    } else {
+        for (int w = tid; w < COLS * NB; w += nthreads) {
+            const int u = w / COLS, l = w % COLS;
+            p2_butterfly<N, S, INV, COLS>(s + l, u, tw);
+        }
     }
 }

@@ -101,14 +101,14 @@ static void e_inv_rows(cpx* s, int nt, const cpx* tw) {
 template <int N, int S, int S1, int COLS>
 static void e_fwd_cols(cpx* s, int nt, const cpx* tw) {
     if constexpr (S < S1) {
-        for_threads(nt, [&](int t) { p2_stage_cols<N, S, false, COLS>(s, t, nt, tw); });
+        for_threads(nt, [&](int t) { p2_stage_cols<N, S, false, COLS, p2_col_threads(N)>(s, t, nt, tw); });
         e_fwd_cols<N, S + 1, S1, COLS>(s, nt, tw);
     }
 }
 template <int N, int S, int S0, int COLS>
 static void e_inv_cols(cpx* s, int nt, const cpx* tw) {
     if constexpr (S >= S0) {
-        for_threads(nt, [&](int t) { p2_stage_cols<N, S, true, COLS>(s, t, nt, tw); });
+        for_threads(nt, [&](int t) { p2_stage_cols<N, S, true, COLS, p2_col_threads(N)>(s, t, nt, tw); });
         e_inv_cols<N, S - 1, S0, COLS>(s, nt, tw);
     }
 }
