@@ -130,6 +130,12 @@ typedef struct thz_asm_desc {
     int32_t slab_rows;         /* rows per field in every column slab                                       */
     int32_t slab_reserved;
     void* slab_ptrs[8];
+    /* tf_mode 0 only.  0: tf_rowvec is [C][Hp][2] in slot order.  1: "chunked" for the static column kernels, whose
+       threads each own the R consecutive slots 16u .. of one last-stage butterfly: [C][R/2][Hp/R] float4 entries, entry
+       (q, u) = {Kx^2, tau}[R u + 2 q], {Kx^2, tau}[R u + 2 q + 1] with R = the last radix of thz_fft_plan_info(Hp), so that
+       the 32 lanes of a warp read 512 contiguous bytes instead of 32 different cache lines.  Needs thz_fft_is_static(Hp). */
+    int32_t tf_row_chunked;
+    int32_t reserved2;
 } thz_asm_desc;
 
 uint64_t thz_asm_workspace_bytes(const thz_asm_desc* desc);

@@ -158,14 +158,16 @@ class ASM_prop(nn.Module):
                 self.check_Zc = False
             rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
             table, mode = None, 0
-            dv = AH.tf_device_vectors(rowvec, colvec, scal) if self.kernel_mode == 'inregister' else None
+            chunked = AH.row_vectors_chunked(Hp)
+            dv = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked) if self.kernel_mode == 'inregister' else None
             if dv is not None:
                 rowvec, colvec, scal = dv
             if self.kernel_mode == 'cached' or dv is None:
                 Hc = AH.tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
                 table, mode = AH.tf_table_slot_order(Hc), 1
             unpad = bool(self.do_padding and self.do_unpad_after_pad)
-            self._plan = Fn.AsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, mode)
+            self._plan = Fn.AsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, mode,
+                                    row_chunked=chunked)
             self._plan_key = key
         self._fast_key = fast
         self._fast_refs = (spacing, wavelengths)      # keep the keyed tensors alive so their ids stay unique

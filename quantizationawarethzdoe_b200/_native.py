@@ -46,6 +46,7 @@ class AsmDesc(ctypes.Structure):
         ("slab_parts", ctypes.c_int32), ("slab_row0", ctypes.c_int32),
         ("slab_rows", ctypes.c_int32), ("slab_reserved", ctypes.c_int32),
         ("slab_ptrs", ctypes.c_void_p * 8),
+        ("tf_row_chunked", ctypes.c_int32), ("reserved2", ctypes.c_int32),
     ]
 
 
@@ -190,6 +191,13 @@ def slot_to_bin(n, fn=None):
         p = torch.tensor(list(buf), dtype=torch.int64)
         _perm_host[n] = p
     return p
+
+
+def plan_radices(n):
+    """Radices of the length-n plan, first stage first (thz_fft_plan_info)."""
+    rad, ns = (ctypes.c_int32 * 16)(), ctypes.c_int32(0)
+    check(lib().thz_fft_plan_info(int(n), rad, ctypes.byref(ns)), "thz_fft_plan_info")
+    return [int(rad[i]) for i in range(ns.value)]
 
 
 def ptr(t):

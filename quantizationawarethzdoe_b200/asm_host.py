@@ -190,15 +190,31 @@ def _tf_row_thresholds_dense(rowvec, colvec, scal, chunk_rows=512):
     return tau
 
 
-def tf_device_vectors(rowvec, colvec, scal, slot_to_bin_fn=None):
+def row_vectors_chunked(Hp):
+    """True if the column kernels for length Hp read the row vectors in the chunked layout (thz_asm_desc.tf_row_chunked):
+    the static kernels do, the runtime-planned engine reads plain slot order."""
+    return bool(N.lib().thz_fft_is_static(int(Hp)))
+
+
+def chunk_row_vectors(rowtau, last_radix):
+    """[C,Hp,2] slot order -> [C, R/2, Hp/R, 4]: entry (q, u) = slots R u + 2 q and R u + 2 q + 1 (R = last radix)."""
+    C, Hp, _ = rowtau.shape
+    R = int(last_radix)
+    return rowtau.reshape(C, Hp // R, R // 2, 4).permute(0, 2, 1, 3).contiguous()
+
+
+def tf_device_vectors(rowvec, colvec, scal, slot_to_bin_fn=None, chunked=False):
     """What the kernels consume (tf_mode 0): rowtau [C,Hp,2] = {Kx^2, tau} and colk2 [C,Wp] = Ky^2, both in the
-    plans' slot order, plus scal.  Returns None if the thresholds cannot be formed."""
+    plans' slot order, plus scal.  chunked=True re-lays rowtau out for the static column kernels (pass
+    tf_row_chunked=1 in the descriptor).  Returns None if the thresholds cannot be formed."""
     tau = tf_row_thresholds(rowvec, colvec, scal)
     if tau is None:
         return None
     pr = N.slot_to_bin(rowvec.shape[1], slot_to_bin_fn)
     pc = N.slot_to_bin(colvec.shape[1], slot_to_bin_fn)
     rowtau = torch.stack([rowvec[:, :, 0], tau], dim=2)[:, pr].contiguous()
+    if chunked:
+        rowtau = chunk_row_vectors(rowtau, N.plan_radices(rowvec.shape[1])[-1])
     colk2 = colvec[:, pc, 0].contiguous()
     return rowtau, colk2, scal
 
@@ -248,7 +264,7 @@ def doe_coefficients(wavelengths, epsilon, tand):
 
 def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, out_c0, tf_mode, tf_conj,
                rowvec, colvec, scal, table, doe_mode, doe_base, hmap, coef, xsaved, gh, tw_h, tw_w, ws,
-               bc_chunk=0, tune_k2_cols=0, tune_lines=0, stages=0, slab=None):
+               bc_chunk=0, tune_k2_cols=0, tune_lines=0, stages=0, slab=None, tf_row_chunked=0):
     """Fill a thz_asm_desc from tensors (device or, in the CPU replay tests, host tensors)."""
     d = N.AsmDesc()
     d.B, d.C, d.inH, d.inW, d.Hp, d.Wp = B, C, inH, inW, Hp, Wp
@@ -261,6 +277,7 @@ def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, o
     d.tw_h, d.tw_w = N.ptr(tw_h), N.ptr(tw_w)
     d.ws = N.ptr(ws)
     d.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
+    d.tf_row_chunked = int(tf_row_chunked)
     if slab is not None:          # (parts, row0, rows, [pointer of every rank's column slab]); see thz_asm_desc.slab_*
         d.slab_parts, d.slab_row0, d.slab_rows = int(slab[0]), int(slab[1]), int(slab[2])
         for i, q in enumerate(slab[3]):

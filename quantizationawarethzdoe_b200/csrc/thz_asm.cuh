@@ -31,6 +31,7 @@ struct TfArgs {
     const float* colvec;      // [C][Wp] Ky^2 in SLOT order
     const float2* scal;       // [C]     {klam^2, z}
     const cpx* table;         // [C][Hp][Wp] in (slot_r, slot_c) scrambled layout (mode 1)
+    int row_chunked;          // 1: rowvec is [C][R/2][Hp/R] float4 pairs (thz_asm_desc.tf_row_chunked), static column kernels only
 };
 
 struct DoeArgs {

@@ -180,6 +180,7 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a2.tf.colvec = (const float*)d->tf_colvec;
     a2.tf.scal = (const float2*)d->tf_scal;
     a2.tf.table = (const cpx*)d->tf_table;
+    a2.tf.row_chunked = d->tf_row_chunked;
     {
         int cols = 16;
         // shrink the tile until it fits and until there are enough tiles to fill the GPU twice
@@ -239,5 +240,6 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     }
     thz_asm_apply_p2(d, nbc, sm_count, L);
     if (d->slab_parts > 1 && !L->p2_w) return THZ_E_UNSUPPORTED;   // only the static row kernels scatter / gather slabs
+    if (d->tf_row_chunked && d->tf_mode == 0 && !L->p2_h) return THZ_E_UNSUPPORTED;   // chunked row vectors: static column kernels only
     return THZ_OK;
 }

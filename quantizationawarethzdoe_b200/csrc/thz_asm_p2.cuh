@@ -204,9 +204,15 @@ THZ_HD void p2k2_middle(const ColArgs& a, cpx* s, int bx, int by, int tid, int n
         float cv = 0.f;
         float2 sc = cmake(0.f, 0.f);
         if (gen) {
-            const float4* rvp = reinterpret_cast<const float4*>(a.tf.rowvec + (size_t)c_chan * N + p0);
+            if (a.tf.row_chunked) {      // [c][q][u] float4: the lanes of a warp (consecutive u) read contiguous memory
+                const float4* rvp = reinterpret_cast<const float4*>(a.tf.rowvec + (size_t)c_chan * N) + u;
 #pragma unroll
-            for (int q = 0; q < R / 2; ++q) rv4[q] = thz_ldg(rvp + q);
+                for (int q = 0; q < R / 2; ++q) rv4[q] = thz_ldg(rvp + (size_t)q * NB);
+            } else {
+                const float4* rvp = reinterpret_cast<const float4*>(a.tf.rowvec + (size_t)c_chan * N + p0);
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) rv4[q] = thz_ldg(rvp + q);
+            }
             cv = thz_ldg(a.tf.colvec + (size_t)c_chan * a.Wp + col);
             sc = thz_ldg(a.tf.scal + c_chan);
         }

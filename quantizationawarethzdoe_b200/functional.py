@@ -50,7 +50,7 @@ class AsmPlan:
     """Everything static about one ASM_prop call: geometry + device copies of the transfer-function
     vectors / table and DOE coefficients.  Built once per (shape, spacing, wavelengths, z) by ASM_prop."""
 
-    def __init__(self, B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, tf_mode):
+    def __init__(self, B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, tf_mode, row_chunked=False):
         self.B, self.C, self.H, self.W = B, C, H, W
         self.pad_h, self.pad_w, self.Hp, self.Wp = pad_h, pad_w, Hp, Wp
         self.unpad = unpad
@@ -64,6 +64,7 @@ class AsmPlan:
         self.scal = scal.to(device) if scal is not None else None
         self.table = table.to(device) if table is not None else None
         self.tf_mode = tf_mode
+        self.row_chunked = 1 if (row_chunked and tf_mode == 0) else 0   # layout of rowvec, see thz_asm_desc.tf_row_chunked
         self.tw_h = N.twiddles(Hp, device)
         self.tw_w = N.twiddles(Wp, device)
 
@@ -82,7 +83,8 @@ class AsmPlan:
         d = AH.build_desc(x, y, x.shape[0], C, inH, inW, self.Hp, self.Wp, in_r0, in_c0, outH, outW, out_r0, out_c0,
                           self.tf_mode, 1 if conj else 0, self.rowvec, self.colvec, self.scal, self.table,
                           doe_mode, BASE_PLANE_THICKNESS, hmap, coef, xsaved, gh, self.tw_h, self.tw_w, ws,
-                          bc_chunk=TUNE["bc_chunk"], tune_k2_cols=TUNE["k2_cols"], tune_lines=TUNE["lines"])
+                          bc_chunk=TUNE["bc_chunk"], tune_k2_cols=TUNE["k2_cols"], tune_lines=TUNE["lines"],
+                          tf_row_chunked=self.row_chunked)
         _asm_call(d, x.device)
         return y
 

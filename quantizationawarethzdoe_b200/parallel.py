@@ -74,7 +74,7 @@ def _all_to_all(send, group):
 
 
 class _SlabPlan:
-    def __init__(self, G, rank, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, tf_mode):
+    def __init__(self, G, rank, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, tf_mode, row_chunked=False):
         if H % G or Wp % G:
             raise ValueError("slab FFT: rows (%d) and padded width (%d) must be divisible by the world size %d" % (H, Wp, G))
         self.G, self.rank, self.C = G, rank, C
@@ -89,6 +89,7 @@ class _SlabPlan:
         self.scal = scal.to(device) if scal is not None else None
         self.table = table[:, :, c0:c0 + self.Wc].contiguous().to(device) if table is not None else None
         self.tf_mode = tf_mode
+        self.row_chunked = 1 if (row_chunked and tf_mode == 0) else 0
         self.tw_h, self.tw_w, self.tw_c = N.twiddles(Hp, device), N.twiddles(Wp, device), N.twiddles(self.Wc, device)
 
 
@@ -114,7 +115,7 @@ def _slab_run(x_local, p, conj, group):
     Hl, Ol, Wc, Wp = inH // G, outH // G, p.Wc, p.Wp
     assert x_local.shape[2] == Hl and x_local.shape[3] == inW, "local slab has the wrong shape"
     common = dict(B=B, C=C, Hp=p.Hp, tf_mode=p.tf_mode, tf_conj=1 if conj else 0, rowvec=p.rowvec, scal=p.scal,
-                  doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h)
+                  doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h, tf_row_chunked=p.row_chunked)
     _mark("start")
     # ---- stage 1: row FFT of the local rows -> t1 [nbc, Hl, Wp]
     t1 = torch.empty(nbc * Hl * Wp, dtype=torch.complex64, device=dev)
@@ -178,7 +179,8 @@ def _slab_stage_descs(p, x_local, y_local, rank, ptrs, conj):
     Hl, Ol, Wc, Wp = inH // G, outH // G, p.Wc, p.Wp
     rowsT = max(inH, outH)
     common = dict(B=B, C=C, Hp=p.Hp, tf_mode=p.tf_mode, tf_conj=1 if conj else 0, rowvec=p.rowvec, scal=p.scal,
-                  doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h, colvec=p.colvec, table=p.table)
+                  doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h, colvec=p.colvec, table=p.table,
+                  tf_row_chunked=p.row_chunked)
     d1 = AH.build_desc(x=x_local, y=None, inH=Hl, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Hl, outW=outW, out_r0=0, out_c0=out_c0,
                        tw_w=p.tw_w, ws=None, stages=1, slab=(G, rank * Hl, rowsT, ptrs), **common)
     d3 = AH.build_desc(x=None, y=y_local, inH=Ol, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Ol, outW=outW, out_r0=0, out_c0=out_c0,
@@ -310,14 +312,15 @@ class SlabAsm(torch.nn.Module):
             pad_h, pad_w, Hp, Wp = AH.compute_padding(H, W, self.padding_scale, self.do_padding)
             rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type)
             table, mode = None, 0
-            dv = AH.tf_device_vectors(rowvec, colvec, scal) if self.kernel_mode == "inregister" else None
+            chunked = AH.row_vectors_chunked(Hp)
+            dv = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked) if self.kernel_mode == "inregister" else None
             if dv is not None:
                 rowvec, colvec, scal = dv
             else:
                 Hc = AH.tf_centred_reference_order(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type)
                 table, mode = AH.tf_table_slot_order(Hc), 1
             self._plan = _SlabPlan(G, rank, C, H, W, pad_h, pad_w, Hp, Wp, bool(self.do_padding and self.do_unpad_after_pad),
-                                   data.device, rowvec, colvec, scal, table, mode)
+                                   data.device, rowvec, colvec, scal, table, mode, row_chunked=chunked)
             self._key = key
             self._slabs = self._make_slabs(B * C, data.device)
         elif self._slabs is not None and self._slabs.numel < B * C * max(self._plan.H, self._plan.outH) * self._plan.Wc:

@@ -30,14 +30,16 @@ def _setup(B, C, H, W, scale, lams, dxy, z, bt="exact", do_pad=True, unpad=True,
     ps = AH.normalise_padding_scale(scale, do_pad)
     ph, pw, Hp, Wp = AH.compute_padding(H, W, ps, do_pad)
     outH, outW, or0, oc0 = (H, W, ph, pw) if (do_pad and unpad) else (Hp, Wp, 0, 0)
-    rv, cv, sc = AH.tf_device_vectors(*AH.tf_vectors(Hp, Wp, dxy, lams, z, True, bt), E.thz_emul_slot_to_bin)
+    chunked = AH.row_vectors_chunked(Hp)      # the static column kernels read the row vectors in the chunked layout
+    rv, cv, sc = AH.tf_device_vectors(*AH.tf_vectors(Hp, Wp, dxy, lams, z, True, bt), E.thz_emul_slot_to_bin, chunked=chunked)
     table = None
     if mode == 1:
         table = AH.tf_table_slot_order(AH.tf_centred_reference_order(Hp, Wp, dxy, lams, z, True, bt), E.thz_emul_slot_to_bin)
     base = dict(B=B, C=C, inH=H, inW=W, Hp=Hp, Wp=Wp, in_r0=ph, in_c0=pw, outH=outH, outW=outW, out_r0=or0, out_c0=oc0,
                 tf_mode=mode, tf_conj=0, rowvec=rv, colvec=cv, scal=sc, table=table, doe_mode=0, doe_base=0.0, hmap=None,
                 coef=None, xsaved=None, gh=None, tw_h=N.twiddles_host(Hp), tw_w=N.twiddles_host(Wp),
-                ws=torch.zeros(AH.workspace_elems(B, C, max(H, outH), max(H, outH), Wp, chunk), dtype=torch.complex64), bc_chunk=chunk)
+                ws=torch.zeros(AH.workspace_elems(B, C, max(H, outH), max(H, outH), Wp, chunk), dtype=torch.complex64), bc_chunk=chunk,
+                tf_row_chunked=1 if (chunked and mode == 0) else 0)
     return base, (outH, outW)
 
 
@@ -164,11 +166,13 @@ def _slab_plans(G, C, H, W, lams, dxy, z, device, mode="inregister"):
     sp, wl = torch.tensor([dxy, dxy]), torch.tensor(lams)
     rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, sp, wl, torch.tensor(z), True, "exact")
     table, tf_mode = None, 0
+    chunked = AH.row_vectors_chunked(Hp)
     if mode == "inregister":
-        rowvec, colvec, scal = AH.tf_device_vectors(rowvec, colvec, scal)
+        rowvec, colvec, scal = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked)
     else:
         table, tf_mode = AH.tf_table_slot_order(AH.tf_centred_reference_order(Hp, Wp, sp, wl, torch.tensor(z), True, "exact")), 1
-    return [P._SlabPlan(G, r, C, H, W, pad_h, pad_w, Hp, Wp, True, device, rowvec, colvec, scal, table, tf_mode) for r in range(G)]
+    return [P._SlabPlan(G, r, C, H, W, pad_h, pad_w, Hp, Wp, True, device, rowvec, colvec, scal, table, tf_mode, row_chunked=chunked)
+            for r in range(G)]
 
 
 @pytest.mark.parametrize("G,mode", [(2, "cached"), (4, "inregister")])
