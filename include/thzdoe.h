@@ -138,6 +138,10 @@ typedef struct thz_asm_desc {
     int32_t reserved2;
 } thz_asm_desc;
 
+/* Bytes of `ws` a call with this descriptor needs (uses B, C, inH, outH, Hp, Wp, bc_chunk, stages, slab_parts): one
+ * intermediate of the live rows, [fields][max(inH, outH)][Wp] complex64 -- or two of them when both transform lengths are
+ * served by the static kernels and the whole pipeline runs (the row spectra are then kept in 4-column blocks for the
+ * column kernel, whose row-major output goes to the second half). */
 uint64_t thz_asm_workspace_bytes(const thz_asm_desc* desc);
 int thz_asm_propagate(const thz_asm_desc* desc, void* stream);
 

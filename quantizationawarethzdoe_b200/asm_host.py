@@ -286,7 +286,10 @@ def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, o
     return d
 
 
-def workspace_elems(B, C, inH, outH, Wp, bc_chunk=0):
-    nbc = B * C
-    chunk = bc_chunk if 0 < bc_chunk < nbc else nbc
-    return chunk * max(inH, outH) * Wp
+def workspace_elems(B, C, inH, outH, Wp, bc_chunk=0, Hp=None, stages=0):
+    """complex64 elements of workspace thz_asm_propagate needs (thz_asm_workspace_bytes): one intermediate of the live rows,
+    two when both transform lengths are served by the static kernels (blocked row spectra + row-major column-pass output)."""
+    d = N.AsmDesc()
+    d.B, d.C, d.inH, d.outH, d.Wp, d.Hp = B, C, inH, outH, Wp, (Hp if Hp is not None else 0)
+    d.bc_chunk, d.stages = bc_chunk, stages
+    return int(N.lib().thz_asm_workspace_bytes(ctypes.byref(d))) // 8

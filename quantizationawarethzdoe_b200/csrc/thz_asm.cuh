@@ -80,6 +80,18 @@ THZ_HD cpx* thz_slab_addr(const SlabArgs& sl, int f, int r, int p) {
     return sl.ptr[d] + ((size_t)f * sl.rows + (sl.row0 + r)) * sl.Wc + (p - d * sl.Wc);
 }
 
+// Blocked layout of the intermediate between the row-FFT and the column kernel (static kernels, whole-pipeline runs): the
+// columns are grouped in blocks of 4 (32 bytes = one sector) and all rows of a block are contiguous,
+//     T[f][c / 4][r][c % 4]   instead of   T[f][r][c].
+// The column pass, which walks down 2 (or 1, 4, ...) columns, then touches 4 cache lines per warp-wide load instead of
+// 16 (rows 32 bytes apart instead of Wp * 8) -- the L1 data pipe is the busiest unit of that kernel
+// (profiles/README.md) -- at the price of 8 instead of 2 lines per warp-wide STORE in the row-FFT kernel, which costs
+// little because stores do not stall.  The column kernel's output goes row-major to a second buffer: blocked READS in
+// the row-iFFT kernel cost more than the column kernel's stores gain (measured).
+THZ_HD size_t thz_t_tiled_index(int f, int r, int c, int rowsT, int Wp) {
+    return (((size_t)f * (Wp >> 2) + (c >> 2)) * rowsT + r) * 4 + (c & 3);
+}
+
 struct RowFwdArgs {
     const cpx* x;             // [nbc][inH][inW] (already offset to the chunk)
     cpx* T;                   // [nbc][rowsT][Wp]
@@ -93,6 +105,7 @@ struct RowFwdArgs {
     DoeArgs doe;
     int conj_in;              // conjugate on load (inverse transforms via conj . FFT . conj)
     SlabArgs slab;            // parts > 1: scatter the output rows into column slabs instead of T
+    int t_tiled;              // 1: T is stored in 4-column blocks, see thz_t_tiled_index
 };
 
 THZ_HD void k1_load(const RowFwdArgs& a, cpx* s, int bx, int tid, int nthreads) {
@@ -151,6 +164,9 @@ struct ColArgs {
     FftPlan planW;            // length Wp (only for slot -> bin of the column index)
     const cpx* tw;            // length Hp
     TfArgs tf;
+    int t_tiled;              // 1: the INPUT rows are read from T in 4-column blocks (thz_t_tiled_index) and the output rows
+                              //    are written row-major to Tout (a different buffer: not in place)
+    cpx* Tout;                // output buffer when t_tiled (else unused: in place in T)
 };
 
 THZ_HD void k2_load(const ColArgs& a, cpx* s, int bx, int by, int tid, int nthreads) {

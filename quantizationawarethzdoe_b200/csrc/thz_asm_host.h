@@ -56,12 +56,26 @@ static inline uint64_t thz_asm_chunk_fields(const thz_asm_desc* d) {
     return nbc;
 }
 
+static inline uint64_t rowsT_ws(const thz_asm_desc* d) { return (uint64_t)thz_imax(d->inH, d->outH); }
+// Lengths the static kernels serve and THZ_NO_P2 / THZ_NO_TILED do not veto: such whole-pipeline runs keep TWO
+// intermediates (blocked row spectra, row-major column-pass output), everything else one.
+static inline bool thz_asm_two_buffers(const thz_asm_desc* d);
 static inline uint64_t thz_asm_ws_bytes(const thz_asm_desc* d) {
-    return thz_asm_chunk_fields(d) * (uint64_t)thz_imax(d->inH, d->outH) * (uint64_t)d->Wp * sizeof(cpx);
+    const uint64_t one = thz_asm_chunk_fields(d) * rowsT_ws(d) * (uint64_t)d->Wp * sizeof(cpx);
+    return thz_asm_two_buffers(d) ? 2 * one : one;
 }
 
 
 static inline bool thz_is_p2_size(int n) { return thz_sp_instantiated(n); }
+static inline bool thz_env_is_1(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] == '1';
+}
+static inline bool thz_asm_two_buffers(const thz_asm_desc* d) {
+    const int st = d->stages ? d->stages : 7;
+    return st == 7 && d->slab_parts <= 1 && d->Wp % 4 == 0 && thz_is_p2_size(d->Wp) && thz_is_p2_size(d->Hp) &&
+           !thz_env_is_1("THZ_NO_P2") && !thz_env_is_1("THZ_NO_TILED");
+}
 
 static inline int thz_p2_row_lines_rt(int n) { return p2_row_lines(n); }
 static inline int thz_p2_tw_count_rt(int n) { return p2_tw_count(n); }
@@ -239,6 +253,17 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k3_smem = lines * line_bytes_w;
     }
     thz_asm_apply_p2(d, nbc, sm_count, L);
+    {
+        // blocked intermediate between the static kernels of a whole-pipeline run (THZ_NO_TILED=1 keeps row-major T)
+        const int tiled = thz_asm_two_buffers(d) ? 1 : 0;
+        L->k1.t_tiled = tiled;
+        L->k2.t_tiled = tiled;
+        L->k2.Tout = nullptr;
+        if (tiled) {     // second half of the workspace: the column kernel's row-major output, read by the row-iFFT kernel
+            L->k2.Tout = (cpx*)d->ws + (size_t)thz_asm_chunk_fields(d) * rowsT_ws(d) * d->Wp;
+            L->k3.T = L->k2.Tout;
+        }
+    }
     if (d->slab_parts > 1 && !L->p2_w) return THZ_E_UNSUPPORTED;   // only the static row kernels scatter / gather slabs
     if (d->tf_row_chunked && d->tf_mode == 0 && !L->p2_h) return THZ_E_UNSUPPORTED;   // chunked row vectors: static column kernels only
     return THZ_OK;

@@ -144,6 +144,10 @@ THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int n
             for (int p = tid; p < N; p += nt) *thz_slab_addr(a.slab, f, r, p) = sl[p + (p >> 4)];
             continue;
         }
+        if (a.t_tiled) {
+            for (int p = tid; p < N; p += nt) a.T[thz_t_tiled_index(f, r, p, a.rowsT, N)] = sl[p + (p >> 4)];
+            continue;
+        }
         cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
         for (int p = tid; p < N; p += nt) tr[p] = sl[p + (p >> 4)];
     }
@@ -152,7 +156,7 @@ THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int n
 // =============================================================================== K2<N, COLS>
 struct K2Loader {
     const cpx* col;     // T + field offset + column (NULL if the column is outside the grid)
-    int in_r0, inH, Wp;
+    int in_r0, inH, Wp;   // Wp: distance between consecutive rows of this column in T (elements)
     THZ_HD cpx operator()(int pos) const {
         const int r = pos - in_r0;
         if (col == nullptr || (unsigned)r >= (unsigned)inH) return cmake(0.f, 0.f);  // one compare: r < 0 wraps
@@ -175,10 +179,10 @@ THZ_HD void p2k2_first(const ColArgs& a, cpx* s, int bx, int by, int tid, int nt
         const int j = w / COLS, l = w % COLS;
         const int c = bx * COLS + l;
         K2Loader ld;
-        ld.col = c < a.Wp ? a.T + (size_t)by * a.rowsT * a.Wp + c : nullptr;
+        ld.col = c >= a.Wp ? nullptr : (a.t_tiled ? a.T + thz_t_tiled_index(by, 0, c, a.rowsT, a.Wp) : a.T + (size_t)by * a.rowsT * a.Wp + c);
         ld.in_r0 = a.in_r0;
         ld.inH = a.inH;
-        ld.Wp = a.Wp;
+        ld.Wp = a.t_tiled ? 4 : a.Wp;
         p2_first_stage_from<N, COLS>(s + l, j, a.tw, ld);
     }
 }
@@ -248,7 +252,7 @@ THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, const cpx* tw, int bx, int
         const int j = w / COLS, l = w % COLS;
         const int c = bx * COLS + l;
         K2Storer st;
-        st.col = c < a.Wp ? a.T + (size_t)by * a.rowsT * a.Wp + c : nullptr;
+        st.col = c < a.Wp ? (a.t_tiled ? a.Tout : a.T) + (size_t)by * a.rowsT * a.Wp + c : nullptr;   // output rows: always row-major
         st.out_r0 = a.out_r0;
         st.outH = a.outH;
         st.Wp = a.Wp;

@@ -79,7 +79,7 @@ class AsmPlan:
             inH, inW, in_r0, in_c0 = self.outH, self.outW, self.out_r0, self.out_c0
             outH, outW, out_r0, out_c0 = self.H, self.W, self.pad_h, self.pad_w
         nbc = x.shape[0] * x.shape[1]
-        ws = _workspace(AH.workspace_elems(x.shape[0], C, inH, outH, self.Wp, TUNE["bc_chunk"]), x.device)
+        ws = _workspace(AH.workspace_elems(x.shape[0], C, inH, outH, self.Wp, TUNE["bc_chunk"], Hp=self.Hp), x.device)
         d = AH.build_desc(x, y, x.shape[0], C, inH, inW, self.Hp, self.Wp, in_r0, in_c0, outH, outW, out_r0, out_c0,
                           self.tf_mode, 1 if conj else 0, self.rowvec, self.colvec, self.scal, self.table,
                           doe_mode, BASE_PLANE_THICKNESS, hmap, coef, xsaved, gh, self.tw_h, self.tw_w, ws,

@@ -38,7 +38,7 @@ def _setup(B, C, H, W, scale, lams, dxy, z, bt="exact", do_pad=True, unpad=True,
     base = dict(B=B, C=C, inH=H, inW=W, Hp=Hp, Wp=Wp, in_r0=ph, in_c0=pw, outH=outH, outW=outW, out_r0=or0, out_c0=oc0,
                 tf_mode=mode, tf_conj=0, rowvec=rv, colvec=cv, scal=sc, table=table, doe_mode=0, doe_base=0.0, hmap=None,
                 coef=None, xsaved=None, gh=None, tw_h=N.twiddles_host(Hp), tw_w=N.twiddles_host(Wp),
-                ws=torch.zeros(AH.workspace_elems(B, C, max(H, outH), max(H, outH), Wp, chunk), dtype=torch.complex64), bc_chunk=chunk,
+                ws=torch.zeros(AH.workspace_elems(B, C, max(H, outH), max(H, outH), Wp, chunk, Hp=Hp), dtype=torch.complex64), bc_chunk=chunk,
                 tf_row_chunked=1 if (chunked and mode == 0) else 0)
     return base, (outH, outW)
 

@@ -1,0 +1,5 @@
+cd $GRAFT_REPO_ROOT
+python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 300 python tools/config_bench.py czt iteration 2>&1 | grep "^{" | cut -c1-330
