@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     const int tid = threadIdx.x, nt = blockDim.x;
     const int ngroups = (a.nbc * a.inH + LINES - 1) / LINES;
     int grp = blockIdx.x;
-    for (int i = tid; i < p2_tw_count(N); i += nt) tws[i] = a.tw[i];     // visible after the first barrier below
+    p2_tw_fill<N>(tws, a.tw, tid, nt);                                  // visible after the first barrier below
     if constexpr (!p2_row_pipelined(N)) {     // no room for staging: plain load -> transform -> store per group
         for (; grp < ngroups; grp += gridDim.x) {
             p2k1_first<N>(a, s, grp, tid, nt);
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     cpx* s = reinterpret_cast<cpx*>(smem_raw);
     cpx* tws = s + COLS * p2_pitch(N);              // shared-memory copy of the twiddles the in-smem stages use
     const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x, by = blockIdx.y;
-    for (int i = tid; i < p2_tw_count(N); i += nt) tws[i] = a.tw[i];
+    p2_tw_fill<N>(tws, a.tw, tid, nt);
     p2k2_first<N, COLS>(a, s, bx, by, tid, nt);
     __syncthreads();
     fwd_cols<N, 1, NS - 1, COLS>(s, tid, nt, tws);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     cpx* s = reinterpret_cast<cpx*>(smem_raw);      // two line buffers: [0, BUF) and [BUF, 2 BUF)
     cpx* tws = s + (p2_row_pipelined(N) ? 2 : 1) * BUF;                  // shared-memory copy of the stage twiddles
     const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x;
-    for (int i = tid; i < p2_tw_count(N); i += nt) tws[i] = a.tw[i];     // visible after the first barrier below
+    p2_tw_fill<N>(tws, a.tw, tid, nt);                                  // visible after the first barrier below
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;

@@ -61,13 +61,22 @@ THZ_HD constexpr bool sp_static_ok(int N) {
 // Twiddles of every stage but the first are read from a shared-memory copy of tw[0 .. p2_tw_count(N)): stage s uses
 // tw[j * N / L_s] with j < L_s / R_s, i.e. indices below N / R_s.  (An inverse stage multiplies BEFORE its butterfly,
 // so nothing hides the load: from L2 it was ~7 % of the column kernel's stall samples, profiles/README.md.)
-THZ_HD constexpr int p2_tw_count(int N) {
+//   The copy is padded like the data (entry i at i + (i >> 4)): a later stage reads entries j * WT with WT a multiple of
+//   16, i.e. 128-byte strides that would all fall on one bank.
+THZ_HD constexpr int p2_twi(int i) { return i + (i >> 4); }
+THZ_HD constexpr int p2_tw_entries(int N) {      // table entries copied
     int n = 1;
     for (int s = 0; s < p2_stages(N); ++s) {
         const int L = p2_L(N, s), R = p2_radix(N, s);
         if (L / R > 1 && N / R > n) n = N / R;
     }
     return n;
+}
+THZ_HD constexpr int p2_tw_count(int N) { return (p2_twi(p2_tw_entries(N) - 1) + 2) & ~1; }   // shared-memory slots (even: what follows stays 16-byte aligned)
+// fill (all threads of the CTA / the host replay): tws[p2_twi(i)] = tw[i]
+template <int N>
+THZ_HD void p2_tw_fill(cpx* tws, const cpx* tw, int tid, int nthreads) {
+    for (int i = tid; i < p2_tw_entries(N); i += nthreads) tws[p2_twi(i)] = tw[i];
 }
 
 template <int N, int S>
@@ -117,9 +126,9 @@ THZ_HD void p2_butterfly(cpx* base, int u, const cpx* tw) {
     for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
     if (!INV) {
         Dft<R, false>::run(v);
-        if (M > 1) p2_apply_twiddles<R>(v, tw[j * St::WT]);          // tw: shared-memory copy (or the global table)
+        if (M > 1) p2_apply_twiddles<R>(v, tw[p2_twi(j * St::WT)]);  // tw: the padded shared-memory copy
     } else {
-        if (M > 1) p2_apply_twiddles<R>(v, cconj(tw[j * St::WT]));
+        if (M > 1) p2_apply_twiddles<R>(v, cconj(tw[p2_twi(j * St::WT)]));
         Dft<R, true>::run(v);
     }
 #pragma unroll
@@ -192,7 +201,7 @@ THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* tw, Stor
 #pragma unroll
         for (int t = 0; t < PF && t < R; ++t) store.prefetch(j + t * M, t);
     }
-    p2_apply_twiddles<R>(v, cconj(tw[j]));
+    p2_apply_twiddles<R>(v, cconj(tw[p2_twi(j)]));
     Dft<R, true>::run(v);
 #pragma unroll
     for (int t = 0; t < R; ++t) {
@@ -223,7 +232,7 @@ THZ_HD void p2_stage_cols(cpx* s, int tid, int nthreads, const cpx* tw) {
     typedef P2Stage<N, S> St;
     constexpr int NB = St::NB, M = St::M, R = St::R;
     if constexpr (NT > 0 && M > 1 && NT % COLS == 0 && (NT / COLS) % M == 0 && (COLS * NB) > NT) {
-        const cpx w1 = tw[((tid / COLS) % M) * St::WT];
+        const cpx w1 = tw[p2_twi(((tid / COLS) % M) * St::WT)];
         cpx w[R];
         twiddle_powers<R>(INV ? cconj(w1) : w1, w);
         for (int w_ = tid; w_ < COLS * NB; w_ += NT) p2_butterfly_w<N, S, INV, COLS>(s + w_ % COLS, w_ / COLS, w);

@@ -115,6 +115,8 @@ static void e_inv_cols(cpx* s, int nt, const cpx* tw) {
 
 template <int N>
 static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
+    std::vector<cpx> tws(p2_tw_count(N));            // padded twiddle copy, as the kernels keep it in shared memory
+    p2_tw_fill<N>(tws.data(), a.tw, 0, 1);
     constexpr int LINES = p2_row_lines(N);
     std::vector<unsigned char> buf(smem);
     cpx* s = (cpx*)buf.data();
@@ -127,7 +129,7 @@ static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
         if constexpr (!p2_row_pipelined(N)) {
             for (; grp < ngroups; grp += g) {
                 for_threads(nt, [&](int t) { p2k1_first<N>(a, s, grp, t, nt); });
-                e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, a.tw);
+                e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, tws.data());
                 for_threads(nt, [&](int t) { p2k1_store<N>(a, s, grp, t, nt); });
             }
             continue;
@@ -137,27 +139,31 @@ static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
             // the replay copies synchronously, so the "next" prefetch must not clobber the staging buffer before it is consumed
             for_threads(nt, [&](int t) { p2k1_first_staged<N>(a, s, xs, hs, grp, t, nt); });
             if (grp + g < ngroups) for_threads(nt, [&](int t) { p2k1_prefetch<N>(a, xs, hs, grp + g, t, nt); });
-            e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, a.tw);
+            e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, tws.data());
             for_threads(nt, [&](int t) { p2k1_store<N>(a, s, grp, t, nt); });
         }
     }
 }
 template <int N>
 static void run_p2_k2(const ColArgs& a, int gx, int gy, int nt, size_t smem) {
+    std::vector<cpx> tws(p2_tw_count(N));            // padded twiddle copy, as the kernels keep it in shared memory
+    p2_tw_fill<N>(tws.data(), a.tw, 0, 1);
     constexpr int COLS = p2_col_cols(N), NS = p2_stages(N);
     std::vector<unsigned char> buf(smem);
     cpx* s = (cpx*)buf.data();
     for (int by = 0; by < gy; ++by)
         for (int bx = 0; bx < gx; ++bx) {
             for_threads(nt, [&](int t) { p2k2_first<N, COLS>(a, s, bx, by, t, nt); });
-            e_fwd_cols<N, 1, NS - 1, COLS>(s, nt, a.tw);
+            e_fwd_cols<N, 1, NS - 1, COLS>(s, nt, tws.data());
             for_threads(nt, [&](int t) { p2k2_middle<N, COLS>(a, s, bx, by, t, nt); });
-            e_inv_cols<N, NS - 2, 1, COLS>(s, nt, a.tw);
-            for_threads(nt, [&](int t) { p2k2_last<N, COLS>(a, s, a.tw, bx, by, t, nt); });
+            e_inv_cols<N, NS - 2, 1, COLS>(s, nt, tws.data());
+            for_threads(nt, [&](int t) { p2k2_last<N, COLS>(a, s, tws.data(), bx, by, t, nt); });
         }
 }
 template <int N>
 static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) {
+    std::vector<cpx> tws(p2_tw_count(N));            // padded twiddle copy, as the kernels keep it in shared memory
+    p2_tw_fill<N>(tws.data(), a.tw, 0, 1);
     constexpr int NACC = p2k3_acc<N>(), LINES = p2_row_lines(N), BUF = LINES * p2_pitch(N);
     typedef float acc_t[NACC];
     std::vector<unsigned char> buf(smem);
@@ -171,8 +177,8 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
             if constexpr (!p2_row_pipelined(N)) {
                 for (int f = f_lo; f < f_hi; ++f) {
                     for_threads(nt, [&](int t) { p2k3_load<N>(a, s, bx, f, t, nt); });
-                    e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, nt, a.tw);
-                    for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, s, a.tw, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                    e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, nt, tws.data());
+                    for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, s, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
                 }
                 for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
                 continue;
@@ -181,8 +187,8 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
             for (int f = f_lo; f < f_hi; ++f, cur ^= 1) {
                 cpx* sc = s + cur * BUF;
                 if (f + 1 < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, t, nt); });
-                e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, nt, a.tw);
-                for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, sc, a.tw, bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, nt, tws.data());
+                for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, sc, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
             }
             for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
         }
