@@ -88,8 +88,8 @@ THZ_HD cpx* thz_slab_addr(const SlabArgs& sl, int f, int r, int p) {
 // (profiles/README.md) -- at the price of 8 instead of 2 lines per warp-wide STORE in the row-FFT kernel, which costs
 // little because stores do not stall.  The column kernel's output goes row-major to a second buffer: blocked READS in
 // the row-iFFT kernel cost more than the column kernel's stores gain (measured).
-THZ_HD size_t thz_t_tiled_index(int f, int r, int c, int rowsT, int Wp) {
-    return (((size_t)f * (Wp >> 2) + (c >> 2)) * rowsT + r) * 4 + (c & 3);
+THZ_HD size_t thz_t_tiled_index(int f, int r, int c, int rowsT, int Wp, int k = 2) {     // blocks of 2^k columns
+    return ((((size_t)f * (Wp >> k) + (c >> k)) * rowsT + r) << k) + (c & ((1 << k) - 1));
 }
 
 struct RowFwdArgs {
@@ -164,9 +164,10 @@ struct ColArgs {
     FftPlan planW;            // length Wp (only for slot -> bin of the column index)
     const cpx* tw;            // length Hp
     TfArgs tf;
-    int t_tiled;              // 1: the INPUT rows are read from T in 4-column blocks (thz_t_tiled_index) and the output rows
-                              //    are written row-major to Tout (a different buffer: not in place)
+    int t_tiled;              // k > 0: the INPUT rows are read from T in 2^k-column blocks (thz_t_tiled_index) and the output
+                              //    rows are written to Tout (a different buffer: not in place)
     cpx* Tout;                // output buffer when t_tiled (else unused: in place in T)
+    int tout_tiled;           // k > 0: Tout is blocked as well (experiment), 0: row-major
 };
 
 THZ_HD void k2_load(const ColArgs& a, cpx* s, int bx, int by, int tid, int nthreads) {
@@ -282,6 +283,7 @@ struct RowInvArgs {
     float* gh;                // [outH][outW]
     int gh_atomic;            // 1: several CTAs contribute to one gh element -> atomicAdd
     SlabArgs slab;            // parts > 1: gather the input rows from column slabs instead of T
+    int t_tiled;              // k > 0: T is stored in 2^k-column blocks (experiment)
 };
 
 THZ_HD void k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nthreads) {

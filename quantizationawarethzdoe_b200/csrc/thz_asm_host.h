@@ -255,9 +255,17 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     thz_asm_apply_p2(d, nbc, sm_count, L);
     {
         // blocked intermediate between the static kernels of a whole-pipeline run (THZ_NO_TILED=1 keeps row-major T)
-        const int tiled = thz_asm_two_buffers(d) ? 1 : 0;
+        int tiled = thz_asm_two_buffers(d) ? 2 : 0, tiled2 = 0;
+        if (tiled) {      // experiment knobs: log2 of the block widths of the two intermediates
+            const char* e1 = getenv("THZ_T1_LOG2");
+            const char* e2 = getenv("THZ_T2_LOG2");
+            if (e1 && e1[0] >= '1' && e1[0] <= '4' && d->Wp % (1 << (e1[0] - '0')) == 0) tiled = e1[0] - '0';
+            if (e2 && e2[0] >= '1' && e2[0] <= '4' && d->Wp % (1 << (e2[0] - '0')) == 0) tiled2 = e2[0] - '0';
+        }
         L->k1.t_tiled = tiled;
         L->k2.t_tiled = tiled;
+        L->k2.tout_tiled = tiled2;
+        L->k3.t_tiled = tiled2;
         L->k2.Tout = nullptr;
         if (tiled) {     // second half of the workspace: the column kernel's row-major output, read by the row-iFFT kernel
             L->k2.Tout = (cpx*)d->ws + (size_t)thz_asm_chunk_fields(d) * rowsT_ws(d) * d->Wp;

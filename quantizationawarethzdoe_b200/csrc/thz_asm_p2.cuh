@@ -145,7 +145,7 @@ THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int n
             continue;
         }
         if (a.t_tiled) {
-            for (int p = tid; p < N; p += nt) a.T[thz_t_tiled_index(f, r, p, a.rowsT, N)] = sl[p + (p >> 4)];
+            for (int p = tid; p < N; p += nt) a.T[thz_t_tiled_index(f, r, p, a.rowsT, N, a.t_tiled)] = sl[p + (p >> 4)];
             continue;
         }
         cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
@@ -179,10 +179,10 @@ THZ_HD void p2k2_first(const ColArgs& a, cpx* s, int bx, int by, int tid, int nt
         const int j = w / COLS, l = w % COLS;
         const int c = bx * COLS + l;
         K2Loader ld;
-        ld.col = c >= a.Wp ? nullptr : (a.t_tiled ? a.T + thz_t_tiled_index(by, 0, c, a.rowsT, a.Wp) : a.T + (size_t)by * a.rowsT * a.Wp + c);
+        ld.col = c >= a.Wp ? nullptr : (a.t_tiled ? a.T + thz_t_tiled_index(by, 0, c, a.rowsT, a.Wp, a.t_tiled) : a.T + (size_t)by * a.rowsT * a.Wp + c);
         ld.in_r0 = a.in_r0;
         ld.inH = a.inH;
-        ld.Wp = a.t_tiled ? 4 : a.Wp;
+        ld.Wp = a.t_tiled ? (1 << a.t_tiled) : a.Wp;
         p2_first_stage_from<N, COLS>(s + l, j, a.tw, ld);
     }
 }
@@ -252,10 +252,11 @@ THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, const cpx* tw, int bx, int
         const int j = w / COLS, l = w % COLS;
         const int c = bx * COLS + l;
         K2Storer st;
-        st.col = c < a.Wp ? (a.t_tiled ? a.Tout : a.T) + (size_t)by * a.rowsT * a.Wp + c : nullptr;   // output rows: always row-major
+        st.col = c >= a.Wp ? nullptr : (a.tout_tiled ? a.Tout + thz_t_tiled_index(by, 0, c, a.rowsT, a.Wp, a.tout_tiled)
+                                                    : (a.t_tiled ? a.Tout : a.T) + (size_t)by * a.rowsT * a.Wp + c);
         st.out_r0 = a.out_r0;
         st.outH = a.outH;
-        st.Wp = a.Wp;
+        st.Wp = a.tout_tiled ? (1 << a.tout_tiled) : a.Wp;
         p2_last_inverse_stage_to<N, COLS>(s + l, j, tw, st);
     }
 }
@@ -271,6 +272,10 @@ THZ_HD void p2k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int n
         cpx* sl = s + l * PITCH;
         if (a.slab.parts > 1) {           // slab FFT: gather the row from the column slabs of all GPUs
             for (int p = tid; p < N; p += nt) sl[p + (p >> 4)] = *thz_slab_addr(a.slab, f, r, p);
+            continue;
+        }
+        if (a.t_tiled) {
+            for (int p = tid; p < N; p += nt) sl[p + (p >> 4)] = a.T[thz_t_tiled_index(f, r, p, a.rowsT, N, a.t_tiled)];
             continue;
         }
         const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
@@ -290,6 +295,10 @@ THZ_HD void p2k3_prefetch(const RowInvArgs& a, cpx* s, int bx, int f, int tid, i
         cpx* sl = s + l * PITCH;
         if (a.slab.parts > 1) {
             for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), thz_slab_addr(a.slab, f, r, p));
+            continue;
+        }
+        if (a.t_tiled) {
+            for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), a.T + thz_t_tiled_index(f, r, p, a.rowsT, N, a.t_tiled));
             continue;
         }
         const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
