@@ -145,7 +145,11 @@ THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int n
             continue;
         }
         if (a.t_tiled) {
-            for (int p = tid; p < N; p += nt) a.T[thz_t_tiled_index(f, r, p, a.rowsT, N, a.t_tiled)] = sl[p + (p >> 4)];
+            // blocked store: consecutive p of a thread are nt apart, i.e. nt >> k blocks further -- one pointer step
+            const int k = a.t_tiled;
+            cpx* q = a.T + thz_t_tiled_index(f, r, tid, a.rowsT, N, k);
+            const size_t step = ((size_t)(nt >> k) * a.rowsT) << k;          // nt is a multiple of the block width
+            for (int p = tid; p < N; p += nt, q += step) *q = sl[p + (p >> 4)];
             continue;
         }
         cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
