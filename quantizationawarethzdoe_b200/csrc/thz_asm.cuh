@@ -15,15 +15,6 @@
 #pragma once
 #include "thz_fft.cuh"
 
-struct AsmGeom {
-    int B, C;                 // batch, wavelengths
-    int inH, inW;             // live input region
-    int Hp, Wp;               // transform size
-    int in_r0, in_c0;         // where the input sits inside the Hp x Wp canvas
-    int outH, outW;           // output (crop) region
-    int out_r0, out_c0;
-};
-
 struct TfArgs {
     int mode;                 // 0: generate H in registers from separable vectors; 1: cached table; 2: H == 1
     int conj;                 // 1: use conj(H) (adjoint / backward)
@@ -161,7 +152,6 @@ struct ColArgs {
     int in_r0, out_r0;
     int cols;                 // columns per CTA tile
     FftPlan plan;             // length Hp (column transform)
-    FftPlan planW;            // length Wp (only for slot -> bin of the column index)
     const cpx* tw;            // length Hp
     TfArgs tf;
     int t_tiled;              // k > 0: the INPUT rows are read from T in 2^k-column blocks (thz_t_tiled_index) and the output

@@ -186,7 +186,6 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a2.in_r0 = d->in_r0;
     a2.out_r0 = d->out_r0;
     a2.plan = ph;
-    a2.planW = pw;
     a2.tw = (const cpx*)d->tw_h;
     a2.tf.mode = d->tf_mode;
     a2.tf.conj = d->tf_conj;

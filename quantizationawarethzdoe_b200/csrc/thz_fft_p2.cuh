@@ -38,11 +38,6 @@ THZ_HD constexpr int p2_stages(int N) {
     }
     return k;
 }
-THZ_HD constexpr int p2_log2(int v) {
-    int k = 0;
-    while ((1 << k) < v) ++k;
-    return k;
-}
 // slot offset of element t of a butterfly with sub-block length M (relative to the slot of element 0)
 THZ_HD constexpr int p2_coff(int M, int t) { return t * M + ((t * M) >> 4); }
 
@@ -88,20 +83,6 @@ struct P2Stage {
     static constexpr int WT = N / L;      // twiddle table step and bin weight of this digit
     static constexpr int NB = N / R;      // butterflies per line
 };
-
-// slot -> bin for a slot that is the first element of a last-stage butterfly (p0 = u * R_last):
-// digits of stage s < last are (p0 / M_s) % R_s.
-template <int N>
-THZ_HD int p2_bin_of_slot(int pos) {
-    int bin = 0;
-#pragma unroll
-    for (int s = 0; s < p2_stages(N); ++s) {
-        const int M = p2_L(N, s) / p2_radix(N, s);
-        const int q = (pos / M) % p2_radix(N, s);
-        bin += q * (N / p2_L(N, s));
-    }
-    return bin;
-}
 
 template <int R>
 THZ_HD void p2_apply_twiddles(cpx (&v)[R], cpx w1) {
