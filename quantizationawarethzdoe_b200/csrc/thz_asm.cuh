@@ -96,6 +96,7 @@ struct RowFwdArgs {
     DoeArgs doe;
     int conj_in;              // conjugate on load (inverse transforms via conj . FFT . conj)
     SlabArgs slab;            // parts > 1: scatter the output rows into column slabs instead of T
+    int half_in;              // 1: the input columns are exactly [Wp/4, 3Wp/4) (centred 2x padding): pruned first stage
     int t_tiled;              // 1: T is stored in 4-column blocks, see thz_t_tiled_index
 };
 
@@ -157,6 +158,7 @@ struct ColArgs {
     int t_tiled;              // k > 0: the INPUT rows are read from T in 2^k-column blocks (thz_t_tiled_index) and the output
                               //    rows are written to Tout (a different buffer: not in place)
     cpx* Tout;                // output buffer when t_tiled (else unused: in place in T)
+    int half_in, half_out;    // 1: input / output rows are exactly [Hp/4, 3Hp/4): pruned first / last stage
     int tout_tiled;           // k > 0: Tout is blocked as well (experiment), 0: row-major
 };
 
@@ -273,6 +275,7 @@ struct RowInvArgs {
     float* gh;                // [outH][outW]
     int gh_atomic;            // 1: several CTAs contribute to one gh element -> atomicAdd
     SlabArgs slab;            // parts > 1: gather the input rows from column slabs instead of T
+    int half_out;             // 1: the output columns are exactly [Wp/4, 3Wp/4): pruned last stage
     int t_tiled;              // k > 0: T is stored in 2^k-column blocks (experiment)
 };
 

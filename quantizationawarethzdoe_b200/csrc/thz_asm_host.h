@@ -271,6 +271,13 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
             L->k3.T = L->k2.Tout;
         }
     }
+    {   // centred 2x padding / crop: the static kernels prune their first / last radix-16 stage (THZ_NO_PRUNE=1: off)
+        const bool on = !thz_env_is_1("THZ_NO_PRUNE");
+        L->k1.half_in = (on && 4 * d->in_c0 == d->Wp && 2 * d->inW == d->Wp) ? 1 : 0;
+        L->k2.half_in = (on && 4 * d->in_r0 == d->Hp && 2 * d->inH == d->Hp) ? 1 : 0;
+        L->k2.half_out = (on && 4 * d->out_r0 == d->Hp && 2 * d->outH == d->Hp) ? 1 : 0;
+        L->k3.half_out = (on && 4 * d->out_c0 == d->Wp && 2 * d->outW == d->Wp) ? 1 : 0;
+    }
     if (d->slab_parts > 1 && !L->p2_w) return THZ_E_UNSUPPORTED;   // only the static row kernels scatter / gather slabs
     if (d->tf_row_chunked && d->tf_mode == 0 && !L->p2_h) return THZ_E_UNSUPPORTED;   // chunked row vectors: static column kernels only
     return THZ_OK;

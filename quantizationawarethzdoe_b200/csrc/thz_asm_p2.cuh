@@ -46,6 +46,14 @@ struct K1Loader {
         if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
         return v;
     }
+    THZ_HD cpx live(int pos) const {             // pos known to be inside [in_c0, in_c0 + inW)
+        if (xr == nullptr) return cmake(0.f, 0.f);
+        const int c = pos - in_c0;
+        cpx v = xr[c];
+        if (conj_in) v.y = -v.y;
+        if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
+        return v;
+    }
 };
 
 template <int N>
@@ -71,7 +79,8 @@ THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
                 ld.hr = a.doe.hmap + (size_t)r * a.inW;
             }
         }
-        p2_first_stage_from<N, 1>(s + line * PITCH, j, a.tw, ld);
+        if (a.half_in) p2_first_stage_from<N, 1, true>(s + line * PITCH, j, a.tw, ld);
+        else p2_first_stage_from<N, 1>(s + line * PITCH, j, a.tw, ld);
     }
 }
 
@@ -126,7 +135,8 @@ THZ_HD void p2k1_first_staged(const RowFwdArgs& a, cpx* s, const cpx* xs, const 
                 ld.hr = hs + (size_t)line * a.inW;
             }
         }
-        p2_first_stage_from<N, 1>(s + line * PITCH, j, a.tw, ld);
+        if (a.half_in) p2_first_stage_from<N, 1, true>(s + line * PITCH, j, a.tw, ld);
+        else p2_first_stage_from<N, 1>(s + line * PITCH, j, a.tw, ld);
     }
 }
 
@@ -166,6 +176,7 @@ struct K2Loader {
         if (col == nullptr || (unsigned)r >= (unsigned)inH) return cmake(0.f, 0.f);  // one compare: r < 0 wraps
         return col[(size_t)r * Wp];
     }
+    THZ_HD cpx live(int pos) const { return col ? col[(size_t)(pos - in_r0) * Wp] : cmake(0.f, 0.f); }
 };
 struct K2Storer {
     cpx* col;
@@ -173,6 +184,9 @@ struct K2Storer {
     THZ_HD void operator()(int pos, int, cpx v) const {
         const int r = pos - out_r0;
         if (col != nullptr && (unsigned)r < (unsigned)outH) col[(size_t)r * Wp] = v;
+    }
+    THZ_HD void live(int pos, int, int, cpx v) const {
+        if (col != nullptr) col[(size_t)(pos - out_r0) * Wp] = v;
     }
 };
 
@@ -187,7 +201,8 @@ THZ_HD void p2k2_first(const ColArgs& a, cpx* s, int bx, int by, int tid, int nt
         ld.in_r0 = a.in_r0;
         ld.inH = a.inH;
         ld.Wp = a.t_tiled ? (1 << a.t_tiled) : a.Wp;
-        p2_first_stage_from<N, COLS>(s + l, j, a.tw, ld);
+        if (a.half_in) p2_first_stage_from<N, COLS, true>(s + l, j, a.tw, ld);
+        else p2_first_stage_from<N, COLS>(s + l, j, a.tw, ld);
     }
 }
 
@@ -261,7 +276,8 @@ THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, const cpx* tw, int bx, int
         st.out_r0 = a.out_r0;
         st.outH = a.outH;
         st.Wp = a.tout_tiled ? (1 << a.tout_tiled) : a.Wp;
-        p2_last_inverse_stage_to<N, COLS>(s + l, j, tw, st);
+        if (a.half_out) p2_last_inverse_stage_to<N, COLS, true>(s + l, j, tw, st);
+        else p2_last_inverse_stage_to<N, COLS>(s + l, j, tw, st);
     }
 }
 
@@ -335,19 +351,31 @@ struct K3Storer {
         hq[t % PF] = thz_ldg(hrow + c);
         xq[t % PF] = thz_ldg(xrow + c);
     }
+    THZ_HD void prefetch_live(int pos, int slot) {      // pos known to be inside the crop
+        if (hrow == nullptr) return;
+        const int c = pos - out_c0;
+        hq[slot % PF] = thz_ldg(hrow + c);
+        xq[slot % PF] = thz_ldg(xrow + c);
+    }
+    THZ_HD void live(int pos, int slot, int t, cpx v) {
+        emit(pos - out_c0, slot, t, v);
+    }
     THZ_HD void operator()(int pos, int t, cpx v) {
         const int c = pos - out_c0;
         if ((unsigned)c >= (unsigned)outW) return;
+        emit(c, t, t, v);
+    }
+    THZ_HD void emit(int c, int slot, int t, cpx v) {
         v = cscale(v, scale);
         if (hrow == nullptr) {
             yrow[c] = v;
             return;
         }
-        const cpx p = thz_doe_phase(hq[t % PF], cf, base);
+        const cpx p = thz_doe_phase(hq[slot % PF], cf, base);
         const cpx q = cmulc(v, p);                 // grad wrt the field that entered the DOE
         if (yrow) yrow[c] = q;
         // gh += Re(conj(v) x p gamma) = Re(conj(q) x gamma)
-        const cpx xg = cmul(xq[t % PF], gamma);
+        const cpx xg = cmul(xq[slot % PF], gamma);
         acc[t] += q.x * xg.x + q.y * xg.y;
     }
 };
@@ -402,7 +430,8 @@ THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, 
         st.xrow = a.xsaved ? a.xsaved + o : nullptr;
         st.hrow = a.doe.hmap ? a.doe.hmap + (size_t)r * a.outW : nullptr;
         st.acc = &acc[k * R];
-        p2_last_inverse_stage_to<N, 1>(s + line * PITCH, j, tw, st);
+        if (a.half_out) p2_last_inverse_stage_to<N, 1, true>(s + line * PITCH, j, tw, st);
+        else p2_last_inverse_stage_to<N, 1>(s + line * PITCH, j, tw, st);
     }
 }
 

@@ -163,6 +163,59 @@ THZ_HD void dft_ct(cpx (&v)[R1 * R2]) {
     }
 }
 
+// ---------------------------------------------------------------- pruned radix-16 butterflies (2x zero padding)
+// A line that is zero-padded to twice its length, centred, is live in [N/4, 3N/4): element t of a first-stage butterfly
+// (stride N/16) is live iff 4 <= t < 12, for every butterfly -- and likewise only outputs 4..11 of a last inverse
+// stage butterfly survive the crop.  In the 4 x 4 Cooley-Tukey form:
+//   inputs 0..3, 12..15 zero : every first-layer radix-4 sees (0, a, b, 0): 4 complex adds instead of 8;
+//   outputs 4..11 only       : every second-layer radix-4 needs outputs 1 and 2 only: 6 instead of 8.
+template <bool INV>
+THZ_HD void dft16_half_in(const cpx (&in)[8], cpx (&v)[16]) {       // in[i] = v[4 + i]
+    cpx y[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        const cpx a = in[n2], b = in[4 + n2];                       // n1 = 1 and n1 = 2
+        const cpx ia = INV ? cmul_pi(a) : cmul_mi(a);               // w4 a
+        cpx t[4];
+        t[0] = cadd(a, b);
+        t[1] = csub(ia, b);                                         // w4 a + w4^2 b
+        t[2] = csub(b, a);                                          // w4^2 a + w4^4 b
+        t[3] = csub(cmake(-ia.x, -ia.y), b);                        // w4^3 a + w4^6 b
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) y[k1 * 4 + n2] = mul_root<16, INV>(t[k1], n2 * k1);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        cpx t[4];
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) t[n2] = y[k1 * 4 + n2];
+        Dft<4, INV>::run(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = t[k2];
+    }
+}
+template <bool INV>
+THZ_HD void dft16_half_out(const cpx (&v)[16], cpx (&out)[8]) {     // out[i] = V[4 + i]
+    cpx y[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        cpx t[4];
+#pragma unroll
+        for (int n1 = 0; n1 < 4; ++n1) t[n1] = v[4 * n1 + n2];
+        Dft<4, INV>::run(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) y[k1 * 4 + n2] = mul_root<16, INV>(t[k1], n2 * k1);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {                                // outputs k1 + 4 k2 for k2 = 1, 2
+        const cpx a = cadd(y[k1 * 4 + 0], y[k1 * 4 + 2]), b = csub(y[k1 * 4 + 0], y[k1 * 4 + 2]);
+        const cpx c = cadd(y[k1 * 4 + 1], y[k1 * 4 + 3]), d = csub(y[k1 * 4 + 1], y[k1 * 4 + 3]);
+        const cpx id = INV ? cmul_pi(d) : cmul_mi(d);
+        out[k1] = cadd(b, id);                                      // k2 = 1 -> V[4 + k1]
+        out[4 + k1] = csub(a, c);                                   // k2 = 2 -> V[8 + k1]
+    }
+}
+
 #define THZ_DFT_CT(R, R1, R2)                                             \
     template <bool INV>                                                   \
     struct Dft<R, INV> {                                                  \

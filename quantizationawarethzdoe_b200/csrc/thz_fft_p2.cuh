@@ -144,14 +144,21 @@ THZ_HD void p2_butterfly_w(cpx* base, int u, const cpx (&w)[P2Stage<N, S>::R]) {
 // ---------------------------------------------------------------- first forward stage, inputs from a functor
 //   load(pos) returns the input at logical position pos in [0, N).  Stage 0 has a single block (L = N), so
 //   butterfly j touches positions j + t*M.
-template <int N, int STRIDE, typename Load>
+template <int N, int STRIDE, bool HALF = false, typename Load>
 THZ_HD void p2_first_stage_from(cpx* base, int j, const cpx* __restrict__ tw, Load load) {
     typedef P2Stage<N, 0> St;
     constexpr int R = St::R, M = St::M;
     cpx v[R];
+    if constexpr (HALF && R == 16) {        // centred 2x padding: only t = 4..11 are live, no bounds checks (load.live)
+        cpx in[8];
 #pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = load(j + t * M);
-    Dft<R, false>::run(v);
+        for (int t = 0; t < 8; ++t) in[t] = load.live(j + (4 + t) * M);
+        dft16_half_in<false>(in, v);
+    } else {
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = load(j + t * M);
+        Dft<R, false>::run(v);
+    }
     p2_apply_twiddles<R>(v, thz_ldg(tw + j));
     cpx* p = base + (j + (j >> 4)) * STRIDE;
 #pragma unroll
@@ -170,7 +177,7 @@ struct P2StorePF {
     static constexpr int get(...) { return 0; }
     static constexpr int value = get<Store>(0);
 };
-template <int N, int STRIDE, typename Store>
+template <int N, int STRIDE, bool HALF = false, typename Store>
 THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* tw, Store store) {
     typedef P2Stage<N, 0> St;
     constexpr int R = St::R, M = St::M, PF = P2StorePF<Store>::value;
@@ -178,17 +185,34 @@ THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* tw, Stor
     cpx v[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) v[t] = p[p2_coff(M, t) * STRIDE];
-    if constexpr (PF > 0) {
-#pragma unroll
-        for (int t = 0; t < PF && t < R; ++t) store.prefetch(j + t * M, t);
-    }
-    p2_apply_twiddles<R>(v, cconj(tw[p2_twi(j)]));
-    Dft<R, true>::run(v);
-#pragma unroll
-    for (int t = 0; t < R; ++t) {
-        store(j + t * M, t, v[t]);
+    if constexpr (HALF && R == 16) {        // centred crop to half the line: only outputs 4..11 exist (store.live)
         if constexpr (PF > 0) {
-            if (t + PF < R) store.prefetch(j + (t + PF) * M, t + PF);
+#pragma unroll
+            for (int t = 0; t < PF && t < 8; ++t) store.prefetch_live(j + (4 + t) * M, t);
+        }
+        p2_apply_twiddles<R>(v, cconj(tw[p2_twi(j)]));
+        cpx out[8];
+        dft16_half_out<true>(v, out);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            store.live(j + (4 + t) * M, t, 4 + t, out[t]);
+            if constexpr (PF > 0) {
+                if (t + PF < 8) store.prefetch_live(j + (4 + t + PF) * M, t + PF);
+            }
+        }
+    } else {
+        if constexpr (PF > 0) {
+#pragma unroll
+            for (int t = 0; t < PF && t < R; ++t) store.prefetch(j + t * M, t);
+        }
+        p2_apply_twiddles<R>(v, cconj(tw[p2_twi(j)]));
+        Dft<R, true>::run(v);
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            store(j + t * M, t, v[t]);
+            if constexpr (PF > 0) {
+                if (t + PF < R) store.prefetch(j + (t + PF) * M, t + PF);
+            }
         }
     }
 }
