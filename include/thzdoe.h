@@ -118,17 +118,22 @@ typedef struct thz_asm_desc {
     int32_t stages;            /* 0 = whole pipeline; else bit mask 1 = row FFT (x -> ws), 2 = column pass (ws in
                                   place), 4 = row iFFT + epilogue (ws -> y): the slab-decomposed multi-GPU FFT runs
                                   the three stages separately around its all-to-all transposes                 */
-    /* Slab-decomposed FFT over peer memory (NVLink P2P), slab_parts > 1, stages == 1 or stages == 4 only:
-       the intermediate lives as COLUMN slabs, one per GPU: slab_ptrs[d] = complex64 [B*C][slab_rows][Wp/slab_parts] on
-       GPU d (peer-mapped pointers; d == own rank is the local buffer).  stages == 1: the row-FFT kernel writes segment d
-       of each of its rows (local row r = global row slab_row0 + r) straight into slab_ptrs[d] -- the transpose happens
-       in the kernel's stores, no all-to-all.  stages == 4: the row-iFFT kernel gathers segment d of its rows from
-       slab_ptrs[d].  ws is not used.  The caller orders the stages across GPUs (a barrier after stage 1 and one after
-       stage 2).  Static-path widths only (THZ_E_UNSUPPORTED otherwise).                                              */
+    /* Slab-decomposed FFT over peer memory (NVLink P2P), slab_parts > 1, one stage per call (stages == 1, 2 or 4).
+       Every GPU d owns TWO column slabs of Wc = Wp / slab_parts columns, complex64 [B*C][slab_rows][Wc]:
+         S1[d]  row spectra of ITS columns; row-major, or, if slab_blocked, in 4-column blocks [B*C][Wc/4][slab_rows][4]
+                (what the column kernel reads best, but 32-byte remote stores: slower over NVLink, measured);
+         S2[d]  the column pass output, row-major.
+       stages == 1: slab_ptrs[d] = S1[d] (peer-mapped).  The row-FFT kernel writes segment d of each of its rows (local
+                    row r = global row slab_row0 + r) straight into S1[d]: the transpose happens in the kernel's stores.
+       stages == 2: (descriptor of the local column pass: Wp = Wc) ws = S1[own], slab_ptrs[0] = S2[own].
+       stages == 4: slab_ptrs[d] = S2[d] (peer-mapped).  The row-iFFT kernel gathers segment d of its rows from S2[d].
+       The caller orders the stages across GPUs: a barrier after stage 1 and one after stage 2 (none between calls:
+       a stage only writes the buffer that no GPU can still be reading).  Static-path lengths only
+       (THZ_E_UNSUPPORTED otherwise); Wc must be a multiple of 4.                                                        */
     int32_t slab_parts;        /* 0 or 1: off                                                               */
     int32_t slab_row0;         /* global row index of this GPU's first row                                  */
     int32_t slab_rows;         /* rows per field in every column slab                                       */
-    int32_t slab_reserved;
+    int32_t slab_blocked;      /* layout of S1 (stages 1 and 2 must agree)                                    */
     void* slab_ptrs[8];
     /* tf_mode 0 only.  0: tf_rowvec is [C][Hp][2] in slot order.  1: "chunked" for the static column kernels, whose
        threads each own the R consecutive slots 16u .. of one last-stage butterfly: [C][R/2][Hp/R] float4 entries, entry

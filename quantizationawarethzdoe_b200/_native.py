@@ -44,7 +44,7 @@ class AsmDesc(ctypes.Structure):
         ("bc_chunk", ctypes.c_int32), ("tune_k2_cols", ctypes.c_int32),
         ("tune_lines", ctypes.c_int32), ("stages", ctypes.c_int32),
         ("slab_parts", ctypes.c_int32), ("slab_row0", ctypes.c_int32),
-        ("slab_rows", ctypes.c_int32), ("slab_reserved", ctypes.c_int32),
+        ("slab_rows", ctypes.c_int32), ("slab_blocked", ctypes.c_int32),
         ("slab_ptrs", ctypes.c_void_p * 8),
         ("tf_row_chunked", ctypes.c_int32), ("reserved2", ctypes.c_int32),
     ]

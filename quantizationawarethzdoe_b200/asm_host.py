@@ -278,8 +278,9 @@ def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, o
     d.ws = N.ptr(ws)
     d.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
     d.tf_row_chunked = int(tf_row_chunked)
-    if slab is not None:          # (parts, row0, rows, [pointer of every rank's column slab]); see thz_asm_desc.slab_*
+    if slab is not None:          # (parts, row0, rows, [pointer of every rank's column slab][, blocked]); see thz_asm_desc.slab_*
         d.slab_parts, d.slab_row0, d.slab_rows = int(slab[0]), int(slab[1]), int(slab[2])
+        d.slab_blocked = int(slab[4]) if len(slab) > 4 else 0
         for i, q in enumerate(slab[3]):
             d.slab_ptrs[i] = int(q)
     d.bc_chunk, d.tune_k2_cols, d.tune_lines, d.stages = bc_chunk, tune_k2_cols, tune_lines, stages

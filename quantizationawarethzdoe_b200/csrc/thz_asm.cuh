@@ -61,15 +61,14 @@ THZ_HD cpx thz_tf_value(float2 rv, float ky2, float2 sc, int conj) {
 
 // =============================================================================== K1: row forward
 // Column slabs of a multi-GPU slab FFT (see thz_asm_desc.slab_*): element p of global row (row0 + r) of field f lives in
-// slab d = p / Wc at ptr[d][(f * rows + row0 + r) * Wc + p % Wc]; ptr[d] may be peer memory.
+// slab d = p / Wc, column cc = p % Wc, at ptr[d][(f * rows + row0 + r) * Wc + cc] (row-major slabs, what the row-iFFT
+// kernel gathers from) or, for the slabs the row-FFT kernel scatters into, in 4-column blocks
+// ptr[d][((f * Wc/4 + cc/4) * rows + row0 + r) * 4 + cc % 4]; ptr[d] may be peer memory.
 struct SlabArgs {
     int parts, row0, rows, Wc;
+    int blocked;
     cpx* ptr[8];
 };
-THZ_HD cpx* thz_slab_addr(const SlabArgs& sl, int f, int r, int p) {
-    const int d = p / sl.Wc;
-    return sl.ptr[d] + ((size_t)f * sl.rows + (sl.row0 + r)) * sl.Wc + (p - d * sl.Wc);
-}
 
 // Blocked layout of the intermediate between the row-FFT and the column kernel (static kernels, whole-pipeline runs): the
 // columns are grouped in blocks of 4 (32 bytes = one sector) and all rows of a block are contiguous,
@@ -81,6 +80,12 @@ THZ_HD cpx* thz_slab_addr(const SlabArgs& sl, int f, int r, int p) {
 // the row-iFFT kernel cost more than the column kernel's stores gain (measured).
 THZ_HD size_t thz_t_tiled_index(int f, int r, int c, int rowsT, int Wp, int k = 2) {     // blocks of 2^k columns
     return ((((size_t)f * (Wp >> k) + (c >> k)) * rowsT + r) << k) + (c & ((1 << k) - 1));
+}
+
+THZ_HD cpx* thz_slab_addr(const SlabArgs& sl, int f, int r, int p) {
+    const int d = p / sl.Wc, cc = p - d * sl.Wc;
+    if (sl.blocked) return sl.ptr[d] + thz_t_tiled_index(f, sl.row0 + r, cc, sl.rows, sl.Wc, 2);
+    return sl.ptr[d] + ((size_t)f * sl.rows + (sl.row0 + r)) * sl.Wc + cc;
 }
 
 struct RowFwdArgs {
@@ -157,7 +162,7 @@ struct ColArgs {
     TfArgs tf;
     int t_tiled;              // k > 0: the INPUT rows are read from T in 2^k-column blocks (thz_t_tiled_index) and the output
                               //    rows are written to Tout (a different buffer: not in place)
-    cpx* Tout;                // output buffer when t_tiled (else unused: in place in T)
+    cpx* Tout;                // separate output buffer (NULL: in place in T)
     int half_in, half_out;    // 1: input / output rows are exactly [Hp/4, 3Hp/4): pruned first / last stage
     int tout_tiled;           // k > 0: Tout is blocked as well (experiment), 0: row-major
 };

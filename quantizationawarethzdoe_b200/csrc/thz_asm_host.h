@@ -29,7 +29,7 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     const int st = d->stages ? d->stages : 7;
     if (st < 0 || st > 7) return THZ_E_SHAPE;
     if (st != 7 && d->bc_chunk > 0 && d->bc_chunk < d->B * d->C) return THZ_E_SHAPE;   // staged runs keep all fields in ws
-    if (((st & 1) && !d->x) || !d->tw_h || !d->tw_w || (!d->ws && d->slab_parts <= 1)) return THZ_E_NULL;
+    if (((st & 1) && !d->x) || !d->tw_h || !d->tw_w || (!d->ws && (d->slab_parts <= 1 || st == 2))) return THZ_E_NULL;
     if (d->B < 1 || d->C < 1 || d->inH < 1 || d->inW < 1 || d->outH < 1 || d->outW < 1) return THZ_E_SHAPE;
     if (d->in_r0 < 0 || d->in_c0 < 0 || d->out_r0 < 0 || d->out_c0 < 0) return THZ_E_SHAPE;
     if (d->in_r0 + d->inH > d->Hp || d->in_c0 + d->inW > d->Wp) return THZ_E_SHAPE;
@@ -42,10 +42,16 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     if ((st & 4) && d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
     if ((st & 4) && d->doe_mode != 2 && !d->y) return THZ_E_NULL;
     if (d->slab_parts > 1) {
-        if (d->slab_parts > 8 || (st != 1 && st != 4) || d->Wp % d->slab_parts || d->slab_rows < 1 || d->slab_row0 < 0) return THZ_E_SHAPE;
-        if (d->slab_row0 + (st == 1 ? d->inH : d->outH) > d->slab_rows) return THZ_E_SHAPE;
-        for (int i = 0; i < d->slab_parts; ++i)
-            if (!d->slab_ptrs[i]) return THZ_E_NULL;
+        if (d->slab_parts > 8 || (st != 1 && st != 2 && st != 4) || d->slab_rows < 1 || d->slab_row0 < 0) return THZ_E_SHAPE;
+        if (st == 2) {          // local column pass between the two slabs: ws = S1 (blocked), slab_ptrs[0] = S2 (row-major)
+            if ((d->slab_blocked && d->Wp % 4) || d->slab_rows < thz_imax(d->inH, d->outH)) return THZ_E_SHAPE;
+            if (!d->ws || !d->slab_ptrs[0]) return THZ_E_NULL;
+        } else {
+            if (d->Wp % d->slab_parts || (d->slab_blocked && (d->Wp / d->slab_parts) % 4)) return THZ_E_SHAPE;
+            if (d->slab_row0 + (st == 1 ? d->inH : d->outH) > d->slab_rows) return THZ_E_SHAPE;
+            for (int i = 0; i < d->slab_parts; ++i)
+                if (!d->slab_ptrs[i]) return THZ_E_NULL;
+        }
     }
     return THZ_OK;
 }
@@ -156,9 +162,14 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         sl.row0 = d->slab_row0;
         sl.rows = d->slab_rows;
         sl.Wc = d->Wp / d->slab_parts;
+        sl.blocked = 0;
         for (int i = 0; i < 8; ++i) sl.ptr[i] = i < d->slab_parts ? (cpx*)d->slab_ptrs[i] : nullptr;
-        a1.slab = sl;
-        L->k3.slab = sl;
+        const int st_ = d->stages ? d->stages : 7;
+        if (st_ != 2) {
+            L->k3.slab = sl;          // stage 4 gathers from the row-major slabs S2
+            sl.blocked = d->slab_blocked ? 1 : 0;   // stage 1 scatters into S1 (optionally in 4-column blocks)
+            a1.slab = sl;
+        }
     }
     {
         // enough lines per CTA to give 256 threads at least one radix-16 butterfly each
@@ -266,6 +277,12 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k2.tout_tiled = tiled2;
         L->k3.t_tiled = tiled2;
         L->k2.Tout = nullptr;
+        if ((d->stages ? d->stages : 7) == 2 && d->slab_parts > 1) {   // column pass of a peer-memory slab FFT: S1 (ws) -> S2
+            L->k2.t_tiled = d->slab_blocked ? 2 : 0;
+            L->k2.tout_tiled = 0;
+            L->k2.Tout = (cpx*)d->slab_ptrs[0];
+            if (!L->p2_h) return THZ_E_UNSUPPORTED;
+        }
         if (tiled) {     // second half of the workspace: the column kernel's row-major output, read by the row-iFFT kernel
             L->k2.Tout = (cpx*)d->ws + (size_t)thz_asm_chunk_fields(d) * rowsT_ws(d) * d->Wp;
             L->k3.T = L->k2.Tout;
@@ -278,7 +295,7 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k2.half_out = (on && 4 * d->out_r0 == d->Hp && 2 * d->outH == d->Hp) ? 1 : 0;
         L->k3.half_out = (on && 4 * d->out_c0 == d->Wp && 2 * d->outW == d->Wp) ? 1 : 0;
     }
-    if (d->slab_parts > 1 && !L->p2_w) return THZ_E_UNSUPPORTED;   // only the static row kernels scatter / gather slabs
+    if (d->slab_parts > 1 && (d->stages & 5) && !L->p2_w) return THZ_E_UNSUPPORTED;   // only the static row kernels scatter / gather slabs
     if (d->tf_row_chunked && d->tf_mode == 0 && !L->p2_h) return THZ_E_UNSUPPORTED;   // chunked row vectors: static column kernels only
     return THZ_OK;
 }

@@ -272,7 +272,7 @@ THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, const cpx* tw, int bx, int
         const int c = bx * COLS + l;
         K2Storer st;
         st.col = c >= a.Wp ? nullptr : (a.tout_tiled ? a.Tout + thz_t_tiled_index(by, 0, c, a.rowsT, a.Wp, a.tout_tiled)
-                                                    : (a.t_tiled ? a.Tout : a.T) + (size_t)by * a.rowsT * a.Wp + c);
+                                                    : (a.Tout ? a.Tout : a.T) + (size_t)by * a.rowsT * a.Wp + c);   // Tout: not in place
         st.out_r0 = a.out_r0;
         st.outH = a.outH;
         st.Wp = a.tout_tiled ? (1 << a.tout_tiled) : a.Wp;

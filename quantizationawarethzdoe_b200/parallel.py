@@ -15,6 +15,8 @@ Two patterns:
    Only live rows travel: zero-pad pruning halves the first exchange and crop pruning the second.
    Backward is the same schedule with conj(H) and the pad / crop regions swapped.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -148,29 +150,36 @@ def _slab_run(x_local, p, conj, group):
 
 # ----------------------------------------------------------------------------- slab FFT over peer memory (NVLink P2P)
 class _PeerSlabs:
-    """One column slab [nbc, rows, Wc] per rank in symmetric memory: every rank holds peer-mapped pointers to all of
-    them, so the row-FFT kernel can store each row segment straight into its owner's slab and the row-iFFT kernel can
-    read its rows straight out of the peers' slabs -- the two transposes of the slab FFT happen inside the kernels'
-    stores / loads and overlap with the butterflies; no pack / all-to-all / unpack passes.  torch's symmetric-memory
-    allocator provides the mapping and a stream-ordered cross-GPU barrier (plumbing); the data path is ours."""
+    """Two column slabs per rank in symmetric memory -- S1 [nbc, Wc/4, rows, 4] (row spectra, blocked for the column kernel)
+    and S2 [nbc, rows, Wc] (column pass output) -- with peer-mapped pointers to all of them on every rank, so the row-FFT
+    kernel can store each row segment straight into its owner's S1 and the row-iFFT kernel can read its rows straight
+    out of the peers' S2: the two transposes of the slab FFT happen inside the kernels' stores / loads and overlap with the
+    butterflies; no pack / all-to-all / unpack passes.  torch's symmetric-memory allocator provides the mapping and a
+    stream-ordered cross-GPU barrier (plumbing); the data path is ours."""
 
     def __init__(self, numel, device, group):
         import torch.distributed._symmetric_memory as symm
-        self.buf = symm.empty(2 * numel, dtype=torch.float32, device=device)      # complex64 as float pairs
+        self.buf = symm.empty(4 * numel, dtype=torch.float32, device=device)      # 2 x numel complex64 as float pairs
         self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-        self.ptrs = [int(q) for q in self.hdl.buffer_ptrs]
+        base = [int(q) for q in self.hdl.buffer_ptrs]
+        self.ptrs1 = base
+        self.ptrs2 = [q + 8 * numel for q in base]
         self.numel = numel
 
-    def local(self, nbc, rows, Wc):
-        return torch.view_as_complex(self.buf.view(-1, 2))[:nbc * rows * Wc].view(nbc, rows, Wc)
+    def local(self, which):
+        c = torch.view_as_complex(self.buf.view(-1, 2))
+        return c[:self.numel] if which == 1 else c[self.numel:]
 
     def barrier(self):
         self.hdl.barrier()
 
 
-def _slab_stage_descs(p, x_local, y_local, rank, ptrs, conj):
-    """The three descriptors of one rank's part of a peer-memory slab propagation (stage 1 scatter, stage 2 on the local
-    column slab, stage 4 gather).  ptrs[d] = address of rank d's column slab [nbc, rowsT, Wc]."""
+SLAB_BLOCKED = int(os.environ.get("THZ_SLAB_BLOCKED", "0"))   # 1: S1 slabs in 4-column blocks (32-byte remote stores: slower on NVLink)
+
+
+def _slab_stage_descs(p, x_local, y_local, rank, ptrs1, ptrs2, s1_local, conj):
+    """The three descriptors of one rank's part of a peer-memory slab propagation (stage 1 scatter into the S1 slabs, stage 2
+    from the local S1 to the local S2, stage 4 gather from the S2 slabs).  ptrsK[d] = address of rank d's slab SK."""
     G, B, C = p.G, x_local.shape[0], p.C
     if not conj:
         inH, inW, in_r0, in_c0, outH, outW, out_r0, out_c0 = p.H, p.W, p.pad_h, p.pad_w, p.outH, p.outW, p.out_r0, p.out_c0
@@ -182,33 +191,28 @@ def _slab_stage_descs(p, x_local, y_local, rank, ptrs, conj):
                   doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h, colvec=p.colvec, table=p.table,
                   tf_row_chunked=p.row_chunked)
     d1 = AH.build_desc(x=x_local, y=None, inH=Hl, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Hl, outW=outW, out_r0=0, out_c0=out_c0,
-                       tw_w=p.tw_w, ws=None, stages=1, slab=(G, rank * Hl, rowsT, ptrs), **common)
+                       tw_w=p.tw_w, ws=None, stages=1, slab=(G, rank * Hl, rowsT, ptrs1, SLAB_BLOCKED), **common)
+    d2 = AH.build_desc(x=None, y=None, inH=inH, inW=min(inW, Wc), Wp=Wc, in_r0=in_r0, in_c0=0, outH=outH, outW=min(outW, Wc),
+                       out_r0=out_r0, out_c0=0, tw_w=p.tw_c, ws=s1_local, stages=2, slab=(G, 0, rowsT, [ptrs2[rank]], SLAB_BLOCKED), **common)
     d3 = AH.build_desc(x=None, y=y_local, inH=Ol, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Ol, outW=outW, out_r0=0, out_c0=out_c0,
-                       tw_w=p.tw_w, ws=None, stages=4, slab=(G, rank * Ol, rowsT, ptrs), **common)
-
-    def d2(t2):
-        return AH.build_desc(x=None, y=None, inH=inH, inW=min(inW, Wc), Wp=Wc, in_r0=in_r0, in_c0=0, outH=outH, outW=min(outW, Wc),
-                             out_r0=out_r0, out_c0=0, tw_w=p.tw_c, ws=t2, stages=2, **common)
-    return d1, d2, d3, (Ol, outW, rowsT)
+                       tw_w=p.tw_w, ws=None, stages=4, slab=(G, rank * Ol, rowsT, ptrs2), **common)
+    return d1, d2, d3
 
 
 def _slab_run_peer(x_local, p, conj, slabs):
     """Slab-decomposed propagation with the transposes fused into the row kernels (see _PeerSlabs)."""
     B, C, dev = x_local.shape[0], p.C, x_local.device
     outH, outW = (p.outH, p.outW) if not conj else (p.H, p.W)
-    inH = p.H if not conj else p.outH
     y = torch.empty(B, C, outH // p.G, outW, dtype=torch.complex64, device=dev)
-    d1, d2, d3, (_, _, rowsT) = _slab_stage_descs(p, x_local, y, p.rank, slabs.ptrs, conj)
-    t2 = slabs.local(B * C, rowsT, p.Wc)
+    d1, d2, d3 = _slab_stage_descs(p, x_local, y, p.rank, slabs.ptrs1, slabs.ptrs2, slabs.local(1), conj)
     _mark("start")
-    slabs.barrier()                      # every rank has finished reading the slabs of the previous call
-    Fn._asm_call(d1, dev)                # row FFT; stores go to the owners of the column blocks
+    Fn._asm_call(d1, dev)                # row FFT; stores go to the owners of the column blocks (their S1)
     _mark("row fft + scatter")
-    slabs.barrier()                      # all row segments have landed in my column slab
-    Fn._asm_call(d2(t2), dev)            # column FFT . H . column iFFT in place
+    slabs.barrier()                      # all row segments have landed in my S1
+    Fn._asm_call(d2, dev)                # column FFT . H . column iFFT: S1 -> S2
     _mark("column pass")
-    slabs.barrier()                      # every column slab is final
-    Fn._asm_call(d3, dev)                # row iFFT; loads come from the owners of the column blocks
+    slabs.barrier()                      # every S2 is final
+    Fn._asm_call(d3, dev)                # row iFFT; loads come from the owners of the column blocks (their S2)
     _mark("gather + row ifft")
     return y
 
@@ -221,24 +225,24 @@ def slab_emulate_ranks(x_full, plans, conj=False):
     inH = p0.H if not conj else p0.outH
     outH, outW = (p0.outH, p0.outW) if not conj else (p0.H, p0.W)
     rowsT = max(p0.H, p0.outH)
-    slabs = [torch.zeros(B * p0.C, rowsT, p0.Wc, dtype=torch.complex64, device=dev) for _ in range(G)]
-    ptrs = [t.data_ptr() for t in slabs]
+    n = B * p0.C * rowsT * p0.Wc
+    s1 = [torch.zeros(n, dtype=torch.complex64, device=dev) for _ in range(G)]
+    s2 = [torch.zeros(n, dtype=torch.complex64, device=dev) for _ in range(G)]
+    ptrs1, ptrs2 = [t.data_ptr() for t in s1], [t.data_ptr() for t in s2]
     Hl = inH // G
     ys = [torch.empty(B, p0.C, outH // G, outW, dtype=torch.complex64, device=dev) for _ in range(G)]
     xs = [x_full[:, :, r * Hl:(r + 1) * Hl].contiguous() for r in range(G)]
-    descs = [_slab_stage_descs(plans[r], xs[r], ys[r], r, ptrs, conj) for r in range(G)]
-    for r in range(G):
-        Fn._asm_call(descs[r][0], dev)
-    for r in range(G):
-        Fn._asm_call(descs[r][1](slabs[r]), dev)
-    for r in range(G):
-        Fn._asm_call(descs[r][2], dev)
+    descs = [_slab_stage_descs(plans[r], xs[r], ys[r], r, ptrs1, ptrs2, s1[r], conj) for r in range(G)]
+    for k in range(3):
+        for r in range(G):
+            Fn._asm_call(descs[r][k], dev)
     return torch.cat(ys, dim=2)
 
 
 def _peer_transport_possible(plan, device):
     from . import _native
-    return device.type == "cuda" and dist.get_backend() == "nccl" and plan.G <= 8 and bool(_native.lib().thz_fft_is_static(plan.Wp))
+    return (device.type == "cuda" and dist.get_backend() == "nccl" and plan.G <= 8 and plan.Wc % 4 == 0 and
+            bool(_native.lib().thz_fft_is_static(plan.Wp)) and bool(_native.lib().thz_fft_is_static(plan.Hp)))
 
 
 class _SlabFn(torch.autograd.Function):

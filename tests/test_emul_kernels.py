@@ -211,7 +211,7 @@ def test_slab_descriptor_is_validated():
     kw = dict(base, x=x, y=None, inH=64, outH=64, in_r0=0, out_r0=0, ws=None)
     ok = AH.build_desc(**dict(kw, stages=1, slab=(2, 64, 128, [slab.data_ptr(), slab.data_ptr()])))
     assert E.thz_emul_asm_propagate(ctypes.byref(ok), 148) == 0
-    for bad in (dict(stages=2), dict(stages=1, slab=(3, 0, 128, [slab.data_ptr()] * 3)), dict(stages=1, slab=(2, 100, 128, [slab.data_ptr()] * 2)),
+    for bad in (dict(stages=3), dict(stages=2), dict(stages=1, slab=(3, 0, 128, [slab.data_ptr()] * 3)), dict(stages=1, slab=(2, 100, 128, [slab.data_ptr()] * 2)),
                 dict(stages=1, slab=(2, 0, 128, [slab.data_ptr(), 0]))):
         d = AH.build_desc(**dict(dict(kw, stages=1, slab=(2, 64, 128, [slab.data_ptr(), slab.data_ptr()])), **bad))
         assert E.thz_emul_asm_propagate(ctypes.byref(d), 148) in (-1, -2), bad
