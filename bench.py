@@ -315,7 +315,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": "metric shape: STE %d-level DOE + band-limited ASM fwd+bwd, x=(1,%d,%d,%d) c64 per GPU, 2x pad -> %d^2, "
                                "z=100 mm, dx=0.5 mm, lambda=1 mm(1+0.01c)" % (LEVELS, C, n, n, Np),
                    "fields_per_gpu": B * C, "samples_per_step": samples_per_step, "kernel_mode": asm.kernel_mode,
-                   "l2": "inputs larger than L2 (512 MiB fields + 1 GiB spectra per step)", "tune": dict(Fn.TUNE),
+                   "l2": "inputs larger than L2 (512 MiB fields + 2 x 1 GiB intermediate spectra per step)", "tune": dict(Fn.TUNE),
                    "parallelism": "dp%d over wavelengths, NCCL all-reduce of grad(weights)" % world if world > 1 else "single GPU"},
         "e2e": {"value": e2e_val, "unit": "Msamples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_host.numel() * 8,
                 "d2h_bytes_per_step": gw_host.numel() * 4},
