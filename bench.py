@@ -225,25 +225,30 @@ def run_ours(args, rank, local_rank, world):
     # ---- e2e: host buffers in, host gradient out, through the same module API.  Every step copies ITS input
     # fields from pinned host memory and reads its weight gradient back; the copy of step i+1 runs on a second
     # stream while step i computes (two device buffers), which is how a user would feed a stream of fields.
-    copy_stream = torch.cuda.Stream(device=dev)
+    ncopy = int(os.environ.get("THZ_E2E_COPY_STREAMS", "1"))       # the H2D copy may be split over several streams
+    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(ncopy)]
     bufs = [torch.empty_like(x_dev).detach() for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]      # H2D of the buffer finished
+    ready = [[torch.cuda.Event() for _ in range(ncopy)] for _ in range(2)]      # H2D of the buffer finished
     freed = [torch.cuda.Event() for _ in range(2)]      # compute that read the buffer finished
+    parts = [slice(k * C // ncopy, (k + 1) * C // ncopy) for k in range(ncopy)]
+
+    def h2d(b, wait):
+        for k, cs in enumerate(copy_streams):
+            with torch.cuda.stream(cs):
+                if wait:
+                    cs.wait_event(freed[b])
+                bufs[b][:, parts[k]].copy_(x_host[:, parts[k]], non_blocking=True)
+                ready[b][k].record(cs)
 
     def e2e_run(nsteps):
         cur = torch.cuda.current_stream(dev)
-        with torch.cuda.stream(copy_stream):
-            bufs[0].copy_(x_host, non_blocking=True)
-            ready[0].record(copy_stream)
+        h2d(0, False)
         for i in range(nsteps):
             b = i & 1
             if i + 1 < nsteps:
-                with torch.cuda.stream(copy_stream):
-                    if i >= 1:
-                        copy_stream.wait_event(freed[b ^ 1])
-                    bufs[b ^ 1].copy_(x_host, non_blocking=True)
-                    ready[b ^ 1].record(copy_stream)
-            cur.wait_event(ready[b])
+                h2d(b ^ 1, i >= 1)
+            for ev in ready[b]:
+                cur.wait_event(ev)
             gw = step(bufs[b].detach().requires_grad_(True))     # fresh leaf over the same storage
             freed[b].record(cur)
             gw_host.copy_(gw, non_blocking=True)
