@@ -227,6 +227,30 @@ def gen_train(R):
         save(name, p0=p0, grads=torch.stack(grads), hist=torch.stack(hist), weight_decay=np.float64(wd), decoupled=np.int64(dec))
 
 
+def gen_rsc(R):
+    """Rayleigh-Sommerfeld convolution (Props/RSC_Prop.py): scalar and vectorial, forward output + input gradient."""
+    cpu = torch.device("cpu")
+    cases = {"rsc_pow2": (1, 2, 64, 64, [1 * mm, 1.05 * mm], 0.5 * mm, 0.1), "rsc_rect": (1, 1, 48, 40, [1 * mm], [1 * mm, 0.7 * mm], 0.2),
+             "rsc_notebook": (1, 1, 100, 100, [1 * mm], 1 * mm, 0.3)}
+    for name, (B, C, H, W, lams, dxy, z) in cases.items():
+        torch.manual_seed(zlib.crc32(name.encode()) % 1000)
+        x = torch.randn(B, C, H, W, dtype=torch.complex64, requires_grad=True)
+        g = torch.randn(B, C, H, W, dtype=torch.complex64)
+        prop = R.RSC_prop(z_distance=z, device=cpu)
+        prop.check_Zc = False      # check_RS_minimum_z (Props/RSC_Prop.py:117) crashes when its energy-conservation bound is <= 0
+        with quiet():
+            y = prop(R.ElectricField(x, wavelengths=lams, spacing=dxy, device=cpu)).data
+        (gx,) = torch.autograd.grad(y, x, g)
+        save(name, x=x, y=y, g=g, gx=gx, wavelengths=np.array(lams), spacing=np.array(dxy if isinstance(dxy, list) else [dxy, dxy]), z=np.float64(z))
+    torch.manual_seed(9)
+    x = torch.randn(3, 2, 32, 32, dtype=torch.complex64)
+    prop = R.VRS_prop(z_distance=0.08, device=cpu)
+    prop.check_Zc = False
+    with quiet():
+        y = prop(R.ElectricField(x, wavelengths=[1 * mm, 1.1 * mm], spacing=0.5 * mm, device=cpu)).data
+    save("rsc_vectorial", x=x, y=y, wavelengths=np.array([1 * mm, 1.1 * mm]), spacing=np.array([0.5 * mm, 0.5 * mm]), z=np.float64(0.08))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = import_reference()
@@ -235,3 +259,4 @@ if __name__ == "__main__":
     gen_quant(R)
     gen_czt(R)
     gen_train(R)
+    gen_rsc(R)

@@ -60,6 +60,7 @@ def import_reference():
         from DataType.ElectricField import ElectricField
         from Props.ASM_Prop import ASM_prop
         from Props.CZT_Prop import CZT_prop
+        from Props.RSC_Prop import RSC_prop, VRS_prop
         import Components.QuantizedDOE as QD
         import Components.quantization as QZ
         from Components.discrete_doe import DiscreteDOE
@@ -67,6 +68,8 @@ def import_reference():
     ns.ElectricField = ElectricField
     ns.ASM_prop = ASM_prop
     ns.CZT_prop = CZT_prop
+    ns.RSC_prop = RSC_prop
+    ns.VRS_prop = VRS_prop
     ns.QD = QD
     ns.QZ = QZ
     ns.DiscreteDOE = DiscreteDOE

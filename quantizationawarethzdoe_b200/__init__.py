@@ -16,6 +16,7 @@ from .Components.QuantizedDOE import (
 )
 
 from .Props.CZT_Prop import CZT_prop
+from .Props.RSC_Prop import RSC_prop, VRS_prop
 from .train import FusedAdam, normalized_intensity_mse
 
 __version__ = "0.1.0"

@@ -489,3 +489,36 @@ def test_peer_memory_slab_kernels_on_one_gpu(G, n, dev):
     (gxr,) = torch.autograd.grad(yr, xr, g)
     assert torch.equal(y, yr.detach())
     assert torch.equal(gx, gxr)
+
+
+# ------------------------------------------------------------------------------- Rayleigh-Sommerfeld
+@pytest.mark.parametrize("name", golden_names("rsc_"))
+def test_rsc_matches_reference_vectors(name, dev):
+    """RSC_prop / VRS_prop on the fused FFT pipeline (input in the upper-left corner, lower-right crop, cached spectrum of
+    the impulse response) against the reference's own output and input gradient."""
+    from quantizationawarethzdoe_b200 import ElectricField, RSC_prop, VRS_prop
+    g = golden(name)
+    cls = VRS_prop if name == "rsc_vectorial" else RSC_prop
+    prop = cls(z_distance=g["z"], device=dev)
+    prop.check_Zc = False
+    x = g["x"].to(dev).requires_grad_(True)
+    y = prop(ElectricField(x, wavelengths=g["wavelengths"].float(), spacing=g["spacing"].float(), device=dev)).data
+    assert y.shape == g["y"].shape
+    assert rel_l2(y.detach().cpu(), g["y"]) < TOL
+    if "gx" in g:
+        (gx,) = torch.autograd.grad(y, x, g["g"].to(dev))
+        assert rel_l2(gx.cpu(), g["gx"]) < TOL
+
+
+def test_rsc_large_vs_oracle(dev):
+    """512 -> 1024 grid (static kernels, blocked intermediate) and a batch of fields vs the oracle."""
+    from oracle import rsc_oracle as RO
+    from quantizationawarethzdoe_b200 import ElectricField, RSC_prop
+    torch.manual_seed(2)
+    x = torch.randn(2, 2, 512, 512, dtype=torch.complex64)
+    lams = [1 * mm, 1.02 * mm]
+    yo = RO.rsc_forward(x, lams, 0.5 * mm, 0.25)
+    prop = RSC_prop(z_distance=0.25, device=dev)
+    prop.check_Zc = False
+    y = prop(ElectricField(x.to(dev), wavelengths=lams, spacing=0.5 * mm, device=dev)).data
+    assert rel_l2(y.cpu(), yo) < TOL

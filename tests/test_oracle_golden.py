@@ -152,3 +152,17 @@ def test_adam_oracle_matches_torch_optimizers(name):
     g = golden(name)
     hist = TO.adam_reference(g["p0"], list(g["grads"]), lr=0.02, weight_decay=g["weight_decay"], decoupled=bool(g["decoupled"]))
     assert torch.equal(torch.stack(hist), g["hist"])
+
+
+@pytest.mark.parametrize("name", golden_names("rsc_"))
+def test_rsc_oracle_matches_reference_vectors(name):
+    """Rayleigh-Sommerfeld convolution restatement vs the reference's RSC_prop / VRS_prop (Props/RSC_Prop.py)."""
+    from oracle import rsc_oracle as RO
+    g = golden(name)
+    fwd = RO.vrs_forward if name == "rsc_vectorial" else RO.rsc_forward
+    x = g["x"].clone().requires_grad_(True)
+    y = fwd(x, g["wavelengths"].float(), g["spacing"].float(), g["z"])
+    assert rel_l2(y.detach(), g["y"]) <= 2e-6
+    if "gx" in g:
+        (gx,) = torch.autograd.grad(y, x, g["g"])
+        assert rel_l2(gx, g["gx"]) <= 2e-6
