@@ -263,6 +263,11 @@ int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* desc, void* stream);
  *   advance = 1 for the last tensor of a parameter group.  No host-side state, so the launch sequence can be
  *   captured in a CUDA graph.
  * ------------------------------------------------------------------------------------------- */
+/* thz_field_mul: y[f][p] = x[f][p] * m, the pointwise optical elements between propagations -- the thin lens phase
+ * (Components/Thin_Lens.py:31-85: m complex64 [C][HW], per_channel = 1) and the aperture mask (Components/Aperture.py:
+ * 105-135: m float32 [HW], m_real = 1).  conj_m = 1 gives the adjoint (gradient wrt x).  x, y complex64 [BC][HW]. */
+int thz_field_mul(const void* x, const void* m, void* y, int32_t BC, int32_t C, uint64_t HW, int32_t per_channel,
+                  int32_t m_real, int32_t conj_m, void* stream);
 int thz_normmse_loss(const void* y, const void* target, int32_t B, uint64_t n_per_b, void* scratch, void* loss,
                      void* gy, void* stream);
 int thz_adam_step(void* p, const void* g, void* m, void* v, void* step, uint64_t n, float lr, float beta1, float beta2,

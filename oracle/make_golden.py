@@ -251,6 +251,27 @@ def gen_rsc(R):
     save("rsc_vectorial", x=x, y=y, wavelengths=np.array([1 * mm, 1.1 * mm]), spacing=np.array([0.5 * mm, 0.5 * mm]), z=np.float64(0.08))
 
 
+def gen_elements(R):
+    """Thin lens and apertures (Components/Thin_Lens.py, Components/Aperture.py): forward output + input gradient."""
+    cpu = torch.device("cpu")
+    torch.manual_seed(21)
+    x = torch.randn(2, 2, 33, 40, dtype=torch.complex64, requires_grad=True)
+    g = torch.randn(2, 2, 33, 40, dtype=torch.complex64)
+    lams, sp = [1 * mm, 1.2 * mm], [0.5 * mm, 0.4 * mm]
+    f = R.ElectricField(x, wavelengths=lams, spacing=sp, device=cpu)
+    out = {}
+    for name, el in {"lens": R.Thin_LensElement(focal_length=0.127), "circ": R.ApertureElement("circ", 6 * mm),
+                     "rect": R.ApertureElement("rect", 8 * mm)}.items():
+        el.device = cpu
+        if name == "lens":
+            el.focal_length = el.focal_length.cpu()
+        y = el(f).data
+        (gx,) = torch.autograd.grad(y, x, g)
+        out["y_" + name], out["gx_" + name] = y, gx
+    save("elem_lens_aperture", x=x, g=g, wavelengths=np.array(lams), spacing=np.array(sp), focal=np.float64(0.127),
+         radius=np.float64(6 * mm), side=np.float64(8 * mm), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = import_reference()
@@ -260,3 +281,4 @@ if __name__ == "__main__":
     gen_czt(R)
     gen_train(R)
     gen_rsc(R)
+    gen_elements(R)

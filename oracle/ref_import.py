@@ -65,6 +65,8 @@ def import_reference():
         import Components.quantization as QZ
         from Components.discrete_doe import DiscreteDOE
         import utils.Helper_Functions as HF
+        from Components.Thin_Lens import Thin_LensElement
+        from Components.Aperture import ApertureElement
     ns.ElectricField = ElectricField
     ns.ASM_prop = ASM_prop
     ns.CZT_prop = CZT_prop
@@ -74,6 +76,8 @@ def import_reference():
     ns.QZ = QZ
     ns.DiscreteDOE = DiscreteDOE
     ns.HF = HF
+    ns.Thin_LensElement = Thin_LensElement
+    ns.ApertureElement = ApertureElement
     return ns
 
 

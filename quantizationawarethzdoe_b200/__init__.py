@@ -17,6 +17,8 @@ from .Components.QuantizedDOE import (
 
 from .Props.CZT_Prop import CZT_prop
 from .Props.RSC_Prop import RSC_prop, VRS_prop
+from .Components.Thin_Lens import Thin_LensElement
+from .Components.Aperture import ApertureElement
 from .train import FusedAdam, normalized_intensity_mse
 
 __version__ = "0.1.0"

@@ -290,3 +290,38 @@ extern "C" int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise,
     THZ_CHECK_LAUNCH("thz_k_gumbel_naive_fwd");
     return THZ_OK;
 }
+
+// ------------------------------------------------------------------------------- pointwise optical elements
+// y[f, p] = x[f, p] * m[(f % C) * per_channel, p]  (m complex, optionally conjugated) or  * mask[p]  (real):
+// thin lens (Components/Thin_Lens.py:66-72) and aperture (Components/Aperture.py:126), forward and adjoint.
+__global__ void __launch_bounds__(256) thz_k_field_mul(const cpx* __restrict__ x, const void* __restrict__ m, cpx* __restrict__ y,
+                                                       int BC, int C, size_t HW, int per_channel, int m_real, int conj_m) {
+    const size_t total = (size_t)BC * HW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / HW, p = i - f * HW;
+        const size_t mi = (per_channel ? (f % C) * HW : 0) + p;
+        const cpx v = x[i];
+        if (m_real) {
+            y[i] = cscale(v, __ldg((const float*)m + mi));
+        } else {
+            const cpx w = __ldg((const cpx*)m + mi);
+            y[i] = conj_m ? cmulc(v, w) : cmul(v, w);
+        }
+    }
+}
+
+extern "C" int thz_field_mul(const void* x, const void* m, void* y, int32_t BC, int32_t C, uint64_t HW, int32_t per_channel,
+                             int32_t m_real, int32_t conj_m, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (BC < 0 || C < 1) return thz_set_error(THZ_E_SHAPE, "thz_field_mul: bad sizes");
+    if (BC == 0 || HW == 0) return THZ_OK;
+    if (!x || !m || !y) return thz_set_error(THZ_E_NULL, "thz_field_mul: null pointer");
+    const size_t total = (size_t)BC * HW, want = (total + 255) / 256, cap = (size_t)thz_sm_count() * 16;
+    thz_launch_begin(stream, THZ_KC_DOE);
+    thz_k_field_mul<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>((const cpx*)x, m, (cpx*)y, BC, C, (size_t)HW, per_channel,
+                                                                           m_real, conj_m);
+    thz_launch_end(stream, THZ_KC_DOE);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return thz_set_cuda_error("thz_field_mul", e);
+    return THZ_OK;
+}

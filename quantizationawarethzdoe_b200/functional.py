@@ -349,6 +349,36 @@ class GumbelNaiveFn(torch.autograd.Function):
         return g.unsqueeze(-1) * dq, None, None, None
 
 
+class FieldMulFn(torch.autograd.Function):
+    """y = x * m for a fixed pointwise element m (complex [C,H,W] per wavelength, or a real mask [H,W]); backward x conj(m)."""
+
+    @staticmethod
+    def forward(ctx, x, m):
+        x = _c64(x, "field.data")
+        N.require_cuda(m, "element")
+        real = not m.is_complex()
+        per_channel = m.dim() == 3
+        if (real and m.dtype != torch.float32) or (not real and m.dtype != torch.complex64) or not m.is_contiguous():
+            raise ValueError("pointwise element must be a contiguous float32 [H,W] mask or complex64 [C,H,W] kernel")
+        B, C, H, W = x.shape
+        if tuple(m.shape[-2:]) != (H, W) or (per_channel and m.shape[0] != C):
+            raise ValueError("pointwise element does not match the field")
+        ctx.m, ctx.real, ctx.per_channel = m, real, per_channel
+        return FieldMulFn._run(x, m, real, per_channel, 0)
+
+    @staticmethod
+    def _run(x, m, real, per_channel, conj):
+        B, C, H, W = x.shape
+        y = torch.empty_like(x)
+        N.check(N.lib().thz_field_mul(N.ptr(x), N.ptr(m), N.ptr(y), B * C, C, H * W, 1 if per_channel else 0, 1 if real else 0, conj,
+                                      N.current_stream_ptr(x.device)), "thz_field_mul")
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return FieldMulFn._run(_c64(g, "grad_output"), ctx.m, ctx.real, ctx.per_channel, 1), None
+
+
 def fft2_c2c(x, inverse=False, ortho=False):
     """Stand-alone natural-order batched 2-D FFT over the last two dims (thz_fft2_c2c)."""
     x = _c64(x, "input")

@@ -522,3 +522,21 @@ def test_rsc_large_vs_oracle(dev):
     prop.check_Zc = False
     y = prop(ElectricField(x.to(dev), wavelengths=lams, spacing=0.5 * mm, device=dev)).data
     assert rel_l2(y.cpu(), yo) < TOL
+
+
+def test_lens_and_apertures_match_reference(dev):
+    """Thin_LensElement / ApertureElement through thz_field_mul: outputs and input gradients vs the reference."""
+    from quantizationawarethzdoe_b200 import ApertureElement, ElectricField, Thin_LensElement
+    g = golden("elem_lens_aperture")
+    els = {"lens": Thin_LensElement(focal_length=g["focal"], device=dev), "circ": ApertureElement("circ", g["radius"], device=dev),
+           "rect": ApertureElement("rect", g["side"], device=dev)}
+    for name, el in els.items():
+        x = g["x"].to(dev).requires_grad_(True)
+        y = el(ElectricField(x, wavelengths=g["wavelengths"].float(), spacing=g["spacing"].float(), device=dev)).data
+        (gx,) = torch.autograd.grad(y, x, g["g"].to(dev))
+        tol = 2e-6 if name == "lens" else 0.0
+        assert rel_l2(y.detach().cpu(), g["y_" + name]) <= tol, name
+        assert rel_l2(gx.cpu(), g["gx_" + name]) <= tol, name
+    with pytest.raises(ValueError):
+        ApertureElement("circ", 1.0, device=dev)(ElectricField(g["x"].to(dev), wavelengths=g["wavelengths"].float(),
+                                                               spacing=g["spacing"].float(), device=dev))

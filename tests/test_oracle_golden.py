@@ -166,3 +166,14 @@ def test_rsc_oracle_matches_reference_vectors(name):
     if "gx" in g:
         (gx,) = torch.autograd.grad(y, x, g["g"])
         assert rel_l2(gx, g["gx"]) <= 2e-6
+
+
+def test_element_oracle_matches_reference_vectors():
+    """Thin lens kernel and aperture masks vs the reference's Thin_LensElement / ApertureElement outputs."""
+    from oracle import element_oracle as EO
+    g = golden("elem_lens_aperture")
+    x, sp = g["x"], g["spacing"].float()
+    H, W = x.shape[-2:]
+    assert rel_l2(x * EO.lens_kernel(H, W, sp, g["wavelengths"].float(), g["focal"]), g["y_lens"]) <= 1e-6
+    assert torch.equal(x * EO.circ_mask(H, W, sp, g["radius"]), g["y_circ"])
+    assert torch.equal(x * EO.rect_mask(H, W, sp, g["side"]), g["y_rect"])
