@@ -272,6 +272,33 @@ def gen_elements(R):
          radius=np.float64(6 * mm), side=np.float64(8 * mm), **out)
 
 
+def gen_setup(R):
+    """The notebooks' whole set-up (experiment_four_focal_spots.ipynb cells 2-8, `Submm_Setupv2` with the STE layer):
+    Gaussian beam -> ASM 127 mm -> thin lens -> rect aperture -> 4-level STE DOE -> ASM 200 mm -> normalize(|y|^2) -> MSE."""
+    cpu = torch.device("cpu")
+    n, dxy, lam = 100, 1 * mm, 2.998e8 / 300e9
+    src = R.Guassian_beam(height=n, width=n, beam_waist_x=None, beam_waist_y=None, wavelengths=lam, spacing=dxy, device=cpu)
+    asm1 = R.ASM_prop(z_distance=0.127, bandlimit_type="exact", padding_scale=2, bandlimit_kernel=True, device=cpu)
+    lens = R.Thin_LensElement(focal_length=0.127)
+    lens.device, lens.focal_length = cpu, lens.focal_length.cpu()
+    ap = R.ApertureElement(aperture_type="rect", aperture_size=0.08)
+    ap.device = cpu
+    torch.manual_seed(31)
+    doe = R.QD.STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=dxy, doe_level=4, look_up_table=None, num_unit=None,
+                                         height_constraint_max=1 * mm, tolerance=None, material=[2.66, 0.03]), {}, device=cpu)
+    asm3 = R.ASM_prop(z_distance=0.2, bandlimit_type="exact", padding_scale=2, bandlimit_kernel=True, device=cpu)
+    target = torch.rand(1, 1, n, n)
+    with quiet():
+        s0 = src()               # (the reference's source mutates its waists in forward: call it once)
+        source = s0.data.clone()
+        fin = ap(lens(asm1(s0)))
+        out = asm3(doe(fin, None))
+        loss = torch.nn.MSELoss()(R.HF.normalize(torch.abs(out.data) ** 2), target)
+        (gw,) = torch.autograd.grad(loss, doe.weight_height_map)
+    save("setup_four_focal_spots", source=source, field_before_doe=fin.data, w0=doe.weight_height_map.detach(), out=out.data, target=target,
+         loss=loss, gw=gw, height_map=doe.height_map.detach(), wavelength=np.float64(lam), spacing=np.float64(dxy))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = import_reference()
@@ -282,3 +309,4 @@ if __name__ == "__main__":
     gen_train(R)
     gen_rsc(R)
     gen_elements(R)
+    gen_setup(R)

@@ -67,6 +67,7 @@ def import_reference():
         import utils.Helper_Functions as HF
         from Components.Thin_Lens import Thin_LensElement
         from Components.Aperture import ApertureElement
+        from LightSource.Gaussian_beam import Guassian_beam
     ns.ElectricField = ElectricField
     ns.ASM_prop = ASM_prop
     ns.CZT_prop = CZT_prop
@@ -78,6 +79,7 @@ def import_reference():
     ns.HF = HF
     ns.Thin_LensElement = Thin_LensElement
     ns.ApertureElement = ApertureElement
+    ns.Guassian_beam = Guassian_beam
     return ns
 
 

@@ -19,6 +19,7 @@ from .Props.CZT_Prop import CZT_prop
 from .Props.RSC_Prop import RSC_prop, VRS_prop
 from .Components.Thin_Lens import Thin_LensElement
 from .Components.Aperture import ApertureElement
+from .LightSource.Gaussian_beam import Guassian_beam
 from .train import FusedAdam, normalized_intensity_mse
 
 __version__ = "0.1.0"
