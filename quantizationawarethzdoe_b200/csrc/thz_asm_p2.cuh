@@ -306,23 +306,26 @@ THZ_HD void p2k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int n
 // asynchronous variant of the load: T rows of field f -> padded line buffer `s` (8-byte cp.async: the padded
 // slots of odd 16-groups are only 8-byte aligned)
 template <int N>
-THZ_HD void p2k3_prefetch(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nt) {
+// (part, nparts): the copies are issued in nparts interleaved portions, between the stages of the current line, so that
+// they do not arrive at the LSU queue in one burst
+THZ_HD void p2k3_prefetch(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nt, int part = 0, int nparts = 1) {
     constexpr int LINES = p2_row_lines(N), PITCH = p2_pitch(N);
+    const int p_lo = tid + part * nt, p_step = nparts * nt;
 #pragma unroll
     for (int l = 0; l < LINES; ++l) {
         const int r = bx * LINES + l;
         if (r >= a.outH) break;
         cpx* sl = s + l * PITCH;
         if (a.slab.parts > 1) {
-            for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), thz_slab_addr(a.slab, f, r, p));
+            for (int p = p_lo; p < N; p += p_step) thz_cp_async8(sl + p + (p >> 4), thz_slab_addr(a.slab, f, r, p));
             continue;
         }
         if (a.t_tiled) {
-            for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), a.T + thz_t_tiled_index(f, r, p, a.rowsT, N, a.t_tiled));
+            for (int p = p_lo; p < N; p += p_step) thz_cp_async8(sl + p + (p >> 4), a.T + thz_t_tiled_index(f, r, p, a.rowsT, N, a.t_tiled));
             continue;
         }
         const cpx* tr = a.T + ((size_t)f * a.rowsT + r) * N;
-        for (int p = tid; p < N; p += nt) thz_cp_async8(sl + p + (p >> 4), tr + p);
+        for (int p = p_lo; p < N; p += p_step) thz_cp_async8(sl + p + (p >> 4), tr + p);
     }
 }
 
