@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
         thz_cp_async_wait_all();
         __syncthreads();                      // rows of field f have landed; the other buffer is free (its epilogue ran)
         if (f + 1 < f_hi) p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, tid, nt, 0, 2);
+#ifndef THZ_NO_EPI_PREFETCH
         p2k3_prefetch_epilogue<N>(a, bx, f, tid, nt);
+#endif
         inv_rows<N, p2_stages(N) - 1, p2_stages(N) - 1, LINES>(sc, tid, nt, tws);
         if (f + 1 < f_hi) p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, tid, nt, 1, 2);
         thz_cp_async_commit();
