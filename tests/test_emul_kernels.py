@@ -215,3 +215,36 @@ def test_slab_descriptor_is_validated():
                 dict(stages=1, slab=(2, 0, 128, [slab.data_ptr(), 0]))):
         d = AH.build_desc(**dict(dict(kw, stages=1, slab=(2, 64, 128, [slab.data_ptr(), slab.data_ptr()])), **bad))
         assert E.thz_emul_asm_propagate(ctypes.byref(d), 148) in (-1, -2), bad
+
+
+@pytest.mark.parametrize("env", [dict(THZ_NO_TILED="1"), dict(THZ_NO_PRUNE="1"), dict(THZ_T1_LOG2="3"), dict(THZ_T1_LOG2="2", THZ_T2_LOG2="3"),
+                                 dict(THZ_T2_LOG2="2"), dict(THZ_NO_P2="1")], ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+def test_layout_and_pruning_switches_do_not_change_the_result(env, monkeypatch):
+    """The A/B switches of DESIGN 3.5 (row-major / blocked intermediates of either width, full instead of pruned stages,
+    runtime-planned engine) select different code for the same arithmetic: forward and DOE adjoint must agree with the default
+    path to round-off."""
+    B, C, H, W = 2, 2, 128, 256                      # 256 x 512 padded: static kernels, centred 2x padding (pruned stages)
+    lams, dxy, z = [1e-3, 1.03e-3], 0.5e-3, 0.1
+    torch.manual_seed(3)
+    x = torch.randn(B, C, H, W, dtype=torch.complex64)
+    g = torch.randn(B, C, H, W, dtype=torch.complex64)
+    h = torch.rand(H, W) * 1e-3
+    coef = AH.doe_coefficients(lams, 2.66, 0.003)
+
+    def run():
+        base, _ = _setup(B, C, H, W, None, lams, dxy, z, mode=1)
+        y = torch.zeros_like(x)
+        _run(x, dict(base, x=x, y=y, doe_mode=1, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef))
+        gx, gh = torch.zeros_like(x), torch.zeros(H, W)
+        adj = dict(base, x=g, y=gx, tf_conj=1, doe_mode=2, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef, xsaved=x, gh=gh,
+                   inH=base["outH"], inW=base["outW"], in_r0=base["out_r0"], in_c0=base["out_c0"],
+                   outH=base["inH"], outW=base["inW"], out_r0=base["in_r0"], out_c0=base["in_c0"])
+        _run(g, adj)
+        return y, gx, gh
+
+    ref = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    for a, b in zip(got, ref):
+        assert rel_l2(a, b) < 2e-6
