@@ -67,6 +67,7 @@ class AsmPlan:
         self.row_chunked = 1 if (row_chunked and tf_mode == 0) else 0   # layout of rowvec, see thz_asm_desc.tf_row_chunked
         self.tw_h = N.twiddles(Hp, device)
         self.tw_w = N.twiddles(Wp, device)
+        self._descs = {}
 
     def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None):
         """One thz_asm_propagate call.  Forward: x [B,C,H,W] -> y [B,C,outH,outW].
@@ -78,13 +79,21 @@ class AsmPlan:
         else:
             inH, inW, in_r0, in_c0 = self.outH, self.outW, self.out_r0, self.out_c0
             outH, outW, out_r0, out_c0 = self.H, self.W, self.pad_h, self.pad_w
-        nbc = x.shape[0] * x.shape[1]
-        ws = _workspace(AH.workspace_elems(x.shape[0], C, inH, outH, self.Wp, TUNE["bc_chunk"], Hp=self.Hp), x.device)
-        d = AH.build_desc(x, y, x.shape[0], C, inH, inW, self.Hp, self.Wp, in_r0, in_c0, outH, outW, out_r0, out_c0,
-                          self.tf_mode, 1 if conj else 0, self.rowvec, self.colvec, self.scal, self.table,
-                          doe_mode, BASE_PLANE_THICKNESS, hmap, coef, xsaved, gh, self.tw_h, self.tw_w, ws,
-                          bc_chunk=TUNE["bc_chunk"], tune_k2_cols=TUNE["k2_cols"], tune_lines=TUNE["lines"],
-                          tf_row_chunked=self.row_chunked)
+        # the descriptor of a (batch, direction, DOE mode) triple is built once; per call only the pointers change
+        key = (x.shape[0], bool(conj), doe_mode, TUNE["bc_chunk"], TUNE["k2_cols"], TUNE["lines"])
+        ent = self._descs.get(key)
+        if ent is None:
+            elems = AH.workspace_elems(x.shape[0], C, inH, outH, self.Wp, TUNE["bc_chunk"], Hp=self.Hp)
+            d = AH.build_desc(None, None, x.shape[0], C, inH, inW, self.Hp, self.Wp, in_r0, in_c0, outH, outW, out_r0, out_c0,
+                              self.tf_mode, 1 if conj else 0, self.rowvec, self.colvec, self.scal, self.table,
+                              doe_mode, BASE_PLANE_THICKNESS, None, None, None, None, self.tw_h, self.tw_w, None,
+                              bc_chunk=TUNE["bc_chunk"], tune_k2_cols=TUNE["k2_cols"], tune_lines=TUNE["lines"],
+                              tf_row_chunked=self.row_chunked)
+            ent = self._descs[key] = (d, elems)
+        d, elems = ent
+        ws = _workspace(elems, x.device)
+        d.x, d.y, d.ws, d.ws_bytes = N.ptr(x), N.ptr(y), N.ptr(ws), ws.numel() * 8
+        d.doe_hmap, d.doe_coef, d.doe_xsaved, d.doe_gh = N.ptr(hmap), N.ptr(coef), N.ptr(xsaved), N.ptr(gh)
         _asm_call(d, x.device)
         return y
 

@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
 python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/config_bench.py c2 iteration zsweep 2>&1 | grep "^{" | cut -c1-330
