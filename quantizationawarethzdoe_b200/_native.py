@@ -150,7 +150,13 @@ def require_cuda(t, name="tensor"):
         raise ThzError("%s must live on a CUDA device (got %s); this package has no CPU path" % (name, t.device))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def current_stream_ptr(device):
+    """torch's current CUDA stream on `device` as a cudaStream_t (the raw-handle query: this runs before every launch)."""
+    if _raw_stream is not None and device.index is not None:
+        return ctypes.c_void_p(_raw_stream(device.index))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
