@@ -1,6 +1,13 @@
-// Power-of-two fast path of the fused ASM pipeline: the same three kernels as thz_asm.cuh (same
-// argument structs, same T layout, same results), with the transform length a template parameter and
-// the first / last FFT stage of each kernel fused with its global-memory traffic:
+// Static ("p2": historically power-of-two) fast path of the fused ASM pipeline: the same three kernels as thz_asm.cuh
+// (same argument structs, same results), with the transform length a template parameter and the first / last FFT
+// stage of each kernel fused with its global-memory traffic.  On top of that, where it applies:
+//   * the K1 -> K2 intermediate is stored in 4-column blocks and the K2 -> K3 one row-major in a second buffer
+//     (thz_t_tiled_index in thz_asm.cuh: the column kernel's loads then touch 4 instead of 16 cache lines per warp);
+//   * for centred 2x padding the first forward / last inverse radix-16 stage is pruned (half_in / half_out);
+//   * stage twiddles come from a padded shared-memory copy, and a thread's butterflies share one power tree when they
+//     can (p2_stage_cols); the row vectors of the transfer function are read in a warp-contiguous "chunked" layout;
+//   * the row kernels are software-pipelined with cp.async (K1 persistent; K3 double-buffered, copies issued in portions);
+//   * multi-GPU slab FFT: K1 can scatter its rows into, and K3 gather them from, column slabs in peer memory (SlabArgs).
 //
 //   K1<N>       x row --[DOE phase]--> registers -> stage 0 -> smem -> stages 1.. -> smem -> T row
 //   K2<N,COLS>  T column tile -> registers -> stage 0 -> smem -> ... -> (last stage . H . last stage^-1)
@@ -13,8 +20,8 @@
 #include "thz_asm.cuh"
 #include "thz_fft_p2.cuh"
 
-// lengths with a compiled static path: powers of two 256 .. 16384 and the multiples of 16 of the form 25*16*2^a / 25*20*4*2^a
-// that the BASELINE configs and the reference notebooks produce (200 -> 400, 1000 -> 2000, ...)
+// lengths with a compiled static path: powers of two 256 .. 16384, the multiples of 16 of the form 25*16*2^a / 25*20*4*2^a
+// that the BASELINE configs and the reference notebooks produce (200 -> 400, 1000 -> 2000, ...), and 3 * 2^a (padding_scale 2)
 #define THZ_SP_SIZES(X) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384) X(400) X(800) X(1600) X(2000) X(3200) X(4000) X(768) X(1536) X(3072) X(6144)
 THZ_HD constexpr bool thz_sp_instantiated(int n) {
 #define THZ_SP_CMP(NN) if (n == NN) return true;
