@@ -186,8 +186,11 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
             if (f_lo < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s, bx, f_lo, t, nt); });
             for (int f = f_lo; f < f_hi; ++f, cur ^= 1) {
                 cpx* sc = s + cur * BUF;
-                if (f + 1 < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, t, nt); });
-                e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(sc, nt, tws.data());
+                // as in thz_p2_k3: the next line is fetched in two portions, around the first in-smem stage
+                if (f + 1 < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, t, nt, 0, 2); });
+                e_inv_rows<N, p2_stages(N) - 1, p2_stages(N) - 1, LINES>(sc, nt, tws.data());
+                if (f + 1 < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, t, nt, 1, 2); });
+                e_inv_rows<N, p2_stages(N) - 2, 1, LINES>(sc, nt, tws.data());
                 for_threads(nt, [&](int t) { p2k3_last<N, NACC>(a, sc, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
             }
             for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
