@@ -207,6 +207,31 @@ int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise, const void
                                void* idx, void* dq, uint64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Thickness-space softmax quantization: SoftmaxBasedQuantization.forward + score_thickness
+ * (Components/quantization.py:128-161 and :36-55), reached through Quantization(method='*softmax*' | '*gumbel*') (:164-207).
+ *
+ * thz_quant_softmax_fwd: thickness float32 [n] (one map: the reference normalises by the maximum of |thickness - lut_j| over
+ *   the WHOLE tensor, :41), lut float32 [L] (the caller passes lut[:-1] like :182), noise float32 [L, n] = the Gumbel noise
+ *   F.gumbel_softmax would draw, or NULL for the plain-softmax branch (:146-152); c, tau, s = tau_max / tau; hard as :134.
+ *   Writes q float32 [n], idx int32 [n] (argmax level; optional) and, when dq_dt != NULL, the three per-pixel factors of the
+ *   backward (dq_dt, dq_dm, tie_sign: float32 [n] each).  stats: device float32 [4] scratch that links forward and backward
+ *   ({max |diff|, number of ties attaining it, sum g dq/dm, unused}).
+ * thz_quant_softmax_bwd: gt = g dq_dt + (sum g dq_dm) / ties * tie_sign -- autograd through the out-of-place form
+ *   diff / max|diff| (torch.max splits its gradient evenly over ties).  The reference's own backward raises (its in-place
+ *   `diff /= max`, :41, invalidates what abs() saved), so this gradient is pinned by the oracle restatement, the forward by
+ *   the reference.
+ * thz_score_thickness: the scoring function alone, scores float32 [batch, L, n_per_b] from thickness [batch, 1, n_per_b];
+ *   func 0 sigmoid, 1 log, 2 poly, 3 sine, 4 chirp (:43-53).
+ * ------------------------------------------------------------------------------------------- */
+int thz_quant_softmax_fwd(const void* thickness, const void* lut, int32_t L, const void* noise, float c, float tau, float s,
+                          int32_t hard, void* q, void* idx, void* dq_dt, void* dq_dm, void* tie_sign, void* stats, uint64_t n,
+                          void* stream);
+int thz_quant_softmax_bwd(const void* g, const void* dq_dt, const void* dq_dm, const void* tie_sign, void* stats, void* gt,
+                          uint64_t n, void* stream);
+int thz_score_thickness(const void* thickness, const void* lut, int32_t L, float s, int32_t func, void* scores, void* stats,
+                        int32_t batch, uint64_t n_per_b, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Launch accounting (used by bench.py).  thz_launch_count: kernels launched by this library in this
  * process so far.  thz_profile_enable(1) makes every launch record a CUDA event pair on its stream
  * (small overhead, off by default); thz_profile_read sums elapsed milliseconds and launches per
@@ -214,6 +239,10 @@ int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise, const void
  * modulation, 5 quantizers, 6 CZT) after synchronising the recorded events; enable(0) clears them.
  * ------------------------------------------------------------------------------------------- */
 uint64_t thz_launch_count(void);
+/* launches of one kernel class so far: 0 row FFT, 1 column pass, 2 row iFFT, 3 fft2 column pass, 4 DOE modulation / field
+ * multiply, 5 quantizers, 6 CUDA-core Toeplitz GEMM, 7 loss / optimizer, 8 tcgen05 Toeplitz GEMM (+ its prologue
+ * multiply), 9 small-grid single-kernel ASM. */
+uint64_t thz_launch_count_class(int32_t kernel_class);
 int thz_profile_enable(int32_t on);
 int thz_profile_read(int32_t nclasses, float* ms_sum, int32_t* count);
 
@@ -236,7 +265,10 @@ typedef struct thz_toeplitz_gemm_desc {
     int32_t batch, M, N, K;
     const void* g;             /* complex64 [batch, L] chirp filter (1/h zero-extended to np2, CZT_Prop.py:161) */
     int32_t L, off, sm, sk;    /* Toeplitz index = (off + sm*m + sk*k) mod L, sm, sk in {+1, -1}              */
-    int32_t conj_g, conj_pro, conj_epi, reserved;
+    int32_t conj_g, conj_pro, conj_epi;
+    int32_t impl;              /* 0 auto (tcgen05 kernel if eligible, else CUDA cores + one stderr warning); 1 tcgen05 or
+                                  THZ_E_UNSUPPORTED; 2 CUDA-core kernel.  Eligible: sm == -sk, L >= 64, and, with `pro`, a dense
+                                  B and a `scratch` buffer.  thz_launch_count_class(8 / 6) counts the two kinds of launch */
     const void* B;
     int64_t sb_b, sb_k, sb_n;
     const void* pro;

@@ -180,6 +180,70 @@ def gen_quant(R):
          idx=torch.argmin(torch.abs(hh.unsqueeze(-1) - l8), dim=-1))
 
 
+def gen_quant_softmax(R):
+    """SoftmaxBasedQuantization + score_thickness through the reference's own Quantization dispatch
+    (Components/quantization.py:36-55, 128-161, 164-207): '*softmax*' with and without Gumbel noise, hard and soft."""
+    H, W, bits = 48, 40, 2
+    hmax = 1 * mm
+    torch.manual_seed(41)
+    t0 = torch.rand(1, 1, H, W) * 1.2 * hmax - 0.1 * hmax
+    gq = torch.randn(H, W)
+    cases = {"gumbel_hard": ("gumbel_softmax", 0.5, True, 201), "gumbel_soft": ("gumbel_softmax", 0.2, False, 202),
+             "plain_hard": ("softmax", 0.3, True, None), "plain_soft": ("softmax", 0.8, False, None)}
+    # NOTE: the reference's own backward through score_thickness raises ("modified by an inplace operation": `diff /=
+    # torch.max(torch.abs(diff))`, quantization.py:41, invalidates what abs() saved), so the reference pins only the
+    # FORWARD values here; the gradients stored next to them come from the oracle's out-of-place restatement
+    # (doe_oracle.softmax_quantize), i.e. autograd through diff / max|diff| including the path through the max.
+    from oracle import doe_oracle as DO
+    lut_full = torch.linspace(0, hmax, 2 ** bits + 1)
+    out = {}
+    for name, (method, frac, hard, seed) in cases.items():
+        qz = R.QZ.Quantization(method=method, max_thickness=hmax, num_bits=bits, dev=torch.device("cpu"), tau_min=0.5, tau_max=3.0, c=300.)
+        noise = None
+        if seed is not None:
+            torch.manual_seed(seed)
+            noise = -torch.empty(1, 2 ** bits, H, W).exponential_().log()   # what F.gumbel_softmax draws under this seed
+            torch.manual_seed(seed)
+            out["noise_" + name] = noise
+        with torch.no_grad():
+            q = qz(t0.clone(), iter_frac=frac, hard=hard)
+        try:
+            qz(t0.clone().requires_grad_(True), iter_frac=frac, hard=hard).sum().backward()
+            raise SystemExit("the reference's backward unexpectedly works: regenerate the gradients from it")
+        except RuntimeError as e:
+            assert "inplace" in str(e)
+        tau = R.QZ.tau_iter(method, frac, 0.5, 3.0, None)
+        t = t0.clone().requires_grad_(True)
+        qo = DO.softmax_quantize(t, lut_full[:-1], torch.tensor(tau, dtype=torch.float32), 3.0, 300., gumbel_noise=noise, hard=hard).squeeze(0, 1)
+        assert torch.equal(qo.detach(), q), name            # the restatement reproduces the reference forward bit for bit
+        (gt,) = torch.autograd.grad(qo, t, gq)
+        # the same restatement in float64: how far fp32 itself is from the exact gradient (the soft branches at small tau are
+        # ill-conditioned -- logits of O(1000) -- and the tests budget the GPU's distance with this number)
+        t64 = t0.double().requires_grad_(True)
+        q64 = DO.softmax_quantize(t64, lut_full[:-1].double(), float(np.float32(tau)), 3.0, 300.,
+                                  gumbel_noise=None if noise is None else noise.double(), hard=hard).squeeze(0, 1)
+        (gt64,) = torch.autograd.grad(q64, t64, gq.double())
+        out["gt64_" + name] = gt64
+        out["q_" + name], out["gt_" + name] = q, gt
+        out["tau_" + name] = np.float64(tau)
+        out["frac_" + name] = np.float64(frac)
+    # a map with many equal values: the global max |diff| of score_thickness has ties, autograd splits its gradient evenly
+    tt = torch.zeros(1, 1, 8, 8)
+    tt[0, 0, 2:5, 3:6] = 0.4 * hmax
+    qz = R.QZ.Quantization(method="softmax", max_thickness=hmax, num_bits=bits, dev=torch.device("cpu"), tau_min=0.5, tau_max=3.0, c=300.)
+    gq2 = torch.randn(8, 8)
+    with torch.no_grad():
+        q2 = qz(tt.clone(), iter_frac=0.6, hard=True)
+    tau2 = R.QZ.tau_iter("softmax", 0.6, 0.5, 3.0, None)
+    tg = tt.clone().requires_grad_(True)
+    qo2 = DO.softmax_quantize(tg, lut_full[:-1], torch.tensor(tau2, dtype=torch.float32), 3.0, 300., hard=True).squeeze(0, 1)
+    assert torch.equal(qo2.detach(), q2)
+    (gt2,) = torch.autograd.grad(qo2, tg, gq2)
+    save("quant_softmax", thickness=t0, gq=gq, lut=lut_full, hmax=np.float64(hmax), tau_max=np.float64(3.0),
+         tau_min=np.float64(0.5), c=np.float64(300.), ties_t=tt, ties_gq=gq2, ties_q=q2, ties_gt=gt2,
+         ties_tau=np.float64(tau2), **out)
+
+
 def gen_czt(R):
     cases = {
         "czt_small": (64, 64, 32, [1 * mm, 1.1 * mm], 0.5 * mm, 0.1 * mm, 0.5),
@@ -305,6 +369,7 @@ if __name__ == "__main__":
     gen_asm(R)
     gen_doe(R)
     gen_quant(R)
+    gen_quant_softmax(R)
     gen_czt(R)
     gen_train(R)
     gen_rsc(R)

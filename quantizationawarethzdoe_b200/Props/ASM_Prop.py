@@ -9,7 +9,11 @@ generated in registers, the crop, and (when the incoming field carries a deferre
 the DOE phase multiply and its adjoint, all without cuFFT / torch.fft.
 
 `kernel_mode`:
-  'inregister' (default) H is generated inside the column kernel from O(Hp+Wp) host-built vectors;
+  'auto' (default)       'inregister' when that stays within half of the 1e-5 parity budget for this geometry
+                         (asm_host.inregister_deviation_estimate, evaluated once per plan: it does at the benchmark
+                         physics, k z ~ 630 rad; it does not beyond z ~ 0.15 m at 1 mm wavelength), else 'cached'.
+                         `resolved_kernel_mode` / `inregister_estimate` say what was picked and why.
+  'inregister'           H is generated inside the column kernel from O(Hp+Wp) host-built vectors;
                          the band-limit mask is bit-identical to the reference, the phase differs from
                          the reference's only where torch's CPU sqrt is not correctly rounded.
   'cached'               H is built once per (shape, spacing, wavelengths, z) on the host with the
@@ -34,7 +38,7 @@ class ASM_prop(nn.Module):
                  bandlimit_kernel=True,
                  bandlimit_type='exact',
                  device=None,
-                 kernel_mode='inregister'):
+                 kernel_mode='auto'):
         super().__init__()
         padding_scale = AH.normalise_padding_scale(padding_scale, do_padding)   # raises like ASM_Prop.py:96
         self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
@@ -44,9 +48,11 @@ class ASM_prop(nn.Module):
         self.padding_scale = padding_scale
         self.bandlimit_kernel = bandlimit_kernel
         self.bandlimit_type = bandlimit_type
-        if kernel_mode not in ('inregister', 'cached'):
-            raise ValueError("kernel_mode must be 'inregister' or 'cached'")
+        if kernel_mode not in ('auto', 'inregister', 'cached'):
+            raise ValueError("kernel_mode must be 'auto', 'inregister' or 'cached'")
         self.kernel_mode = kernel_mode
+        self.resolved_kernel_mode = None if kernel_mode == 'auto' else kernel_mode
+        self.inregister_estimate = None
         self._shape = None
         self.Kx = None
         self.Ky = None
@@ -159,10 +165,16 @@ class ASM_prop(nn.Module):
             rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
             table, mode = None, 0
             chunked = AH.row_vectors_chunked(Hp)
-            dv = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked) if self.kernel_mode == 'inregister' else None
+            mode_ = self.kernel_mode
+            if mode_ == 'auto':
+                self.inregister_estimate = AH.inregister_deviation_estimate(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel,
+                                                                            self.bandlimit_type)
+                mode_ = 'inregister' if self.inregister_estimate <= AH.INREGISTER_BUDGET else 'cached'
+            dv = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked) if mode_ == 'inregister' else None
             if dv is not None:
                 rowvec, colvec, scal = dv
-            if self.kernel_mode == 'cached' or dv is None:
+            self.resolved_kernel_mode = 'inregister' if dv is not None else 'cached'
+            if mode_ == 'cached' or dv is None:
                 Hc = AH.tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
                 table, mode = AH.tf_table_slot_order(Hc), 1
             unpad = bool(self.do_padding and self.do_unpad_after_pad)

@@ -35,7 +35,19 @@ class CZT_prop(nn.Module):
             z = z.to(self.device)
         self._z = z
 
-    def _get_plan(self, field, out_h, out_w, out_dx, out_dy, device):
+    @staticmethod
+    def _tok(v):
+        """Identity token of a plan input: tensors by (object, in-place version) -- no device->host read --, scalars by value."""
+        return (id(v), v._version) if isinstance(v, torch.Tensor) else float(v)
+
+    def _get_plan(self, field, out_h, out_w, out_dx, out_dy, device, dx_tok=None, dy_tok=None):
+        # fast path (as in ASM_prop): the same tensor objects, unchanged in place, as last time -> the same plan, and no
+        # device->host reads of wavelengths / spacing / z on the hot path
+        fast = (self._tok(field.wavelengths), self._tok(field.spacing), self._tok(self._z), field.height, field.width,
+                int(out_h), int(out_w), dx_tok if dx_tok is not None else self._tok(out_dx),
+                dy_tok if dy_tok is not None else self._tok(out_dy), str(device))
+        if self._plan is not None and getattr(self, "_fast_key", None) == fast:
+            return self._plan
         z = self._z.detach().cpu() if isinstance(self._z, torch.Tensor) else torch.tensor(float(self._z))
         key = (tuple(field.wavelengths.detach().cpu().reshape(-1).tolist()), tuple(field.spacing.detach().cpu().reshape(-1).tolist()),
                float(z), field.height, field.width, int(out_h), int(out_w), float(out_dx), float(out_dy), str(device))
@@ -44,10 +56,15 @@ class CZT_prop(nn.Module):
                             torch.as_tensor(out_dx).detach().cpu(), torch.as_tensor(out_dy).detach().cpu())
             self._plan = Fn.CztDevicePlan(hp, device)
             self._plan_key = key
+        self._fast_key = fast
+        self._fast_refs = (field.wavelengths, field.spacing, self._z, out_dx, out_dy)   # keep the keyed objects alive: ids stay unique
         return self._plan
 
     def forward(self, field, outputHeight=None, outputWidth=None, outputPixel_dx=None, outputPixel_dy=None):
         in_dx, in_dy = field.spacing[0], field.spacing[1]
+        # default output pitch = input pitch: keyed by the spacing tensor itself (field.spacing[0] is a new view every call)
+        dx_tok = ("in", self._tok(field.spacing)) if outputPixel_dx is None else self._tok(outputPixel_dx)
+        dy_tok = ("in", self._tok(field.spacing)) if outputPixel_dy is None else self._tok(outputPixel_dy)
         if outputHeight is None:
             outputHeight = field.height
         if outputPixel_dx is None:
@@ -57,10 +74,14 @@ class CZT_prop(nn.Module):
         if outputPixel_dy is None:
             outputPixel_dy = in_dy
         data = field.data
-        plan = self._get_plan(field, outputHeight, outputWidth, outputPixel_dx, outputPixel_dy, data.device)
+        plan = self._get_plan(field, outputHeight, outputWidth, outputPixel_dx, outputPixel_dy, data.device, dx_tok, dy_tok)
         out = Fn.CztFn.apply(data, plan)
-        return ElectricField(data=out, wavelengths=field.wavelengths, spacing=[float(outputPixel_dx), float(outputPixel_dy)],
-                             device=data.device)
+        sp_key = (dx_tok, dy_tok, str(data.device))
+        if getattr(self, "_out_spacing_key", None) != sp_key:       # [dx_out, dy_out] (CZT_Prop.py:308-312), built once per geometry
+            self._out_spacing = torch.tensor([float(outputPixel_dx), float(outputPixel_dy)], dtype=torch.float32, device=data.device)
+            self._out_spacing_key = sp_key
+            self._out_spacing_refs = (outputPixel_dx, outputPixel_dy)
+        return ElectricField(data=out, wavelengths=field.wavelengths, spacing=self._out_spacing, device=data.device)
 
 
 class VCZT_prop(CZT_prop):

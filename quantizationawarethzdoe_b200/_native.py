@@ -56,7 +56,7 @@ class ToeplitzGemmDesc(ctypes.Structure):
         ("batch", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
         ("g", ctypes.c_void_p),
         ("L", ctypes.c_int32), ("off", ctypes.c_int32), ("sm", ctypes.c_int32), ("sk", ctypes.c_int32),
-        ("conj_g", ctypes.c_int32), ("conj_pro", ctypes.c_int32), ("conj_epi", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("conj_g", ctypes.c_int32), ("conj_pro", ctypes.c_int32), ("conj_epi", ctypes.c_int32), ("impl", ctypes.c_int32),
         ("B", ctypes.c_void_p),
         ("sb_b", ctypes.c_int64), ("sb_k", ctypes.c_int64), ("sb_n", ctypes.c_int64),
         ("pro", ctypes.c_void_p),
@@ -95,11 +95,16 @@ def _declare(l):
     l.thz_quant_gumbel_v3_fwd.argtypes = [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp, u64, vp]
     l.thz_quant_gumbel_naive_fwd.argtypes = [vp, vp, vp, i32, f32, vp, vp, vp, u64, vp]
     l.thz_toeplitz_gemm.argtypes = [ctypes.POINTER(ToeplitzGemmDesc), vp]
+    l.thz_quant_softmax_fwd.argtypes = [vp, vp, i32, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, u64, vp]
+    l.thz_quant_softmax_bwd.argtypes = [vp, vp, vp, vp, vp, vp, u64, vp]
+    l.thz_score_thickness.argtypes = [vp, vp, i32, f32, i32, vp, vp, i32, u64, vp]
     l.thz_tf_row_thresholds.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.thz_field_mul.argtypes = [vp, vp, vp, i32, i32, u64, i32, i32, i32, vp]
     l.thz_normmse_loss.argtypes = [vp, vp, i32, u64, vp, vp, vp, vp]
     l.thz_adam_step.argtypes = [vp, vp, vp, vp, vp, u64, f32, f32, f32, f32, f32, i32, i32, vp]
     l.thz_launch_count.restype = u64
+    l.thz_launch_count_class.restype = u64
+    l.thz_launch_count_class.argtypes = [i32]
     l.thz_profile_enable.argtypes = [i32]
     l.thz_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     for name in EXPORTS:
@@ -114,8 +119,9 @@ EXPORTS = [
     "thz_doe_modulate_fwd", "thz_doe_modulate_bwd", "thz_height_fwd", "thz_height_bwd",
     "thz_quant_ste_fwd", "thz_quant_nn_fwd", "thz_quant_nn_bwd", "thz_quant_psq_fwd",
     "thz_quant_gumbel_v3_fwd", "thz_quant_gumbel_naive_fwd",
-    "thz_launch_count", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm", "thz_tf_row_thresholds",
+    "thz_launch_count", "thz_launch_count_class", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm", "thz_tf_row_thresholds",
     "thz_normmse_loss", "thz_adam_step", "thz_fft_is_static", "thz_field_mul",
+    "thz_quant_softmax_fwd", "thz_quant_softmax_bwd", "thz_score_thickness",
 ]
 
 

@@ -236,6 +236,34 @@ def tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, bandlimit=True, 
     return out
 
 
+INREGISTER_BUDGET = 5e-6     # kernel_mode='auto' generates H in registers only if the estimate below stays under this
+
+
+def inregister_deviation_estimate(Hp, Wp, spacing, wavelengths, z, bandlimit=True, bandlimit_type="exact", max_rows=64):
+    """rel-L2 distance between the reference's transfer function and the one the column kernel generates in registers,
+    estimated on `max_rows` evenly spaced rows of the centred grid.
+
+    The mask is bit-identical by construction; the phase z*sqrt(klam^2 - K^2) is not: torch's CPU sqrt (MKL VML, what the
+    reference runs: Props/ASM_Prop.py:257) is off by one ulp from the correctly rounded value on ~0.7 % of the elements,
+    and the GPU (like numpy) rounds correctly.  One ulp of sqrt(d) ~ k is 2^-11 .. 2^-10 at THz wavelengths, times z:
+    3e-6 at z = 0.1 m, 1.5e-5 at z = 0.3 m.  Both square roots are evaluated here with the libraries in question, so the
+    estimate needs no model of either."""
+    rowvec, colvec, scal = tf_vectors(Hp, Wp, spacing, wavelengths, z, bandlimit, bandlimit_type)
+    ridx = torch.unique(torch.linspace(0, Hp - 1, min(Hp, max_rows)).round().long())
+    rv, cv = rowvec[:, ridx], colvec
+    K2 = rv[:, :, None, 0] + cv[:, None, :, 0]
+    d = scal[:, 0, None, None] - K2
+    keep = ((rv[:, :, None, 1] + cv[:, None, :, 1]) <= 1) & ((rv[:, :, None, 2] + cv[:, None, :, 2]) <= 1) & ~(d < 0)
+    if not bool(keep.any()):
+        return 0.0
+    zc = scal[:, 1, None, None]
+    ang_ref = zc * torch.sqrt(d)                                              # the reference's library
+    with np.errstate(invalid="ignore"):
+        ang_gpu = zc * torch.from_numpy(np.sqrt(d.numpy()))                    # IEEE-correct, as sqrt.rn on the GPU
+    delta = (ang_ref - ang_gpu)[keep].double()
+    return float(torch.sqrt(torch.mean(delta * delta)))
+
+
 def tf_table_slot_order(Hc, slot_to_bin_fn=None):
     """Centred kernel [C,Hp,Wp] -> table[c][slot_r][slot_c] = ifftshift(Hc)[c][bin(slot_r)][bin(slot_c)]."""
     Hn = torch.fft.ifftshift(Hc, dim=(-2, -1))

@@ -29,7 +29,22 @@ int thz_sm_count(void) {
     return n;
 }
 
-extern "C" int thz_version(void) { return 100; /* 0.1.0 */ }
+ThzDeviceGuard::ThzDeviceGuard(const void* p) : prev(-1), switched(false) {
+    if (!p) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return;
+    if (cudaGetDevice(&prev) != cudaSuccess || prev == at.device) return;
+    if (cudaSetDevice(at.device) == cudaSuccess) switched = true;
+}
+ThzDeviceGuard::~ThzDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+}
+
+extern "C" int thz_version(void) { return 200; /* 0.2.0 */ }
 
 extern "C" const char* thz_last_error(void) { return g_last_error; }
 
@@ -70,13 +85,15 @@ struct ProfRec {
     int cls;
 };
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_launches_cls[THZ_KC_COUNT];
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static thread_local cudaEvent_t g_open_event = nullptr;
 
-void thz_launch_begin(cudaStream_t stream, int) {
+void thz_launch_begin(cudaStream_t stream, int kernel_class) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (kernel_class >= 0 && kernel_class < THZ_KC_COUNT) g_launches_cls[kernel_class].fetch_add(1, std::memory_order_relaxed);
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
     cudaEvent_t a;
     if (cudaEventCreate(&a) != cudaSuccess) return;
@@ -100,6 +117,9 @@ void thz_launch_end(cudaStream_t stream, int kernel_class) {
 }
 
 extern "C" uint64_t thz_launch_count(void) { return g_launches.load(); }
+extern "C" uint64_t thz_launch_count_class(int32_t kernel_class) {
+    return (kernel_class >= 0 && kernel_class < THZ_KC_COUNT) ? g_launches_cls[kernel_class].load() : 0;
+}
 
 extern "C" int thz_profile_enable(int32_t on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

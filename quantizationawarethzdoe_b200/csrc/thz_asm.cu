@@ -113,6 +113,7 @@ extern "C" uint64_t thz_asm_workspace_bytes(const thz_asm_desc* d) {
 }
 
 extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
+    ThzDeviceGuard dev_guard(d ? d->x : nullptr);
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = thz_asm_validate(d);
     if (rc != THZ_OK) return thz_set_error(rc, "thz_asm_propagate: invalid descriptor");
@@ -162,6 +163,7 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
 // ------------------------------------------------------------------------------- stand-alone fft2
 extern "C" int thz_fft2_c2c(const void* x, void* y, int32_t batch, int32_t H, int32_t W, int32_t inverse, int32_t ortho,
                             const void* tw_h, const void* tw_w, void* ws, uint64_t ws_bytes, void* stream_) {
+    ThzDeviceGuard dev_guard(x);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!x || !y || !tw_h || !tw_w || !ws) return thz_set_error(THZ_E_NULL, "thz_fft2_c2c: null pointer");
     if (batch < 1 || H < 1 || W < 1) return thz_set_error(THZ_E_SHAPE, "thz_fft2_c2c: bad shape");

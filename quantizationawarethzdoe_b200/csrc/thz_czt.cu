@@ -18,6 +18,8 @@
 
 #include "thz_common.cuh"
 #include "thz_czt_args.h"
+#include <atomic>
+#include <stdio.h>
 #include "thz_runtime.h"
 
 
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(256) thz_k_toeplitz_gemm(const __grid_constant
 }
 
 extern "C" int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* d, void* stream_) {
+    ThzDeviceGuard dev_guard(d ? d->C : nullptr);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!d) return thz_set_error(THZ_E_NULL, "thz_toeplitz_gemm: null descriptor");
     if (!d->g || !d->B || !d->C) return thz_set_error(THZ_E_NULL, "thz_toeplitz_gemm: null pointer");
@@ -151,11 +154,30 @@ extern "C" int thz_toeplitz_gemm(const thz_toeplitz_gemm_desc* d, void* stream_)
     a.epi = (const cpx*)d->epi;
     a.conj_epi = d->conj_epi;
     { const char* dbg = getenv("THZ_CZT_DEBUG"); a.debug_mode = dbg ? atoi(dbg) : 0; }
-    // implementation choice: tcgen05 3xTF32 tensor-core kernel unless THZ_CZT_IMPL=simt asks for the CUDA-core one
-    const char* impl = getenv("THZ_CZT_IMPL");
-    if (!(impl && strcmp(impl, "simt") == 0)) {
-        const int rc = thz_toeplitz_gemm_tc_launch(a, d->scratch, stream);
-        if (rc != THZ_E_WORKSPACE) return rc;       // else: no scratch for the prologue factor -> CUDA-core kernel
+    // implementation choice (desc->impl; the environment variable THZ_CZT_IMPL = tc | simt overrides "auto" for A/B runs):
+    //   0 auto: the tcgen05 3xTF32 kernel when the call is eligible, else the CUDA-core kernel with ONE warning on stderr;
+    //   1 tc:   the tcgen05 kernel or THZ_E_UNSUPPORTED -- never a silent switch;   2 simt: the CUDA-core kernel.
+    // The two implementations launch under different kernel classes (THZ_KC_CZT_TC / THZ_KC_CZT), so
+    // thz_launch_count_class() tells a caller which one ran.
+    int impl = d->impl;
+    if (impl < 0 || impl > 2) return thz_set_error(THZ_E_SHAPE, "thz_toeplitz_gemm: impl must be 0 (auto), 1 (tc) or 2 (simt)");
+    if (impl == 0) {
+        const char* env = getenv("THZ_CZT_IMPL");
+        if (env && strcmp(env, "simt") == 0) impl = 2;
+        else if (env && strcmp(env, "tc") == 0) impl = 1;
+    }
+    if (impl != 2) {
+        const char* why = thz_toeplitz_gemm_tc_ineligible(a, d->scratch);     // checked BEFORE anything is launched
+        if (!why) return thz_toeplitz_gemm_tc_launch(a, d->scratch, stream);
+        if (impl == 1) {
+            char msg[256];
+            snprintf(msg, sizeof(msg), "thz_toeplitz_gemm: impl = tc requested but the call is not eligible (%s)", why);
+            return thz_set_error(THZ_E_UNSUPPORTED, msg);
+        }
+        static std::atomic<int> warned{0};
+        if (!warned.exchange(1))
+            fprintf(stderr, "thzdoe: thz_toeplitz_gemm runs the CUDA-core kernel instead of tcgen05 (%s); "
+                            "pass impl = 1 to make this an error\n", why);
     }
     dim3 grid((d->N + TG_BN - 1) / TG_BN, (d->M + TG_BM - 1) / TG_BM, d->batch);
     thz_launch_begin(stream, THZ_KC_CZT);

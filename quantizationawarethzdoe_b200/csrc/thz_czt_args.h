@@ -21,5 +21,6 @@ struct ToeplitzGemmArgs {
 };
 
 // tcgen05 / TMEM implementation (thz_czt_tc.cu)
-// Returns THZ_E_WORKSPACE (without launching) if `pro` is set but no dense scratch buffer is available.
+// thz_toeplitz_gemm_tc_ineligible: NULL if the kernel can serve the call, else the reason; the launch refuses ineligible calls.
+const char* thz_toeplitz_gemm_tc_ineligible(const ToeplitzGemmArgs& a, const void* scratch);
 int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a, void* scratch, cudaStream_t stream);

@@ -481,29 +481,38 @@ extern "C" int thz_debug_tc_timeline(long long* out) {
     return (int)cudaMemcpyFromSymbol(out, g_tc_timeline, sizeof(long long) * 3 * TC_TL_N * 4);
 }
 
-int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a_in, void* scratch, cudaStream_t stream) {
-    ToeplitzGemmArgs a = a_in;
+// NULL if the tcgen05 kernel can serve the call, else the reason (static string).  No launch happens before this check.
+const char* thz_toeplitz_gemm_tc_ineligible(const ToeplitzGemmArgs& a, const void* scratch) {
     if (a.pro) {
         const bool dense = a.sb_b == (long long)a.K * a.N && ((a.sb_k == a.N && a.sb_n == 1) || (a.sb_k == 1 && a.sb_n == a.K));
-        if (!scratch || !dense) return THZ_E_WORKSPACE;      // caller falls back to the CUDA-core kernel
+        if (!scratch) return "a prologue factor needs desc->scratch";
+        if (!dense) return "a prologue factor needs a dense B operand";
+    }
+    if (a.sm != -a.sk) return "the sliding-strip A operand needs sm == -sk";   // T(m, k) = g[off + sm (m - k)]
+    if (a.L < 64) return "chirp filter shorter than 64";
+    return nullptr;
+}
+
+int thz_toeplitz_gemm_tc_launch(const ToeplitzGemmArgs& a_in, void* scratch, cudaStream_t stream) {
+    ToeplitzGemmArgs a = a_in;
+    if (thz_toeplitz_gemm_tc_ineligible(a, scratch)) return thz_set_error(THZ_E_UNSUPPORTED, "thz_toeplitz_gemm_tc_launch: not eligible");
+    if (a.pro) {
         const size_t n = (size_t)a.batch * a.K * a.N;
         size_t blocks = (n + 255) / 256;
         const size_t cap = (size_t)thz_sm_count() * 16;
-        thz_launch_begin(stream, THZ_KC_CZT);
+        thz_launch_begin(stream, THZ_KC_CZT_TC);
         thz_k_cmul<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, stream>>>(a.B, a.pro, (cpx*)scratch, n, a.conj_pro);
-        thz_launch_end(stream, THZ_KC_CZT);
+        thz_launch_end(stream, THZ_KC_CZT_TC);
         a.B = (const cpx*)scratch;
         a.pro = nullptr;
     }
-    if (a.sm != -a.sk) return THZ_E_WORKSPACE;                   // the sliding-strip A operand needs T(m, k) = g[off + sm (m - k)]
-    if (a.L < 64) return THZ_E_WORKSPACE;
     const size_t smem = (size_t)TC_SMEM_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return thz_set_cuda_error("cudaFuncSetAttribute(thz_k_toeplitz_gemm_tc)", e);
     dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM, a.batch);
-    thz_launch_begin(stream, THZ_KC_CZT);
+    thz_launch_begin(stream, THZ_KC_CZT_TC);
     thz_k_toeplitz_gemm_tc<<<grid, TC_THREADS, smem, stream>>>(a);
-    thz_launch_end(stream, THZ_KC_CZT);
+    thz_launch_end(stream, THZ_KC_CZT_TC);
     e = cudaGetLastError();
     if (e != cudaSuccess) return thz_set_cuda_error("thz_k_toeplitz_gemm_tc", e);
     return THZ_OK;

@@ -155,6 +155,7 @@ static inline int grid_for(size_t n) {
 
 extern "C" int thz_doe_modulate_fwd(const void* x, void* y, const void* hmap, const void* coef, float base, int32_t B,
                                     int32_t C, int32_t H, int32_t W, void* stream) {
+    ThzDeviceGuard dev_guard(y);
     if (!x || !y || !hmap || !coef) return thz_set_error(THZ_E_NULL, "thz_doe_modulate_fwd: null pointer");
     if (B < 1 || C < 1 || H < 1 || W < 1) return thz_set_error(THZ_E_SHAPE, "thz_doe_modulate_fwd: bad shape");
     const size_t HW = (size_t)H * W;
@@ -168,6 +169,7 @@ extern "C" int thz_doe_modulate_fwd(const void* x, void* y, const void* hmap, co
 
 extern "C" int thz_doe_modulate_bwd(const void* g, const void* x, const void* hmap, const void* coef, float base, void* gx,
                                     void* gh, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+    ThzDeviceGuard dev_guard(g);
     if (!g || !hmap || !coef) return thz_set_error(THZ_E_NULL, "thz_doe_modulate_bwd: null pointer");
     if (gh && !x) return thz_set_error(THZ_E_NULL, "thz_doe_modulate_bwd: grad_height needs the saved input field");
     if (B < 1 || C < 1 || H < 1 || W < 1) return thz_set_error(THZ_E_SHAPE, "thz_doe_modulate_bwd: bad shape");
@@ -182,6 +184,7 @@ extern "C" int thz_doe_modulate_bwd(const void* g, const void* x, const void* hm
 
 extern "C" int thz_quant_ste_fwd(const void* in, int32_t from_weights, float hmax, float clampv, const void* lut, int32_t L,
                                  void* q, void* idx, void* h_pre, uint64_t n, void* stream) {
+    ThzDeviceGuard dev_guard(in);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!in || !lut || !q) return thz_set_error(THZ_E_NULL, "thz_quant_ste_fwd: null pointer");
     if (L < 1 || L > THZ_MAX_LEVELS) return thz_set_error(THZ_E_SHAPE, "thz_quant_ste_fwd: 1 <= levels <= 64");
@@ -194,6 +197,7 @@ extern "C" int thz_quant_ste_fwd(const void* in, int32_t from_weights, float hma
 }
 
 extern "C" int thz_height_fwd(const void* w, float hmax, float clampv, void* h, uint64_t n, void* stream) {
+    ThzDeviceGuard dev_guard(w);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!w || !h) return thz_set_error(THZ_E_NULL, "thz_height_fwd: null pointer");
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
@@ -204,6 +208,7 @@ extern "C" int thz_height_fwd(const void* w, float hmax, float clampv, void* h, 
 }
 
 extern "C" int thz_height_bwd(const void* g, const void* w, float hmax, float clampv, void* gw, uint64_t n, void* stream) {
+    ThzDeviceGuard dev_guard(g);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!g || !w || !gw) return thz_set_error(THZ_E_NULL, "thz_height_bwd: null pointer");
     thz_launch_begin((cudaStream_t)stream, THZ_KC_QUANT);
@@ -215,6 +220,7 @@ extern "C" int thz_height_bwd(const void* g, const void* w, float hmax, float cl
 
 extern "C" int thz_quant_nn_fwd(const void* x, const void* lut, int32_t nlut, const void* mid, int32_t nmid, void* q, void* idx,
                                 uint64_t n, void* stream) {
+    ThzDeviceGuard dev_guard(x);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!x || !lut || !mid || !q || !idx) return thz_set_error(THZ_E_NULL, "thz_quant_nn_fwd: null pointer");
     if (nlut < 1 || nlut > THZ_MAX_LEVELS + 1 || nmid < 1 || nmid > THZ_MAX_LEVELS || nmid >= nlut + 1)
@@ -229,6 +235,7 @@ extern "C" int thz_quant_nn_fwd(const void* x, const void* lut, int32_t nlut, co
 
 extern "C" int thz_quant_nn_bwd(const void* g, const void* x, const void* idx, const void* lut, int32_t nlut, float s,
                                 int32_t kind, void* gx, uint64_t n, void* stream) {
+    ThzDeviceGuard dev_guard(g);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!g || !x || !idx || !lut || !gx) return thz_set_error(THZ_E_NULL, "thz_quant_nn_bwd: null pointer");
     if (nlut < 1 || nlut > THZ_MAX_LEVELS + 1 || kind < 0 || kind > 2) return thz_set_error(THZ_E_SHAPE, "thz_quant_nn_bwd: bad arguments");
@@ -242,6 +249,7 @@ extern "C" int thz_quant_nn_bwd(const void* g, const void* x, const void* idx, c
 
 extern "C" int thz_quant_psq_fwd(const void* w, float hmax, int32_t L, float tau, void* out, void* dout_dw, uint64_t n,
                                  void* stream) {
+    ThzDeviceGuard dev_guard(w);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!w || !out) return thz_set_error(THZ_E_NULL, "thz_quant_psq_fwd: null pointer");
     if (L < 2) return thz_set_error(THZ_E_SHAPE, "thz_quant_psq_fwd: levels >= 2");
@@ -255,6 +263,7 @@ extern "C" int thz_quant_psq_fwd(const void* w, float hmax, int32_t L, float tau
 extern "C" int thz_quant_gumbel_v3_fwd(const void* w, const void* lut, int32_t L, const void* noise, float hmax, float kfac,
                                        float c_s, float tau, float tau_max, float s, float beta, float one_minus_beta,
                                        int32_t phase_input, void* h_out, void* idx, void* dh_dw, uint64_t n, void* stream) {
+    ThzDeviceGuard dev_guard(w);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!w || !lut || !noise || !h_out) return thz_set_error(THZ_E_NULL, "thz_quant_gumbel_v3_fwd: null pointer");
     if (L < 1 || L > THZ_MAX_LEVELS) return thz_set_error(THZ_E_SHAPE, "thz_quant_gumbel_v3_fwd: 1 <= levels <= 64");
@@ -279,6 +288,7 @@ extern "C" int thz_quant_gumbel_v3_fwd(const void* w, const void* lut, int32_t L
 
 extern "C" int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise, const void* lut, int32_t L, float tau, void* q,
                                           void* idx, void* dq, uint64_t n, void* stream) {
+    ThzDeviceGuard dev_guard(logits);
     if (n == 0) return THZ_OK;   // empty maps are legal (and have a NULL data pointer)
     if (!logits || !noise || !lut || !q) return thz_set_error(THZ_E_NULL, "thz_quant_gumbel_naive_fwd: null pointer");
     if (L < 1 || L > THZ_MAX_LEVELS) return thz_set_error(THZ_E_SHAPE, "thz_quant_gumbel_naive_fwd: 1 <= levels <= 64");
@@ -288,6 +298,168 @@ extern "C" int thz_quant_gumbel_naive_fwd(const void* logits, const void* noise,
                                                                           (float*)dq, n);
     thz_launch_end((cudaStream_t)stream, THZ_KC_QUANT);
     THZ_CHECK_LAUNCH("thz_k_gumbel_naive_fwd");
+    return THZ_OK;
+}
+
+// ------------------------------------------------------------------------------- thickness-space softmax quantization
+// stats (device float[4], caller-owned): [0] m = max |t - lut_j| over the map and the levels (bit pattern, via atomicMax on
+// the non-negative float's integer image), [1] number of (pixel, level) pairs attaining it, [2] sum_pixels g dq/dm (backward).
+__global__ void __launch_bounds__(256) thz_k_softmaxq_absmax(const float* __restrict__ t, const float* __restrict__ lut_g, int L,
+                                                             float* __restrict__ stats, size_t n) {
+    __shared__ float lut[THZ_MAX_LEVELS];
+    __shared__ float red[8];
+    for (int j = threadIdx.x; j < L; j += blockDim.x) lut[j] = lut_g[j];
+    __syncthreads();
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = t[i];
+        for (int j = 0; j < L; ++j) m = fmaxf(m, fabsf(thz_sub_rn(v, lut[j])));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]);
+        atomicMax(reinterpret_cast<int*>(stats), __float_as_int(m));
+    }
+}
+
+__global__ void __launch_bounds__(256) thz_k_softmaxq_fwd(const float* __restrict__ t, const float* __restrict__ lut_g,
+                                                          const float* __restrict__ noise, SoftmaxQParams P,
+                                                          float* __restrict__ stats, float* __restrict__ q,
+                                                          int32_t* __restrict__ idx, float* __restrict__ A, float* __restrict__ Bm,
+                                                          float* __restrict__ E, size_t n) {
+    __shared__ float lut[THZ_MAX_LEVELS];
+    for (int j = threadIdx.x; j < P.L; j += blockDim.x) lut[j] = lut_g[j];
+    __syncthreads();
+    P.m = stats[0];
+    int ties = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float qq, a, b, e;
+        int nt;
+        const int k = thz_softmaxq_pixel(t[i], lut, noise ? noise + i : nullptr, n, P, &qq, A ? &a : nullptr, &b, &e, &nt);
+        q[i] = qq;
+        if (idx) idx[i] = k;
+        if (A) {
+            A[i] = a;
+            Bm[i] = b;
+            E[i] = e;
+        }
+        ties += nt;
+    }
+    if (ties) atomicAdd(stats + 1, (float)ties);
+}
+
+__global__ void __launch_bounds__(256) thz_k_softmaxq_bwd_reduce(const float* __restrict__ g, const float* __restrict__ Bm,
+                                                                 float* __restrict__ stats, size_t n) {
+    __shared__ float red[8];
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += g[i] * Bm[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) acc += red[k];
+        atomicAdd(stats + 2, acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) thz_k_softmaxq_bwd(const float* __restrict__ g, const float* __restrict__ A,
+                                                          const float* __restrict__ E, const float* __restrict__ stats,
+                                                          float* __restrict__ gt, size_t n) {
+    const float share = stats[1] > 0.f ? stats[2] / stats[1] : 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        gt[i] = g[i] * A[i] + share * E[i];
+}
+
+__global__ void __launch_bounds__(256) thz_k_score_thickness(const float* __restrict__ t, const float* __restrict__ lut_g, int L,
+                                                             float s, int func, const float* __restrict__ stats,
+                                                             float* __restrict__ scores, size_t n_per_b, size_t total) {
+    __shared__ float lut[THZ_MAX_LEVELS];
+    for (int j = threadIdx.x; j < L; j += blockDim.x) lut[j] = lut_g[j];
+    __syncthreads();
+    const float m = stats[0];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / n_per_b, p = i - b * n_per_b;
+        const float v = t[i];
+        for (int j = 0; j < L; ++j) scores[(b * L + j) * n_per_b + p] = thz_score_value(thz_sub_rn(v, lut[j]) / m, s, func);
+    }
+}
+
+static int softmaxq_absmax(const void* t, const void* lut, int L, void* stats, uint64_t n, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream);
+    if (e != cudaSuccess) return thz_set_cuda_error("cudaMemsetAsync(stats)", e);
+    thz_launch_begin(stream, THZ_KC_QUANT);
+    thz_k_softmaxq_absmax<<<grid_for(n), 256, 0, stream>>>((const float*)t, (const float*)lut, L, (float*)stats, n);
+    thz_launch_end(stream, THZ_KC_QUANT);
+    THZ_CHECK_LAUNCH("thz_k_softmaxq_absmax");
+    return THZ_OK;
+}
+
+extern "C" int thz_quant_softmax_fwd(const void* thickness, const void* lut, int32_t L, const void* noise, float c, float tau,
+                                     float s, int32_t hard, void* q, void* idx, void* dq_dt, void* dq_dm, void* tie_sign,
+                                     void* stats, uint64_t n, void* stream_) {
+    ThzDeviceGuard dev_guard(thickness);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return THZ_OK;
+    if (!thickness || !lut || !q || !stats) return thz_set_error(THZ_E_NULL, "thz_quant_softmax_fwd: null pointer");
+    if (dq_dt && (!dq_dm || !tie_sign)) return thz_set_error(THZ_E_NULL, "thz_quant_softmax_fwd: dq_dt needs dq_dm and tie_sign");
+    if (L < 1 || L > THZ_MAX_LEVELS) return thz_set_error(THZ_E_SHAPE, "thz_quant_softmax_fwd: 1 <= levels <= 64");
+    int rc = softmaxq_absmax(thickness, lut, L, stats, n, stream);
+    if (rc != THZ_OK) return rc;
+    SoftmaxQParams P;
+    P.m = 0.f;
+    P.s = s;
+    P.c = c;
+    P.tau = tau;
+    P.L = L;
+    P.hard = hard ? 1 : 0;
+    P.gumbel = noise ? 1 : 0;
+    thz_launch_begin(stream, THZ_KC_QUANT);
+    thz_k_softmaxq_fwd<<<grid_for(n), 256, 0, stream>>>((const float*)thickness, (const float*)lut, (const float*)noise, P,
+                                                        (float*)stats, (float*)q, (int32_t*)idx, (float*)dq_dt, (float*)dq_dm,
+                                                        (float*)tie_sign, n);
+    thz_launch_end(stream, THZ_KC_QUANT);
+    THZ_CHECK_LAUNCH("thz_k_softmaxq_fwd");
+    return THZ_OK;
+}
+
+extern "C" int thz_quant_softmax_bwd(const void* g, const void* dq_dt, const void* dq_dm, const void* tie_sign, void* stats,
+                                     void* gt, uint64_t n, void* stream_) {
+    ThzDeviceGuard dev_guard(g);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return THZ_OK;
+    if (!g || !dq_dt || !dq_dm || !tie_sign || !stats || !gt) return thz_set_error(THZ_E_NULL, "thz_quant_softmax_bwd: null pointer");
+    cudaError_t e = cudaMemsetAsync((float*)stats + 2, 0, sizeof(float), stream);
+    if (e != cudaSuccess) return thz_set_cuda_error("cudaMemsetAsync(stats)", e);
+    thz_launch_begin(stream, THZ_KC_QUANT);
+    thz_k_softmaxq_bwd_reduce<<<grid_for(n), 256, 0, stream>>>((const float*)g, (const float*)dq_dm, (float*)stats, n);
+    thz_launch_end(stream, THZ_KC_QUANT);
+    THZ_CHECK_LAUNCH("thz_k_softmaxq_bwd_reduce");
+    thz_launch_begin(stream, THZ_KC_QUANT);
+    thz_k_softmaxq_bwd<<<grid_for(n), 256, 0, stream>>>((const float*)g, (const float*)dq_dt, (const float*)tie_sign,
+                                                        (const float*)stats, (float*)gt, n);
+    thz_launch_end(stream, THZ_KC_QUANT);
+    THZ_CHECK_LAUNCH("thz_k_softmaxq_bwd");
+    return THZ_OK;
+}
+
+extern "C" int thz_score_thickness(const void* thickness, const void* lut, int32_t L, float s, int32_t func, void* scores,
+                                   void* stats, int32_t batch, uint64_t n_per_b, void* stream_) {
+    ThzDeviceGuard dev_guard(thickness);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const uint64_t total = (uint64_t)batch * n_per_b;
+    if (batch < 0) return thz_set_error(THZ_E_SHAPE, "thz_score_thickness: bad batch");
+    if (total == 0) return THZ_OK;
+    if (!thickness || !lut || !scores || !stats) return thz_set_error(THZ_E_NULL, "thz_score_thickness: null pointer");
+    if (L < 1 || L > THZ_MAX_LEVELS || func < 0 || func > 4) return thz_set_error(THZ_E_SHAPE, "thz_score_thickness: bad arguments");
+    int rc = softmaxq_absmax(thickness, lut, L, stats, total, stream);
+    if (rc != THZ_OK) return rc;
+    thz_launch_begin(stream, THZ_KC_QUANT);
+    thz_k_score_thickness<<<grid_for(total), 256, 0, stream>>>((const float*)thickness, (const float*)lut, L, s, func,
+                                                               (const float*)stats, (float*)scores, n_per_b, total);
+    thz_launch_end(stream, THZ_KC_QUANT);
+    THZ_CHECK_LAUNCH("thz_k_score_thickness");
     return THZ_OK;
 }
 
@@ -312,6 +484,7 @@ __global__ void __launch_bounds__(256) thz_k_field_mul(const cpx* __restrict__ x
 
 extern "C" int thz_field_mul(const void* x, const void* m, void* y, int32_t BC, int32_t C, uint64_t HW, int32_t per_channel,
                              int32_t m_real, int32_t conj_m, void* stream_) {
+    ThzDeviceGuard dev_guard(x);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (BC < 0 || C < 1) return thz_set_error(THZ_E_SHAPE, "thz_field_mul: bad sizes");
     if (BC == 0 || HW == 0) return THZ_OK;

@@ -175,3 +175,92 @@ THZ_HD int thz_gumbel_v3_pixel(float w, const float* lut, const float* noise, si
     }
     return idx;
 }
+
+// ---------------------------------------------------------------- thickness-space softmax quantization
+// SoftmaxBasedQuantization.forward + score_thickness('sigmoid') (Components/quantization.py:36-46, 128-161) for one pixel:
+//   nd_j = (t - lut_j) / m,  m = max over the WHOLE map and all levels of |t - lut_j|   (score_thickness :40-41)
+//   score_j = sigmoid(s nd_j) (1 - sigmoid(s nd_j)) 4 * c * s,   s = tau_max / tau
+//   gumbel: y = softmax((score + G) / tau), hard -> (onehot - y) + y      [F.gumbel_softmax]
+//   plain:  y = softmax(score / tau),       hard -> (onehot + y) - y      [:146-152]
+//   q = sum_j onehot_j lut_j
+// For the backward (autograd through the out-of-place form diff / max|diff|; the reference's in-place `diff /= max` makes
+// its own backward raise) the pixel also returns
+//   A = d q / d t at fixed m,   Bm = d q / d m,   E = sum over the levels of this pixel that attain the maximum of sign(diff)
+// so that  gt = g A + (sum_pixels g Bm) / ties * E  -- torch.max() splits its gradient evenly over ties.
+struct SoftmaxQParams {
+    float m;          // global max |t - lut_j|
+    float s, c, tau;
+    int L, hard, gumbel;
+};
+THZ_HD int thz_softmaxq_pixel(float t, const float* lut, const float* noise, size_t nstride, const SoftmaxQParams& P, float* q,
+                              float* A, float* Bm, float* E, int* ties) {
+    float logit[THZ_MAX_LEVELS], y[THZ_MAX_LEVELS], dsc[THZ_MAX_LEVELS], diff[THZ_MAX_LEVELS];
+    float e = 0.f;
+    int nt = 0;
+    for (int j = 0; j < P.L; ++j) {
+        diff[j] = thz_sub_rn(t, lut[j]);
+        if (fabsf(diff[j]) == P.m) {
+            e += diff[j] > 0.f ? 1.f : (diff[j] < 0.f ? -1.f : 0.f);
+            ++nt;
+        }
+        const float nd = diff[j] / P.m;
+        const float z = thz_mul_rn(P.s, nd);
+        const float sg = thz_sigmoid(z);
+        const float score = thz_mul_rn(thz_mul_rn(thz_mul_rn(thz_mul_rn(sg, thz_sub_rn(1.0f, sg)), 4.0f), P.c), P.s);
+        logit[j] = P.gumbel ? thz_add_rn(score, noise[(size_t)j * nstride]) / P.tau : score / P.tau;
+        dsc[j] = 4.0f * P.c * P.s * sg * (1.0f - sg) * (1.0f - 2.0f * sg) * P.s;        // d score / d nd
+    }
+    float mx = logit[0];
+    for (int j = 1; j < P.L; ++j) mx = fmaxf(mx, logit[j]);
+    float sum = 0.f;
+    for (int j = 0; j < P.L; ++j) {
+        y[j] = expf(logit[j] - mx);
+        sum += y[j];
+    }
+    int idx = 0;
+    float sm = 0.f;
+    for (int j = 0; j < P.L; ++j) {
+        y[j] = y[j] / sum;
+        if (y[j] > y[idx]) idx = j;
+        sm += lut[j] * y[j];
+    }
+    float qq = 0.f;
+    for (int j = 0; j < P.L; ++j) {
+        float oh = y[j];
+        if (P.hard) {
+            const float hd = (j == idx) ? 1.0f : 0.0f;
+            oh = P.gumbel ? thz_add_rn(thz_sub_rn(hd, y[j]), y[j]) : thz_sub_rn(thz_add_rn(hd, y[j]), y[j]);
+        }
+        qq = thz_add_rn(qq, thz_mul_rn(oh, lut[j]));
+    }
+    *q = qq;
+    if (A) {
+        float a = 0.f, b = 0.f;
+        for (int j = 0; j < P.L; ++j) {
+            const float dq_dnd = y[j] * (lut[j] - sm) * dsc[j] / P.tau;
+            a += dq_dnd;
+            b -= dq_dnd * diff[j];
+        }
+        *A = a / P.m;
+        *Bm = b / (P.m * P.m);
+        *E = e;
+    }
+    *ties = nt;
+    return idx;
+}
+
+// score_thickness for every scoring function the reference offers (quantization.py:36-55): 0 sigmoid, 1 log, 2 poly, 3 sine,
+// 4 chirp; nd = diff / max|diff| already formed.
+THZ_HD float thz_score_value(float nd, float s, int func) {
+    const float PI_F = 3.14159265358979323846f;
+    switch (func) {
+    case 0: {
+        const float sg = thz_sigmoid(thz_mul_rn(s, nd));
+        return thz_mul_rn(thz_mul_rn(sg, thz_sub_rn(1.0f, sg)), 4.0f);
+    }
+    case 1: return thz_mul_rn(-logf(thz_add_rn(fabsf(nd), 1e-20f)), s);
+    case 2: return thz_sub_rn(1.0f, powf(fabsf(nd), s));
+    case 3: return cosf(thz_mul_rn(PI_F, fminf(fmaxf(thz_mul_rn(s, nd), -1.0f), 1.0f)));
+    default: return thz_sub_rn(1.0f, cosf(thz_mul_rn(PI_F, powf(thz_sub_rn(1.0f, fabsf(nd)), s))));
+    }
+}

@@ -97,6 +97,7 @@ __global__ void thz_k_normmse_fixup(const cpx* __restrict__ y, const unsigned lo
 
 extern "C" int thz_normmse_loss(const void* y, const void* target, int32_t B, uint64_t n_per_b, void* scratch, void* loss,
                                 void* gy, void* stream_) {
+    ThzDeviceGuard dev_guard(y);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (B < 0) return thz_set_error(THZ_E_SHAPE, "thz_normmse_loss: negative batch");
     if (B == 0 || n_per_b == 0) return THZ_OK;
@@ -156,6 +157,7 @@ __global__ void thz_k_step_inc(int* step) { *step += 1; }
 
 extern "C" int thz_adam_step(void* p, const void* g, void* m, void* v, void* step, uint64_t n, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int32_t decoupled, int32_t advance, void* stream_) {
+    ThzDeviceGuard dev_guard(p);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return THZ_OK;
     if (!p || !g || !m || !v || !step) return thz_set_error(THZ_E_NULL, "thz_adam_step: null pointer");

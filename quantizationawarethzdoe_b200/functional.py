@@ -16,9 +16,12 @@ BASE_PLANE_THICKNESS = 2 * 1e-3   # Components/QuantizedDOE.py:23
 # tuning knobs (bench.py / tests may override): fields per kernel group, K2 tile width, rows per CTA
 import os as _os
 
-TUNE = {"bc_chunk": int(_os.environ.get("THZ_BC_CHUNK", "0")), "k2_cols": 0, "lines": 0}   # 0 = library defaults
+TUNE = {"bc_chunk": int(_os.environ.get("THZ_BC_CHUNK", "0")), "k2_cols": 0, "lines": 0,   # 0 = library defaults
+        "czt_impl": "auto"}
+CZT_IMPL = {"auto": 0, "tc": 1, "simt": 2}      # thz_toeplitz_gemm_desc.impl
 
-_ws_cache = {}
+_ws_cache = {}      # (device, stream) -> [tensor, handed_out_during_capture]
+_ws_retired = []    # superseded buffers that a CUDA graph may still reference: kept alive for the life of the process
 
 
 def _asm_call(desc, device):
@@ -27,13 +30,21 @@ def _asm_call(desc, device):
 
 
 def _workspace(numel, device):
-    """One cached complex64 scratch tensor per device, grown on demand (never shrunk)."""
-    key = str(device)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < numel:
-        ws = torch.empty(numel, dtype=torch.complex64, device=device)
-        _ws_cache[key] = ws
-    return ws
+    """Cached complex64 scratch, one per (device, stream): two streams never share a buffer, so concurrent calls cannot
+    race on it.  Grown by replacement, but a buffer that was ever handed out while a CUDA graph was being captured is
+    retired, not freed -- the graph has its address baked in, and freeing it would let replays scribble over whatever
+    the caching allocator put there next."""
+    stream = (N.current_stream_ptr(device).value or 0) if device.type == "cuda" else 0
+    key = (str(device), stream)
+    ent = _ws_cache.get(key)
+    capturing = torch.cuda.is_current_stream_capturing() if device.type == "cuda" else False
+    if ent is None or ent[0].numel() < numel:
+        if ent is not None and ent[1]:
+            _ws_retired.append(ent[0])
+        ent = _ws_cache[key] = [torch.empty(numel, dtype=torch.complex64, device=device), False]
+    if capturing:
+        ent[1] = True
+    return ent[0]
 
 
 def _c64(t, name):
@@ -358,6 +369,61 @@ class GumbelNaiveFn(torch.autograd.Function):
         return g.unsqueeze(-1) * dq, None, None, None
 
 
+class SoftmaxQuantizeFn(torch.autograd.Function):
+    """SoftmaxBasedQuantization.forward (Components/quantization.py:128-161) on one thickness map; noise=None is the plain
+    softmax branch.  Returns (q, idx).  Backward: autograd through diff / max|diff| incl. the path through the max."""
+
+    @staticmethod
+    def forward(ctx, thickness, lut, noise, c, tau, s, hard):
+        t = _f32(thickness, "thickness")
+        lut = _f32(lut, "lut")
+        L, n = lut.numel(), t.numel()
+        if noise is not None:
+            noise = _f32(noise, "gumbel noise")
+            assert noise.numel() == L * n, "noise must be [1,L,H,W]"
+        q = torch.empty_like(t)
+        idx = torch.empty(t.shape, dtype=torch.int32, device=t.device)
+        need = ctx.needs_input_grad[0]
+        A, Bm, E = (torch.empty_like(t), torch.empty_like(t), torch.empty_like(t)) if need else (None, None, None)
+        stats = torch.empty(4, dtype=torch.float32, device=t.device)
+        N.check(N.lib().thz_quant_softmax_fwd(N.ptr(t), N.ptr(lut), L, N.ptr(noise), float(c), float(tau), float(s), 1 if hard else 0,
+                                              N.ptr(q), N.ptr(idx), N.ptr(A), N.ptr(Bm), N.ptr(E), N.ptr(stats), n,
+                                              N.current_stream_ptr(t.device)), "thz_quant_softmax_fwd")
+        if need:
+            ctx.save_for_backward(A, Bm, E, stats)
+        ctx.mark_non_differentiable(idx)
+        return q, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        A, Bm, E, stats = ctx.saved_tensors
+        g = _f32(g, "grad")
+        gt = torch.empty_like(A)
+        N.check(N.lib().thz_quant_softmax_bwd(N.ptr(g), N.ptr(A), N.ptr(Bm), N.ptr(E), N.ptr(stats), N.ptr(gt), A.numel(),
+                                              N.current_stream_ptr(g.device)), "thz_quant_softmax_bwd")
+        return (gt,) + (None,) * 6
+
+
+SCORE_FUNCS = {"sigmoid": 0, "log": 1, "poly": 2, "sine": 3, "chirp": 4}
+
+
+def score_thickness(thickness, lut, s=5., func="sigmoid"):
+    """score_thickness (Components/quantization.py:36-55): thickness [N,1,H,W], lut [L] or [1,L,1,1] -> scores [N,L,H,W].
+    Forward only: the reference's own backward through this function raises (in-place normalisation, :41)."""
+    t = _f32(thickness.detach(), "thickness")
+    lut = _f32(torch.as_tensor(lut).reshape(-1).to(t.device), "lut")
+    if func not in SCORE_FUNCS:
+        raise ValueError("func must be one of %s" % sorted(SCORE_FUNCS))
+    if t.dim() != 4 or t.shape[1] != 1:
+        raise ValueError("thickness must be [N,1,H,W]")
+    Nb, _, H, W = t.shape
+    scores = torch.empty(Nb, lut.numel(), H, W, dtype=torch.float32, device=t.device)
+    stats = torch.empty(4, dtype=torch.float32, device=t.device)
+    N.check(N.lib().thz_score_thickness(N.ptr(t), N.ptr(lut), lut.numel(), float(s), SCORE_FUNCS[func], N.ptr(scores), N.ptr(stats),
+                                        Nb, H * W, N.current_stream_ptr(t.device)), "thz_score_thickness")
+    return scores
+
+
 class FieldMulFn(torch.autograd.Function):
     """y = x * m for a fixed pointwise element m (complex [C,H,W] per wavelength, or a real mask [H,W]); backward x conj(m)."""
 
@@ -407,7 +473,7 @@ def _toeplitz_gemm(batch, M, N_, K, g, L, off, sm, sk, conj_g, B, sb, pro, conj_
     d = N.ToeplitzGemmDesc()
     d.batch, d.M, d.N, d.K = batch, M, N_, K
     d.g, d.L, d.off, d.sm, d.sk = N.ptr(g), L, off, sm, sk
-    d.conj_g, d.conj_pro, d.conj_epi, d.reserved = conj_g, conj_pro, conj_epi, 0
+    d.conj_g, d.conj_pro, d.conj_epi, d.impl = conj_g, conj_pro, conj_epi, CZT_IMPL[TUNE.get('czt_impl', 'auto')]
     d.B, (d.sb_b, d.sb_k, d.sb_n) = N.ptr(B), sb
     d.pro = N.ptr(pro)
     d.C, (d.sc_b, d.sc_m, d.sc_n) = N.ptr(C), sc

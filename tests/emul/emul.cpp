@@ -311,3 +311,50 @@ extern "C" int thz_emul_plan_info(int32_t n, int32_t* radices, int32_t* ns) {
     *ns = P.ns;
     return THZ_OK;
 }
+
+// thickness-space softmax quantizer (thz_doe.cuh thz_softmaxq_pixel), forward + backward, on host pointers
+#include "../../quantizationawarethzdoe_b200/csrc/thz_doe.cuh"
+extern "C" int thz_emul_softmaxq(const float* t, const float* lut, int32_t L, const float* noise, float c, float tau, float s,
+                                 int32_t hard, float* q, int32_t* idx, float* A, float* Bm, float* E, float* stats, uint64_t n) {
+    float m = 0.f;
+    for (uint64_t i = 0; i < n; ++i)
+        for (int j = 0; j < L; ++j) m = fmaxf(m, fabsf(thz_sub_rn(t[i], lut[j])));
+    SoftmaxQParams P;
+    P.m = m;
+    P.s = s;
+    P.c = c;
+    P.tau = tau;
+    P.L = L;
+    P.hard = hard;
+    P.gumbel = noise ? 1 : 0;
+    int ties = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        int nt;
+        idx[i] = thz_softmaxq_pixel(t[i], lut, noise ? noise + i : nullptr, n, P, q + i, A + i, Bm + i, E + i, &nt);
+        ties += nt;
+    }
+    stats[0] = m;
+    stats[1] = (float)ties;
+    return THZ_OK;
+}
+extern "C" int thz_emul_softmaxq_bwd(const float* g, const float* A, const float* Bm, const float* E, float* stats, float* gt,
+                                     uint64_t n) {
+    double S = 0.0;
+    for (uint64_t i = 0; i < n; ++i) S += (double)g[i] * Bm[i];
+    stats[2] = (float)S;
+    const float share = stats[1] > 0.f ? stats[2] / stats[1] : 0.f;
+    for (uint64_t i = 0; i < n; ++i) gt[i] = g[i] * A[i] + share * E[i];
+    return THZ_OK;
+}
+extern "C" int thz_emul_score_thickness(const float* t, const float* lut, int32_t L, float s, int32_t func, float* scores,
+                                        int32_t batch, uint64_t n_per_b) {
+    const uint64_t total = (uint64_t)batch * n_per_b;
+    float m = 0.f;
+    for (uint64_t i = 0; i < total; ++i)
+        for (int j = 0; j < L; ++j) m = fmaxf(m, fabsf(thz_sub_rn(t[i], lut[j])));
+    for (uint64_t i = 0; i < total; ++i) {
+        const uint64_t b = i / n_per_b, p = i - b * n_per_b;
+        for (int j = 0; j < L; ++j) scores[(b * L + j) * n_per_b + p] = thz_score_value(thz_sub_rn(t[i], lut[j]) / m, s, func);
+    }
+    return THZ_OK;
+}

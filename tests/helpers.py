@@ -18,6 +18,21 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+def record(test, **vals):
+    """Append measured errors to gpurun_out/parity_errors.jsonl (copied to profiles/ per round) and echo them: the
+    tolerances in the tests are bars, these are the distances actually measured on the GPU."""
+    import json
+    line = json.dumps(dict(test=test, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in vals.items()}))
+    print("PARITY", line)
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_errors.jsonl"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
 def golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     out = {}
@@ -66,4 +81,8 @@ def emul_lib():
     E.thz_emul_plan_info.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     E.thz_emul_fft2_c2c.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    f32, u64 = ctypes.c_float, ctypes.c_uint64
+    E.thz_emul_softmaxq.argtypes = [vp, vp, i32, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, u64]
+    E.thz_emul_softmaxq_bwd.argtypes = [vp, vp, vp, vp, vp, vp, u64]
+    E.thz_emul_score_thickness.argtypes = [vp, vp, i32, f32, i32, vp, i32, u64]
     return E

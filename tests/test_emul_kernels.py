@@ -248,3 +248,76 @@ def test_layout_and_pruning_switches_do_not_change_the_result(env, monkeypatch):
     got = run()
     for a, b in zip(got, ref):
         assert rel_l2(a, b) < 2e-6
+
+
+SOFTMAX_CASES = ("gumbel_hard", "gumbel_soft", "plain_hard", "plain_soft")
+
+
+def _softmaxq_replay(E, t, lut, noise, tau, hard, gq):
+    import ctypes
+    P = lambda v: ctypes.c_void_p(v.data_ptr()) if v is not None else None
+    n, L = t.numel(), lut.numel()
+    s = float(torch.tensor(3.0) / torch.tensor(tau, dtype=torch.float32))
+    q, A, Bm, Ee, gt = (torch.empty(n) for _ in range(5))
+    idx, st = torch.empty(n, dtype=torch.int32), torch.zeros(4)
+    gq = gq.reshape(-1).contiguous()
+    assert E.thz_emul_softmaxq(P(t), P(lut), L, P(noise), 300., float(torch.tensor(tau, dtype=torch.float32)), s, int(hard), P(q),
+                               P(idx), P(A), P(Bm), P(Ee), P(st), n) == 0
+    assert E.thz_emul_softmaxq_bwd(P(gq), P(A), P(Bm), P(Ee), P(st), P(gt), n) == 0
+    return q, gt, st
+
+
+@pytest.mark.parametrize("name", SOFTMAX_CASES)
+def test_softmax_quantizer_body_replay(name):
+    """thz_softmaxq_pixel (the body of thz_quant_softmax_fwd / _bwd) replayed on the CPU against the reference's forward
+    values and the oracle's gradients (tests/golden/quant_softmax.npz).  The soft branches at small tau are ill-conditioned
+    in fp32 (logits of O(1000)): the gradient is held to the distance the fp32 reference itself has from float64."""
+    from helpers import golden
+    E = emul_lib()
+    g = golden("quant_softmax")
+    t = g["thickness"].reshape(-1).contiguous()
+    lut = g["lut"][:-1].contiguous()
+    noise = g["noise_" + name].reshape(lut.numel(), -1).contiguous() if ("noise_" + name) in g else None
+    q, gt, _ = _softmaxq_replay(E, t, lut, noise, g["tau_" + name], "hard" in name, g["gq"])
+    ref_q, ref_g, g64 = g["q_" + name].reshape(-1), g["gt_" + name].reshape(-1), g["gt64_" + name].reshape(-1)
+    assert rel_l2(q, ref_q) < 1e-6
+    if "hard" in name:      # the selected LEVEL is exact; the value carries the ulps of (onehot + y) - y, which depend on libm's exp
+        lv = lambda v: torch.argmin((v[:, None] - lut[None, :]).abs(), dim=1)
+        assert torch.equal(lv(q), lv(ref_q))
+    budget = max(1e-5, 2.0 * rel_l2(ref_g.double(), g64))
+    assert rel_l2(gt, ref_g) < budget, (rel_l2(gt, ref_g), budget)
+
+
+def test_softmax_quantizer_ties_in_the_global_max():
+    """A map with repeated values: many (pixel, level) pairs attain max|diff|, torch.max splits its gradient evenly."""
+    from helpers import golden
+    E = emul_lib()
+    g = golden("quant_softmax")
+    q, gt, st = _softmaxq_replay(E, g["ties_t"].reshape(-1).contiguous(), g["lut"][:-1].contiguous(), None, g["ties_tau"], True,
+                                 g["ties_gq"])
+    assert st[1] == 55
+    assert torch.equal(q, g["ties_q"].reshape(-1))
+    assert (gt - g["ties_gt"].reshape(-1)).abs().max() <= 1e-6 * g["ties_gt"].abs().max() + 1e-20
+
+
+@pytest.mark.parametrize("func", ["sigmoid", "log", "poly", "sine", "chirp"])
+def test_score_thickness_body_replay(func):
+    """All five scoring functions of the reference's score_thickness (quantization.py:36-55), out-of-place restatement."""
+    import ctypes, math
+    E = emul_lib()
+    torch.manual_seed(3)
+    t = torch.rand(2, 1, 9, 7) * 1.2e-3 - 1e-4
+    lut = torch.linspace(0, 1e-3, 5)[:-1].contiguous()
+    s = 2.5
+    diff = t - lut.reshape(1, -1, 1, 1)
+    diff = diff / torch.max(torch.abs(diff))
+    ref = {"sigmoid": lambda: torch.sigmoid(s * diff) * (1 - torch.sigmoid(s * diff)) * 4,
+           "log": lambda: -torch.log(diff.abs() + 1e-20) * s,
+           "poly": lambda: (1 - torch.abs(diff) ** s),
+           "sine": lambda: torch.cos(math.pi * (s * diff).clamp(-1., 1.)),
+           "chirp": lambda: 1 - torch.cos(math.pi * (1 - diff.abs()) ** s)}[func]()
+    out = torch.empty(2, 4, 9, 7)
+    P = lambda v: ctypes.c_void_p(v.data_ptr())
+    assert E.thz_emul_score_thickness(P(t.contiguous()), P(lut), 4, s, ["sigmoid", "log", "poly", "sine", "chirp"].index(func), P(out),
+                                      2, 63) == 0
+    assert rel_l2(out, ref) < 2e-6

@@ -6,7 +6,7 @@ Tolerances (north_star): rel-L2 <= 1e-5 on complex64 fields and gradients; level
 import pytest
 import torch
 
-from helpers import asm_case_kwargs, golden, golden_names, rel_l2
+from helpers import asm_case_kwargs, golden, golden_names, record, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -27,22 +27,41 @@ def _asm(g, dev, mode):
     return a
 
 
-@pytest.mark.parametrize("mode", ["cached", "inregister"])
+def _inregister_estimate(g):
+    """Host-side estimate of how far the reference's own H (MKL sqrt) is from the correctly rounded one for a fixture."""
+    from quantizationawarethzdoe_b200 import asm_host as AH
+    kw = asm_case_kwargs(g)
+    ps = AH.normalise_padding_scale(kw["padding_scale"], kw["do_padding"])
+    _, _, Hp, Wp = AH.compute_padding(g["x"].shape[-2], g["x"].shape[-1], ps, kw["do_padding"])
+    return AH.inregister_deviation_estimate(Hp, Wp, g["spacing"].float(), g["wavelengths"].float(), torch.tensor(g["z"]), True,
+                                            kw["bandlimit_type"])
+
+
+@pytest.mark.parametrize("mode", ["auto", "cached", "inregister"])
 @pytest.mark.parametrize("name", golden_names("asm_"))
 def test_asm_matches_reference_vectors(name, mode, dev):
-    from quantizationawarethzdoe_b200 import ElectricField
+    """'auto' is what ASM_prop ships as the default and 'cached' is its fallback: both are held to 1e-5 on every
+    reference vector.  Forced 'inregister' is held to 1e-5 wherever the plan-time estimate says the reference's own
+    non-IEEE sqrt leaves room for it (that is where 'auto' picks it); elsewhere the measured distance must be explained
+    by that estimate (<= 2.5 x), and is recorded, not hidden."""
+    from quantizationawarethzdoe_b200 import ElectricField, asm_host as AH
     g = golden(name)
     x = g["x"].to(dev).requires_grad_(True)
     f = ElectricField(x, wavelengths=g["wavelengths"].float(), spacing=g["spacing"].float(), device=dev)
-    out = _asm(g, dev, mode)(f)
+    a = _asm(g, dev, mode)
+    out = a(f)
     y = out.data
     assert y.shape == g["y"].shape and y.dtype == torch.complex64
     (gx,) = torch.autograd.grad(y, x, g["g"].to(dev))
-    # in-register H: the reference's own H is off from the correctly rounded one on ~0.7 % of bins (MKL sqrt);
-    # on these tiny grids that is a few e-6..1e-5 of extra distance, so the budget is doubled there.
-    tol = TOL if mode == "cached" else 2.5e-5
-    assert rel_l2(y.detach().cpu(), g["y"]) < tol
-    assert rel_l2(gx.cpu(), g["gx"]) < tol
+    ey, eg = rel_l2(y.detach().cpu(), g["y"]), rel_l2(gx.cpu(), g["gx"])
+    est = _inregister_estimate(g)
+    record("asm_golden", fixture=name, mode=mode, resolved=a.resolved_kernel_mode, y=ey, gx=eg, inregister_estimate=est)
+    tol = TOL
+    if mode == "inregister" and est > AH.INREGISTER_BUDGET:
+        tol = max(TOL, 2.5 * est)
+    if mode == "auto":
+        assert a.resolved_kernel_mode == ("inregister" if est <= AH.INREGISTER_BUDGET else "cached")
+    assert ey < tol and eg < tol
     assert torch.equal(out.spacing.cpu(), f.spacing.cpu()) and torch.equal(out.wavelengths.cpu(), f.wavelengths.cpu())
 
 
@@ -58,14 +77,163 @@ def test_asm_matches_oracle_at_config_sizes(N_, C, scale, dev):
     xo = x.clone().requires_grad_(True)
     yo = AO.asm_forward(xo, lams, 0.5 * mm, 0.1, padding_scale=scale)
     (gxo,) = torch.autograd.grad(yo, xo, g)
-    for mode, tol in (("cached", TOL), ("inregister", TOL)):
+    for mode, tol in (("auto", TOL), ("cached", TOL), ("inregister", TOL)):
         a = ASM_prop(z_distance=0.1, padding_scale=scale, device=dev, kernel_mode=mode)
         a.check_Zc = False
         xd = x.to(dev).requires_grad_(True)
         y = a(ElectricField(xd, wavelengths=lams, spacing=0.5 * mm, device=dev)).data
         (gx,) = torch.autograd.grad(y, xd, g.to(dev))
-        assert rel_l2(y.detach().cpu(), yo.detach()) < tol, mode
-        assert rel_l2(gx.cpu(), gxo) < tol, mode
+        ey, eg = rel_l2(y.detach().cpu(), yo.detach()), rel_l2(gx.cpu(), gxo)
+        record("asm_config_sizes", N=N_, C=C, mode=mode, resolved=a.resolved_kernel_mode, y=ey, gx=eg)
+        assert ey < tol and eg < tol, mode
+
+
+@pytest.mark.parametrize("mode", ["auto", "cached"])
+def test_metric_shape_matches_oracle(mode, dev):
+    """The benchmarked configuration itself (bench.py: 4-level STE DOE fused into band-limited ASM, 2048^2 -> 4096^2 pad,
+    z = 100 mm), ONE wavelength, against the oracle on the CPU: field, gradient wrt the input field, gradient wrt the
+    DOE weights <= 1e-5 rel-L2; the level map bit-exact.  'auto' must resolve to the in-register H here -- it is what
+    bench.py times."""
+    from oracle import asm_oracle as AO, doe_oracle as DO
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, STEQuantizedDOELayer
+    n, lam, z, hmax, L = 2048, [1 * mm], 0.1, 1 * mm, 4
+    torch.manual_seed(0)
+    x = torch.randn(1, 1, n, n, dtype=torch.complex64)
+    torch.manual_seed(1)
+    doe = STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=0.5 * mm, doe_level=L, height_constraint_max=hmax, tolerance=None,
+                                    material=[2.66, 0.003]), {}, device=dev)
+    asm = ASM_prop(z_distance=z, device=dev, kernel_mode=mode)
+    asm.check_Zc = False
+    xd = x.to(dev).requires_grad_(True)
+    y = asm(doe(ElectricField(xd, wavelengths=lam, spacing=0.5 * mm, device=dev))).data
+    gx, gw = torch.autograd.grad(y, (xd, doe.weight_height_map), y.detach())        # the bench's loss gradient g = y
+    torch.cuda.synchronize()
+    if mode == "auto":
+        assert asm.resolved_kernel_mode == "inregister", asm.inregister_estimate
+    # oracle, same weights, fed the SAME upstream gradient (the GPU's y) so that gx / gw isolate the adjoint path
+    xr = x.clone().requires_grad_(True)
+    wr = doe.weight_height_map.detach().cpu().clone().requires_grad_(True)
+    h = DO.ste_quantize(DO.sigmoid_height(wr[0, 0], hmax), DO.linear_lut(hmax, L))
+    yo = AO.asm_forward(DO.modulate(xr, h, lam, 2.66, 0.003), lam, 0.5 * mm, z)
+    gxo, gwo = torch.autograd.grad(yo, (xr, wr), y.detach().cpu())
+    flips = int((doe.height_map.detach().cpu() != h.detach()).sum())
+    ey, egx, egw = rel_l2(y.detach().cpu(), yo.detach()), rel_l2(gx.cpu(), gxo), rel_l2(gw.cpu(), gwo)
+    record("metric_shape", mode=mode, resolved=asm.resolved_kernel_mode, y=ey, gx=egx, gw=egw, level_flips=flips,
+           inregister_estimate=asm.inregister_estimate)
+    assert flips == 0
+    assert ey < TOL and egx < TOL and egw < TOL
+
+
+def test_c3_czt_matches_oracle_on_the_tensor_cores(dev):
+    """BASELINE config 3 geometry, one wavelength: 2048^2 -> 1024^2 zoomed chirp-z propagation against the oracle's FFT
+    (Bluestein) form, forward and input gradient -- with proof that the tcgen05 kernel produced it: impl='tc' turns
+    ineligibility into an error, and the launch counters show tcgen05 launches and no CUDA-core GEMM launch."""
+    from oracle import czt_oracle as CO
+    from quantizationawarethzdoe_b200 import CZT_prop, ElectricField, _native as N, functional as Fn
+    torch.manual_seed(7)
+    n, M, lam = 2048, 1024, [1 * mm]
+    x = torch.randn(1, 1, n, n, dtype=torch.complex64)
+    gy = torch.randn(1, 1, M, M, dtype=torch.complex64)
+    xo = x.clone().requires_grad_(True)
+    yo = CO.czt_forward(xo, torch.tensor(lam), torch.tensor([0.5 * mm, 0.5 * mm]), torch.tensor(0.5), M, M, 0.1 * mm, 0.1 * mm)
+    (gxo,) = torch.autograd.grad(yo, xo, gy)
+    lib = N.lib()
+    tc0, simt0 = lib.thz_launch_count_class(8), lib.thz_launch_count_class(6)
+    old = Fn.TUNE["czt_impl"]
+    Fn.TUNE["czt_impl"] = "tc"
+    try:
+        czt = CZT_prop(z_distance=0.5, device=dev)
+        xd = x.to(dev).requires_grad_(True)
+        y = czt(ElectricField(xd, wavelengths=lam, spacing=0.5 * mm, device=dev), M, M, 0.1 * mm, 0.1 * mm).data
+        (gx,) = torch.autograd.grad(y, xd, gy.to(dev))
+        torch.cuda.synchronize()
+    finally:
+        Fn.TUNE["czt_impl"] = old
+    assert lib.thz_launch_count_class(8) - tc0 >= 4 and lib.thz_launch_count_class(6) == simt0
+    ey, eg = rel_l2(y.detach().cpu(), yo.detach()), rel_l2(gx.cpu(), gxo)
+    record("c3_czt", y=ey, gx=eg, tc_launches=lib.thz_launch_count_class(8) - tc0)
+    assert ey < TOL and eg < TOL
+
+
+def test_czt_impl_tc_is_never_silently_replaced(dev):
+    """impl='tc' on a call the tcgen05 kernel cannot serve (chirp filter shorter than 64) raises instead of switching."""
+    from quantizationawarethzdoe_b200 import CZT_prop, ElectricField, functional as Fn
+    x = torch.randn(1, 1, 12, 12, dtype=torch.complex64, device=dev)
+    old = Fn.TUNE["czt_impl"]
+    Fn.TUNE["czt_impl"] = "tc"
+    try:
+        with pytest.raises(NotImplementedError, match="not eligible"):
+            CZT_prop(z_distance=0.5, device=dev)(ElectricField(x, wavelengths=[1 * mm], spacing=0.5 * mm, device=dev), 8, 8, 0.1 * mm, 0.1 * mm)
+    finally:
+        Fn.TUNE["czt_impl"] = old
+
+
+def test_c4_three_layer_donn_chain_matches_oracle(dev):
+    """BASELINE config 4 layer stack at a small batch: 3 x (4-level STE DOE -> ASM 200 -> 400 pad), batch 8, loss
+    gradient g = y: output field and the weight gradients of ALL THREE layers against autograd through the oracle."""
+    from oracle import asm_oracle as AO, doe_oracle as DO
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, STEQuantizedDOELayer
+    n, B, lam, z, hmax, L = 200, 8, [1 * mm], 0.05, 1 * mm, 4
+    torch.manual_seed(3)
+    x = torch.randn(B, 1, n, n, dtype=torch.complex64)
+    g = torch.randn(B, 1, n, n, dtype=torch.complex64)
+    does, asms = [], []
+    for i in range(3):
+        torch.manual_seed(20 + i)
+        does.append(STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=0.5 * mm, doe_level=L, height_constraint_max=hmax,
+                                              tolerance=None, material=[2.66, 0.003]), {}, device=dev))
+        a = ASM_prop(z_distance=z, device=dev)
+        a.check_Zc = False
+        asms.append(a)
+    f = ElectricField(x.to(dev), wavelengths=lam, spacing=0.5 * mm, device=dev)
+    for d, a in zip(does, asms):
+        f = a(d(f))
+    y = f.data
+    gws = torch.autograd.grad(y, [d.weight_height_map for d in does], g.to(dev))
+    ws = [d.weight_height_map.detach().cpu().clone().requires_grad_(True) for d in does]
+    u = x
+    flips = 0
+    for d, w in zip(does, ws):
+        h = DO.ste_quantize(DO.sigmoid_height(w[0, 0], hmax), DO.linear_lut(hmax, L))
+        flips += int((d.height_map.detach().cpu() != h.detach()).sum())
+        u = AO.asm_forward(DO.modulate(u, h, lam, 2.66, 0.003), lam, 0.5 * mm, z)
+    gwo = torch.autograd.grad(u, ws, g)
+    errs = [rel_l2(a_.cpu(), b_) for a_, b_ in zip(gws, gwo)]
+    ey = rel_l2(y.detach().cpu(), u.detach())
+    record("c4_donn_chain", y=ey, gw1=errs[0], gw2=errs[1], gw3=errs[2], level_flips=flips, modes=[a.resolved_kernel_mode for a in asms])
+    assert flips == 0 and ey < TOL and max(errs) < TOL
+
+
+def test_workspace_survives_growth_after_graph_capture(dev):
+    """A captured step keeps the address of its scratch buffer; a later, larger call on the same stream must not free
+    that buffer: replay after growing the workspace, compare with eager."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField
+    n = 256
+    torch.manual_seed(0)
+    x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+    lam_t, sp_t = torch.tensor([1 * mm], device=dev), torch.tensor([0.5 * mm, 0.5 * mm], device=dev)
+    asm = ASM_prop(z_distance=0.1, device=dev)
+    asm.check_Zc = False
+    F = lambda: asm(ElectricField(x, wavelengths=lam_t, spacing=sp_t, device=dev)).data
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            eager = F().clone()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = F()
+        # a much larger call on the SAME stream regrows the cached workspace ...
+        big = ASM_prop(z_distance=0.1, device=dev)
+        big.check_Zc = False
+        xb = torch.randn(2, 1, 1024, 1024, dtype=torch.complex64, device=dev)
+        big(ElectricField(xb, wavelengths=lam_t, spacing=sp_t, device=dev))
+        junk = [torch.full((1 << 20,), 7.0, device=dev) for _ in range(8)]     # ... and the allocator gets a chance to reuse freed blocks
+        g.replay()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    del junk
 
 
 def test_full_size_properties(dev):
@@ -147,6 +315,8 @@ def test_doe_layers_match_reference_vectors(name, dev):
         assert rel_l2(hm, g["height_map"]) < 1e-6
     else:
         assert int(mism.sum()) <= 2, "level flips: %d" % int(mism.sum())
+    record("doe_golden", fixture=name, level_flips=int(mism.sum()), y=rel_l2(y.detach().cpu(), g["y"]),
+           gw=(rel_l2(gw.cpu(), g["gw"]) if g["gw"].abs().max() > 0 else 0.0))
     if int(mism.sum()) == 0 or name in ("doe_fullprecision", "doe_psq", "doe_gumbel_v3_02", "doe_gumbel_v3_05"):
         assert rel_l2(y.detach().cpu(), g["y"]) < TOL
         if g["gw"].abs().max() > 0:
@@ -216,6 +386,48 @@ def test_level_indices_bit_exact_given_identical_inputs(dev):
     assert nearest_idx(n["kat_x"].to(dev), n["mid"]).tolist() == [0, 0, 0, 1, 1, 1, 2, 3, 0, 0, 0, 0]
 
 
+@pytest.mark.parametrize("name", ["gumbel_hard", "gumbel_soft", "plain_hard", "plain_soft"])
+def test_softmax_quantization_matches_reference(name, dev):
+    """Quantization(method='*softmax*' | '*gumbel*') -> SoftmaxBasedQuantization + score_thickness
+    (Components/quantization.py:36-55, 128-161, 164-207): forward vs the reference's own output, gradient vs the oracle's
+    out-of-place restatement (the reference's backward raises), budgeted by the fp32-vs-float64 distance of that gradient."""
+    from quantizationawarethzdoe_b200.Components.quantization import Quantization
+    g = golden("quant_softmax")
+    method = "gumbel_softmax" if "gumbel" in name else "softmax"
+    qz = Quantization(method=method, max_thickness=g["hmax"], num_bits=2, dev=dev, tau_min=g["tau_min"], tau_max=g["tau_max"], c=g["c"])
+    if "gumbel" in name:
+        qz.quan_fn.gumbel_noise = g["noise_" + name].to(dev)
+    t = g["thickness"].to(dev).requires_grad_(True)
+    q = qz(t, iter_frac=g["frac_" + name], hard="hard" in name)
+    (gt,) = torch.autograd.grad(q, t, g["gq"].to(dev))
+    ref_g, g64 = g["gt_" + name], g["gt64_" + name]
+    budget = max(TOL, 2.0 * rel_l2(ref_g.double(), g64))
+    eq, eg = rel_l2(q.detach().cpu(), g["q_" + name]), rel_l2(gt.cpu(), ref_g)
+    record("quant_softmax", case=name, q=eq, gt=eg, gt_budget=budget, level_flips=int((q.detach().cpu() != g["q_" + name]).sum()) if "hard" in name else -1)
+    assert q.shape == g["q_" + name].shape
+    assert eq < 1e-6 and eg < budget
+    if "hard" in name:      # the selected LEVEL is exact; the value carries the ulps of (onehot + y) - y, which depend on libm's exp
+        lut = g["lut"][:-1]
+        lv = lambda v: torch.argmin((v.reshape(-1, 1) - lut[None, :]).abs(), dim=1)
+        assert torch.equal(lv(q.detach().cpu()), lv(g["q_" + name]))
+
+
+def test_score_thickness_and_per_instance_luts(dev):
+    from quantizationawarethzdoe_b200.Components.quantization import Quantization, score_thickness
+    torch.manual_seed(3)
+    t = (torch.rand(2, 1, 33, 17) * 1.2e-3 - 1e-4)
+    lut = torch.linspace(0, 1e-3, 5)[:-1]
+    diff = t - lut.reshape(1, -1, 1, 1)
+    diff = diff / torch.max(torch.abs(diff))
+    ref = torch.sigmoid(2.5 * diff) * (1 - torch.sigmoid(2.5 * diff)) * 4
+    assert rel_l2(score_thickness(t.to(dev), lut.to(dev), 2.5).cpu(), ref) < 2e-6
+    # two quantizers with different LUTs coexist (ADVICE r1: the LUT used to be process-global)
+    a = Quantization(method="nn", max_thickness=1.0, num_bits=2, dev=dev)
+    b = Quantization(method="nn", max_thickness=2.0, num_bits=2, dev=dev)
+    x = torch.tensor([0.3, 0.9], device=dev).reshape(1, 1, 1, 2)
+    assert a(x, iter_frac=0.1).tolist() == [0.25, 0.0] and b(x, iter_frac=0.1).tolist() == [0.5, 1.0]
+
+
 @pytest.mark.parametrize("H,W", [(64, 64), (60, 100), (1000, 1000), (2048, 1024)])
 def test_fft2_and_shifted_helpers(H, W, dev):
     from quantizationawarethzdoe_b200 import functional as Fn
@@ -265,10 +477,12 @@ def test_static_fast_path_agrees_with_generic_engine(H, W, scale, dev, monkeypat
     assert rel_l2(outs[0][1], outs[1][1]) < 1e-6
 
 
-@pytest.fixture(params=["tc", "simt"])
+@pytest.fixture(params=["auto", "simt"])
 def czt_impl(request, monkeypatch):
-    """Both Toeplitz-GEMM implementations: the tcgen05 3xTF32 kernel (default) and the CUDA-core baseline."""
-    monkeypatch.setenv("THZ_CZT_IMPL", request.param)
+    """Both Toeplitz-GEMM implementations: 'auto' = the tcgen05 3xTF32 kernel wherever it is eligible (the small reference
+    vectors include chirp filters shorter than 64, which only the CUDA-core kernel serves) and the CUDA-core baseline."""
+    from quantizationawarethzdoe_b200 import functional as Fn
+    monkeypatch.setitem(Fn.TUNE, "czt_impl", request.param)
     return request.param
 
 
@@ -312,6 +526,8 @@ def test_czt_adjoint_and_oracle(dev, czt_impl):
     Ax = czt2(ElectricField(xa, wavelengths=[1 * mm], spacing=0.5 * mm, device=dev), M, M, 0.1 * mm, 0.1 * mm).data
     (AHy,) = torch.autograd.grad(Ax, xa, yv)
     lhs, rhs = torch.sum(Ax.detach().conj() * yv), torch.sum(xa.detach().conj() * AHy)
+    record("czt_adjoint_identity", impl=czt_impl, rel=float(abs(lhs - rhs) / abs(lhs)),
+           rel_to_norms=float(abs(lhs - rhs) / (Ax.detach().norm() * yv.norm())))
     assert abs(lhs - rhs) / abs(lhs) < 1e-4
 
 
@@ -328,8 +544,9 @@ def test_czt_tensor_core_kernel_agrees_with_cuda_core_kernel(dev, monkeypatch):
     torch.manual_seed(9)
     x = torch.randn(1, 2, 1024, 1024, dtype=torch.complex64, device=dev)
     outs = {}
+    from quantizationawarethzdoe_b200 import functional as Fn
     for impl in ("tc", "simt"):
-        monkeypatch.setenv("THZ_CZT_IMPL", impl)
+        monkeypatch.setitem(Fn.TUNE, "czt_impl", impl)
         czt = CZT_prop(z_distance=0.5, device=dev)
         f = ElectricField(x, wavelengths=[1 * mm, 1.05 * mm], spacing=0.5 * mm, device=dev)
         outs[impl] = czt(f, 512, 512, 0.1 * mm, 0.1 * mm).data

@@ -188,3 +188,14 @@ def test_gaussian_source_mirror_matches_reference_field():
     # fitted waist: a degree-5 polynomial in fp32 with heavy cancellation, host-libm dependent at the 1e-5 level
     assert rel_l2(src().data, g["source"]) <= 1e-4
     assert torch.equal(src().data, src().data)               # idempotent (the reference's forward is not)
+
+
+@pytest.mark.parametrize("name", ["gumbel_hard", "gumbel_soft", "plain_hard", "plain_soft"])
+def test_softmax_quantizer_oracle_matches_reference_forward(name):
+    """SoftmaxBasedQuantization / score_thickness restatement vs the reference's own forward output, bit for bit (the
+    reference's backward raises -- in-place normalisation, quantization.py:41 -- so only the forward is reference-pinned)."""
+    g = golden("quant_softmax")
+    noise = g.get("noise_" + name)
+    tau = torch.tensor(g["tau_" + name], dtype=torch.float32)
+    q = DO.softmax_quantize(g["thickness"], g["lut"][:-1], tau, g["tau_max"], g["c"], gumbel_noise=noise, hard="hard" in name)
+    assert torch.equal(q.squeeze(0, 1), g["q_" + name])
