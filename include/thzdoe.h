@@ -141,6 +141,10 @@ typedef struct thz_asm_desc {
        the 32 lanes of a warp read 512 contiguous bytes instead of 32 different cache lines.  Needs thz_fft_is_static(Hp). */
     int32_t tf_row_chunked;
     int32_t reserved2;
+    /* doe_mode 1 only.  0: one height map for every batch entry.  Else: floats between the maps of consecutive batch
+       entries, doe_hmap = float32 [B][inH][inW] -- B candidate DOEs evaluated in one pass (loss-landscape sweeps,
+       VisTools/calc_loss.py:8-55).  The adjoint (doe_mode 2) takes a shared map only. */
+    int64_t doe_hmap_bstride;
 } thz_asm_desc;
 
 /* Bytes of `ws` a call with this descriptor needs (uses B, C, inH, outH, Hp, Wp, bc_chunk, stages, slab_parts): one
@@ -302,6 +306,11 @@ int thz_field_mul(const void* x, const void* m, void* y, int32_t BC, int32_t C, 
                   int32_t m_real, int32_t conj_m, void* stream);
 int thz_normmse_loss(const void* y, const void* target, int32_t B, uint64_t n_per_b, void* scratch, void* loss,
                      void* gy, void* stream);
+/* thz_normmse_loss_each: losses[b] = mean((|y_b|^2 / max |y_b|^2 - target)^2) for B candidate outputs at once -- the loss
+ * of VisTools/calc_loss.py:35-39 per grid point of a loss-landscape sweep.  y complex64 [B, n_per_b]; target float32
+ * [n_per_b] (target_shared = 1) or [B, n_per_b]; scratch >= 8*B bytes; losses float32 [B] (overwritten). */
+int thz_normmse_loss_each(const void* y, const void* target, int32_t target_shared, int32_t B, uint64_t n_per_b, void* scratch,
+                          void* losses, void* stream);
 int thz_adam_step(void* p, const void* g, void* m, void* v, void* step, uint64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int32_t decoupled, int32_t advance, void* stream);
 

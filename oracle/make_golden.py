@@ -363,6 +363,78 @@ def gen_setup(R):
          loss=loss, gw=gw, height_map=doe.height_map.detach(), wavelength=np.float64(lam), spacing=np.float64(dxy))
 
 
+class _FakeH5File:
+    """Just enough of h5py.File for the reference's VisTools/calc_loss.py (h5py is not installed here): datasets are numpy
+    arrays in a per-path dict; f[k] = arr, f[k][:], f[k][:] = arr, flush(), context manager."""
+    store = {}
+
+    def __init__(self, path, mode="r"):
+        self.d = _FakeH5File.store.setdefault(path, {}) if mode != "w" else _FakeH5File.store.__setitem__(path, {}) or _FakeH5File.store[path]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def __setitem__(self, k, v):
+        self.d[k] = np.array(v)
+
+    def __getitem__(self, k):
+        return self.d[k]
+
+    def flush(self):
+        pass
+
+
+def gen_landscape(R):
+    """The reference's own calulate_single_element_loss_landscape (VisTools/calc_loss.py:8-55), unmodified, on a small
+    single-DOE system built from the reference's modules -- run over an in-memory stand-in for h5py.  A non-square grid
+    (5 x 4) pins the reference's index convention (meshgrid(x, y) coordinates written into an (xnum, ynum) array)."""
+    import importlib
+    import types
+    fake = types.ModuleType("h5py")
+    fake.File = _FakeH5File
+    sys.modules["h5py"] = fake
+    CL = importlib.import_module("VisTools.calc_loss")
+    importlib.reload(CL)
+    n, lam, dxy = 24, 1 * mm, 0.5 * mm
+    torch.manual_seed(51)
+    x = torch.randn(1, 1, n, n, dtype=torch.complex64)
+
+    class Setup(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.input_field = R.ElectricField(data=x, wavelengths=lam, spacing=dxy)
+            with quiet():
+                self.doe = R.QD.STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=dxy, doe_level=4, look_up_table=None, num_unit=None,
+                                                          height_constraint_max=1 * mm, tolerance=None, material=[2.66, 0.03]), {})
+                self.asm_prop3 = R.ASM_prop(z_distance=0.05, bandlimit_type='exact', padding_scale=None, bandlimit_kernel=True)
+
+        def forward(self, iter_frac):
+            return self.asm_prop3(self.doe(self.input_field, iter_frac))
+
+    torch.manual_seed(52)
+    model = Setup()
+    w0 = [p.data.clone() for p in model.parameters()]
+    torch.manual_seed(53)
+    directions = []
+    for _ in range(2):
+        d = [torch.randn(w.size()) for w in w0]
+        for di, wi in zip(d, w0):
+            di.mul_(wi.norm() / (di.norm() + 1e-10))
+        directions.append(d)
+    target = torch.rand(1, 1, n, n)
+    args = types.SimpleNamespace(xmin=-1.0, xmax=1.0, xnum=5, ymin=-0.5, ymax=0.5, ynum=4)
+    with quiet():
+        path = CL.calulate_single_element_loss_landscape(args, model, target, loss_f=torch.nn.MSELoss(), directions=directions,
+                                                         save_path="/tmp/thz_landscape_golden")
+    d = _FakeH5File.store[path]
+    save("landscape_single_doe", x=x, w0=w0[0], dx=directions[0][0], dy=directions[1][0], target=target, wavelength=np.float64(lam),
+         spacing=np.float64(dxy), z=np.float64(0.05), xcoordinates=d["xcoordinates"], ycoordinates=d["ycoordinates"], loss=d["loss"],
+         args=np.array([args.xmin, args.xmax, args.xnum, args.ymin, args.ymax, args.ynum]), nparams=np.int64(len(w0)))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = import_reference()
@@ -375,3 +447,4 @@ if __name__ == "__main__":
     gen_rsc(R)
     gen_elements(R)
     gen_setup(R)
+    gen_landscape(R)

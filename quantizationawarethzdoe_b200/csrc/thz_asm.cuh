@@ -29,7 +29,14 @@ struct DoeArgs {
     const float* hmap;        // [inH][inW] height map, NULL = no DOE
     const float4* coef;       // [C] {k_c, tand, sqrt(eps), sqrt(eps)-1}
     float base;               // BASE_PLANE_THICKNESS (Components/QuantizedDOE.py:23)
+    int b0;                   // batch entry of the chunk's first field (f0 / C)
+    long long hstride;        // 0: one map for every batch entry; else floats between the maps of consecutive batch entries
+                              // (forward only: a sweep of DOE candidates over one input field)
 };
+// height map of field i of a chunk whose first field has wavelength index c0 (batch entry b0 + (c0 + i) / C)
+THZ_HD const float* thz_doe_map(const DoeArgs& d, int c0, int C, int i) {
+    return d.hstride ? d.hmap + (size_t)(d.b0 + (c0 + i) / C) * (size_t)d.hstride : d.hmap;
+}
 
 // DOE transmission p = exp(-0.5 k (h+b) tand sqrt(eps)) * exp(-i k (h+b) (sqrt(eps)-1)), evaluated in the
 // reference's fp32 rounding order (Components/QuantizedDOE.py:73-77).
@@ -121,7 +128,7 @@ THZ_HD void k1_load(const RowFwdArgs& a, cpx* s, int bx, int tid, int nthreads) 
         const float* hr = nullptr;
         if (a.doe.hmap) {
             cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
-            hr = a.doe.hmap + (size_t)r * a.inW;
+            hr = thz_doe_map(a.doe, a.c0, a.C, f) + (size_t)r * a.inW;
         }
         for (int p = tid; p < a.Wp; p += nthreads) {
             const int c = p - a.in_c0;

@@ -40,6 +40,7 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     if (d->doe_mode < 0 || d->doe_mode > 2) return THZ_E_SHAPE;
     if (d->doe_mode != 0 && (!d->doe_hmap || !d->doe_coef)) return THZ_E_NULL;
     if ((st & 4) && d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
+    if (d->doe_hmap_bstride < 0 || (d->doe_hmap_bstride != 0 && d->doe_mode != 1)) return THZ_E_SHAPE;   // per-entry maps: forward only
     if ((st & 4) && d->doe_mode != 2 && !d->y) return THZ_E_NULL;
     if (d->slab_parts > 1) {
         if (d->slab_parts > 8 || (st != 1 && st != 2 && st != 4) || d->slab_rows < 1 || d->slab_row0 < 0) return THZ_E_SHAPE;
@@ -153,6 +154,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a1.doe.hmap = d->doe_mode == 1 ? (const float*)d->doe_hmap : nullptr;
     a1.doe.coef = (const float4*)d->doe_coef;
     a1.doe.base = d->doe_base;
+    a1.doe.b0 = f0 / d->C;
+    a1.doe.hstride = d->doe_mode == 1 ? d->doe_hmap_bstride : 0;
     a1.conj_in = 0;
     memset(&a1.slab, 0, sizeof(a1.slab));
     memset(&L->k3.slab, 0, sizeof(L->k3.slab));
@@ -237,6 +240,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a3.doe.hmap = d->doe_mode == 2 ? (const float*)d->doe_hmap : nullptr;
     a3.doe.coef = (const float4*)d->doe_coef;
     a3.doe.base = d->doe_base;
+    a3.doe.b0 = 0;
+    a3.doe.hstride = 0;
     a3.xsaved = d->doe_mode == 2 ? (const cpx*)d->doe_xsaved + (size_t)f0 * d->outH * d->outW : nullptr;
     a3.gh = (float*)d->doe_gh;
     {

@@ -83,7 +83,7 @@ THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
             ld.xr = a.x + (size_t)gl * a.inW;
             if (a.doe.hmap) {
                 ld.cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
-                ld.hr = a.doe.hmap + (size_t)r * a.inW;
+                ld.hr = thz_doe_map(a.doe, a.c0, a.C, f) + (size_t)r * a.inW;
             }
         }
         if (a.half_in) p2_first_stage_from<N, 1, true>(s + line * PITCH, j, a.tw, ld);
@@ -109,7 +109,7 @@ THZ_HD void p2k1_prefetch(const RowFwdArgs& a, cpx* xs, float* hs, int grp, int 
             for (int c = tid; c < a.inW; c += nt) thz_cp_async8(xd + c, xr + c);
         }
         if (a.doe.hmap) {
-            const float* hr = a.doe.hmap + (size_t)(gl % a.inH) * a.inW;
+            const float* hr = thz_doe_map(a.doe, a.c0, a.C, gl / a.inH) + (size_t)(gl % a.inH) * a.inW;
             float* hd = hs + (size_t)line * a.inW;
             if ((a.inW & 3) == 0) {
                 for (int c = tid * 4; c < a.inW; c += nt * 4) thz_cp_async16(hd + c, hr + c);

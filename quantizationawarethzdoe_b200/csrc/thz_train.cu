@@ -128,6 +128,61 @@ extern "C" int thz_normmse_loss(const void* y, const void* target, int32_t B, ui
     return THZ_OK;
 }
 
+// ------------------------------------------------------------------------------- per-entry losses (loss-landscape sweeps)
+// losses[b] = mean_i (I_b[i] / max_i I_b[i] - target[i])^2: what VisTools/calc_loss.py:35-39 evaluates once per grid point
+// (output / torch.max(output), then nn.MSELoss), for B candidate outputs at once; the target may be shared by all entries.
+__global__ void __launch_bounds__(256) thz_k_normmse_each(const cpx* __restrict__ y, const float* __restrict__ target,
+                                                          size_t t_bstride, const unsigned long long* __restrict__ key,
+                                                          float* __restrict__ losses, size_t n_per_b, float inv_n) {
+    const int b = blockIdx.y;
+    const float m = __uint_as_float((unsigned)(key[b] >> 32));
+    const cpx* yb = y + (size_t)b * n_per_b;
+    const float* tb = target + (size_t)b * t_bstride;
+    float l = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_b; i += (size_t)gridDim.x * blockDim.x) {
+        const cpx v = yb[i];
+        const float a = hypotf(v.x, v.y);
+        const float diff = __fdiv_rn(a * a, m) - tb[i];
+        l = fmaf(diff, diff, l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    __shared__ float sl[8];
+    if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) l += sl[w];
+        atomicAdd(losses + b, l * inv_n);
+    }
+}
+
+extern "C" int thz_normmse_loss_each(const void* y, const void* target, int32_t target_shared, int32_t B, uint64_t n_per_b,
+                                     void* scratch, void* losses, void* stream_) {
+    ThzDeviceGuard dev_guard(y);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0) return thz_set_error(THZ_E_SHAPE, "thz_normmse_loss_each: negative batch");
+    if (B == 0 || n_per_b == 0) return THZ_OK;
+    if (!y || !target || !scratch || !losses) return thz_set_error(THZ_E_NULL, "thz_normmse_loss_each: null pointer");
+    if (n_per_b > 0xFFFFFFFFull) return thz_set_error(THZ_E_UNSUPPORTED, "thz_normmse_loss_each: more than 2^32 samples per entry");
+    unsigned long long* key = (unsigned long long*)scratch;     // [B] keys
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)B * 8, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(losses, 0, (size_t)B * sizeof(float), stream);
+    if (e != cudaSuccess) return thz_set_cuda_error("thz_normmse_loss_each: memset", e);
+    const size_t want = (n_per_b + 255) / 256;
+    const size_t cap = (size_t)thz_sm_count() * 8 / (size_t)(B < 8 ? B : 8) + 1;
+    dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)B);
+    thz_launch_begin(stream, THZ_KC_TRAIN);
+    thz_k_intensity_max<<<grid, 256, 0, stream>>>((const cpx*)y, key, (size_t)n_per_b);
+    thz_launch_end(stream, THZ_KC_TRAIN);
+    thz_launch_begin(stream, THZ_KC_TRAIN);
+    thz_k_normmse_each<<<grid, 256, 0, stream>>>((const cpx*)y, (const float*)target, target_shared ? 0 : (size_t)n_per_b, key,
+                                                 (float*)losses, (size_t)n_per_b, (float)(1.0 / (double)n_per_b));
+    thz_launch_end(stream, THZ_KC_TRAIN);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return thz_set_cuda_error("thz_normmse_loss_each", e);
+    return THZ_OK;
+}
+
 // ------------------------------------------------------------------------------- Adam / AdamW
 // torch.optim.Adam (single-tensor path): m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
 // p.addcdiv_(m, sqrt(v)/sqrt(1-b2^t) + eps, value = -lr/(1-b1^t)); weight decay: g += wd p (Adam) or p *= 1 - lr wd

@@ -80,7 +80,7 @@ class AsmPlan:
         self.tw_w = N.twiddles(Wp, device)
         self._descs = {}
 
-    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None):
+    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None, hmap_bstride=0):
         """One thz_asm_propagate call.  Forward: x [B,C,H,W] -> y [B,C,outH,outW].
         Adjoint (conj=1): x = grad [B,C,outH,outW] -> y [B,C,H,W] (regions swapped)."""
         B, C = self.B, self.C
@@ -105,6 +105,7 @@ class AsmPlan:
         ws = _workspace(elems, x.device)
         d.x, d.y, d.ws, d.ws_bytes = N.ptr(x), N.ptr(y), N.ptr(ws), ws.numel() * 8
         d.doe_hmap, d.doe_coef, d.doe_xsaved, d.doe_gh = N.ptr(hmap), N.ptr(coef), N.ptr(xsaved), N.ptr(gh)
+        d.doe_hmap_bstride = int(hmap_bstride)
         _asm_call(d, x.device)
         return y
 
@@ -162,6 +163,24 @@ class DoeAsmFn(torch.autograd.Function):
                                                  N.ptr(gx), None, x.shape[0], x.shape[1], x.shape[2], x.shape[3],
                                                  N.current_stream_ptr(g.device)), "thz_doe_modulate_bwd")
         return gx, gh, None, None
+
+
+def doe_asm_sweep(x, hmaps, prop, coef, spacing, wavelengths):
+    """B candidate DOEs over ONE input field in a single fused pass (forward only; loss-landscape sweeps):
+    x complex64 [1,C,H,W], hmaps float32 [Bc,H,W] -> prop(x * p(hmaps[b])) for every b, complex64 [Bc,C,outH,outW].
+    The field is broadcast over the candidates; the height map is per entry (thz_asm_desc.doe_hmap_bstride)."""
+    x = _c64(x, "field.data")
+    N.require_cuda(hmaps, "height maps")
+    hmaps = hmaps.to(torch.float32).contiguous()
+    Bc, H, W = hmaps.shape
+    if x.shape[0] != 1 or tuple(x.shape[-2:]) != (H, W):
+        raise ValueError("doe_asm_sweep needs one input field [1,C,H,W] matching the height maps")
+    C = x.shape[1]
+    plan = prop._get_plan(Bc, C, H, W, spacing, wavelengths, x.device)
+    xb = x.expand(Bc, C, H, W).contiguous()
+    y = torch.empty(Bc, C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
+    plan.run(xb, y, conj=0, doe_mode=1, hmap=hmaps, coef=coef, hmap_bstride=H * W)
+    return y
 
 
 class DoeModulateFn(torch.autograd.Function):

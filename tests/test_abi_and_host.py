@@ -37,8 +37,8 @@ def test_library_exports_every_declared_symbol(lib):
 def test_descriptor_layout_matches_header(tmp_path):
     """ctypes mirrors vs the C header: sizes and field offsets as gcc lays the structs out."""
     # thz_asm_desc: 12 int32, 2 ptr, 2 int32, 4 ptr, int32+float, 4 ptr, 2 ptr, ptr, u64, 4 int32, 4 int32, 8 ptr
-    assert ctypes.sizeof(N.AsmDesc) == 12 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 4 * 4 + 4 * 4 + 8 * 8 + 2 * 4
-    fields = ["x", "tf_mode", "tf_table", "doe_base", "doe_gh", "ws_bytes", "stages", "slab_parts", "slab_ptrs", "tf_row_chunked"]
+    assert ctypes.sizeof(N.AsmDesc) == 12 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 4 * 4 + 4 * 4 + 8 * 8 + 2 * 4 + 8
+    fields = ["x", "tf_mode", "tf_table", "doe_base", "doe_gh", "ws_bytes", "stages", "slab_parts", "slab_ptrs", "tf_row_chunked", "doe_hmap_bstride"]
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "thzdoe.h"\nint main(void) {\n'
                    '  printf("%zu %zu", sizeof(thz_asm_desc), sizeof(thz_toeplitz_gemm_desc));\n' +
@@ -160,3 +160,30 @@ def test_row_thresholds_binary_search_equals_dense_evaluation(lib):
         assert fast is not None and dense is not None
         assert torch.equal(fast, dense), (Hp, Wp, bt)                                    # C helper (host code of the .so)
         assert torch.equal(AH._tf_row_thresholds_numpy(rv, cv, sc), dense), (Hp, Wp, bt)  # numpy restatement
+
+
+def test_loss_landscape_host_helpers(tmp_path):
+    """Surface-file layout and the reference's index convention (VisTools/calc_loss.py:67-98), no GPU involved."""
+    import types
+    from quantizationawarethzdoe_b200.VisTools import calc_loss as CL
+    args = types.SimpleNamespace(xmin=-1.0, xmax=1.0, xnum=5, ymin=-0.5, ymax=0.5, ynum=4)
+    path = CL.setup_surface_file(args, str(tmp_path))
+    d = CL.read_surface_file(path)
+    assert d["loss"].shape == (5, 4) and (d["loss"] == -1).all()
+    assert np.allclose(d["xcoordinates"], np.linspace(-1, 1, 5)) and np.allclose(d["ycoordinates"], np.linspace(-0.5, 0.5, 4))
+    inds, coords = CL.get_indices(d["loss"], d["xcoordinates"], d["ycoordinates"])
+    assert inds.tolist() == list(range(20))
+    # flat index i = iy * xnum + ix is evaluated at (x[ix], y[iy]) -- np.meshgrid(x, y) order -- whatever the loss array's shape
+    assert np.allclose(coords[7], [d["xcoordinates"][2], d["ycoordinates"][1]])
+    d["loss"].ravel()[inds[:3]] = [0.5, 0.25, 0.125]
+    CL._write_losses(path, d["loss"])
+    d2 = CL.read_surface_file(path)
+    assert d2["loss"][0, :3].tolist() == [0.5, 0.25, 0.125]
+    inds2, _ = CL.get_indices(d2["loss"], d2["xcoordinates"], d2["ycoordinates"])
+    assert inds2.tolist() == list(range(3, 20))                 # evaluated points are skipped on a re-run
+    m = torch.nn.Linear(2, 2, bias=False)
+    w0 = [p.data.clone() for p in m.parameters()]
+    CL.overwrite_weights(m, w0, [[torch.ones(2, 2)], [2 * torch.ones(2, 2)]], (0.5, -0.25))
+    assert torch.allclose(m.weight.data, w0[0])                 # 0.5 * 1 - 0.25 * 2 = 0
+    CL.overwrite_weights(m, w0, [[torch.ones(2, 2)], [2 * torch.ones(2, 2)]], (1.0, 1.0))
+    assert torch.allclose(m.weight.data, w0[0] + 3)

@@ -3,6 +3,7 @@ C ABI, against (a) the golden vectors produced by the reference and (b) the orac
 
 Tolerances (north_star): rel-L2 <= 1e-5 on complex64 fields and gradients; level indices bit-exact.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -292,6 +293,29 @@ def _doe_layer(name, g, dev):
     return layer, getattr(layer, pname), kw
 
 
+def _fp32_gradient_budget(name, g):
+    """Tolerance for a gradient that runs through sigmoid' x softmax chains (PSQ, score-Gumbel): the reference's own fp32
+    autograd result sits up to 1.5e-5 from the float64 evaluation of the same formulas (measured here, on the CPU, with the
+    oracle in float64), so the bar is max(1e-5, 2 x that distance) -- 1e-5 wherever fp32 itself is that good."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle_golden import _height_for
+    from oracle import asm_oracle as AO, doe_oracle as DO
+    if name in ("doe_gumbel_v1",) or g["gw"].abs().max() == 0:       # v1 has no oracle restatement; measured 3e-6
+        return TOL
+    g64 = dict(g)
+    g64["w"] = g["w"].double()
+    for k in ("noise", "lut"):
+        if k in g:
+            g64[k] = g[k].double()
+    w, h = _height_for(name, g64)
+    u = DO.modulate(g["x"].to(torch.complex128), h, g["wavelengths"].float(), g["material"][0].float(), g["material"][1].float())
+    y = AO.asm_forward(u, g["wavelengths"].float(), g["spacing"].float(), g["z"])
+    (gw64,) = torch.autograd.grad(y, w, g["g"].to(y.dtype))
+    return max(TOL, 2.0 * rel_l2(g["gw"].double(), gw64))
+
+
 @pytest.mark.parametrize("name", [n for n in golden_names("doe_") if n != "doe_fix_edoe4"])
 def test_doe_layers_match_reference_vectors(name, dev):
     """Every DOE layer: height map (levels bit-exact up to sigmoid ulps, counted), modulated field,
@@ -310,25 +334,27 @@ def test_doe_layers_match_reference_vectors(name, dev):
     (gw,) = torch.autograd.grad(y, param, g["g"].to(dev))
     hm = layer.height_map.detach().cpu()
     mism = (hm != g["height_map"])
-    # CPU and GPU sigmoid/exp differ by ulps: allow a handful of level flips, require the rest bit-exact
-    if name in ("doe_fullprecision", "doe_psq", "doe_gumbel_v3_02", "doe_gumbel_v3_05"):
+    continuous = name in ("doe_fullprecision", "doe_psq", "doe_gumbel_v3_02", "doe_gumbel_v3_05")    # no level selection / blended
+    # level selection is integer work: every discrete map must equal the reference's bit for bit
+    if continuous:
         assert rel_l2(hm, g["height_map"]) < 1e-6
     else:
-        assert int(mism.sum()) <= 2, "level flips: %d" % int(mism.sum())
-    record("doe_golden", fixture=name, level_flips=int(mism.sum()), y=rel_l2(y.detach().cpu(), g["y"]),
-           gw=(rel_l2(gw.cpu(), g["gw"]) if g["gw"].abs().max() > 0 else 0.0))
-    if int(mism.sum()) == 0 or name in ("doe_fullprecision", "doe_psq", "doe_gumbel_v3_02", "doe_gumbel_v3_05"):
-        assert rel_l2(y.detach().cpu(), g["y"]) < TOL
-        if g["gw"].abs().max() > 0:
-            assert rel_l2(gw.cpu(), g["gw"]) < (5 * TOL if "gumbel" in name else TOL)
+        assert int(mism.sum()) == 0, "level flips: %d" % int(mism.sum())
+    ey = rel_l2(y.detach().cpu(), g["y"])
+    egw = rel_l2(gw.cpu(), g["gw"]) if g["gw"].abs().max() > 0 else 0.0
+    budget = _fp32_gradient_budget(name, g)
+    record("doe_golden", fixture=name, level_flips=(-1 if continuous else int(mism.sum())), y=ey, gw=egw, gw_budget=budget)
+    assert ey < TOL
+    assert egw < budget
     # (2) stand-alone modulation kernel (materialised .data) and its own backward
     u2 = layer(f, **kw)
     ud = u2.data
-    if int(mism.sum()) == 0 or name in ("doe_fullprecision", "doe_psq", "doe_gumbel_v3_02", "doe_gumbel_v3_05"):
-        assert rel_l2(ud.detach().cpu(), g["u"]) < TOL
-        (gw2,) = torch.autograd.grad(ud, param, g["g"].to(dev))
-        if g["gw_modulate_only"].abs().max() > 0:
-            assert rel_l2(gw2.cpu(), g["gw_modulate_only"]) < (5 * TOL if "gumbel" in name else TOL)
+    assert rel_l2(ud.detach().cpu(), g["u"]) < TOL
+    (gw2,) = torch.autograd.grad(ud, param, g["g"].to(dev))
+    if g["gw_modulate_only"].abs().max() > 0:
+        e2 = rel_l2(gw2.cpu(), g["gw_modulate_only"])
+        record("doe_golden_modulate_only", fixture=name, gw=e2, gw_budget=budget)
+        assert e2 < budget
 
 
 def test_fix_doe_element_on_reference_height_map(dev):
@@ -425,7 +451,7 @@ def test_score_thickness_and_per_instance_luts(dev):
     a = Quantization(method="nn", max_thickness=1.0, num_bits=2, dev=dev)
     b = Quantization(method="nn", max_thickness=2.0, num_bits=2, dev=dev)
     x = torch.tensor([0.3, 0.9], device=dev).reshape(1, 1, 1, 2)
-    assert a(x, iter_frac=0.1).tolist() == [0.25, 0.0] and b(x, iter_frac=0.1).tolist() == [0.5, 1.0]
+    assert a(x, iter_frac=0.1).reshape(-1).tolist() == [0.25, 0.0] and b(x, iter_frac=0.1).reshape(-1).tolist() == [0.5, 1.0]
 
 
 @pytest.mark.parametrize("H,W", [(64, 64), (60, 100), (1000, 1000), (2048, 1024)])
@@ -528,7 +554,7 @@ def test_czt_adjoint_and_oracle(dev, czt_impl):
     lhs, rhs = torch.sum(Ax.detach().conj() * yv), torch.sum(xa.detach().conj() * AHy)
     record("czt_adjoint_identity", impl=czt_impl, rel=float(abs(lhs - rhs) / abs(lhs)),
            rel_to_norms=float(abs(lhs - rhs) / (Ax.detach().norm() * yv.norm())))
-    assert abs(lhs - rhs) / abs(lhs) < 1e-4
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5        # measured 3-5e-7 (relative to |<Ax, y>|, itself ~1e-2 of |Ax| |y|)
 
 
 def test_czt_rejects_non_square_output_like_the_reference(dev):
@@ -792,3 +818,51 @@ def test_notebook_setup_end_to_end(dev):
     (gw,) = torch.autograd.grad(loss, doe.weight_height_map)
     assert abs(float(loss) - g["loss"]) <= 1e-5 * abs(g["loss"])
     assert rel_l2(gw.cpu(), g["gw"]) < 2e-5
+
+
+# ------------------------------------------------------------------------------- loss-landscape sweep
+@pytest.mark.parametrize("batched", [True, False])
+def test_loss_landscape_matches_the_reference_run(batched, dev, tmp_path):
+    """calulate_single_element_loss_landscape on the small single-DOE system of tests/golden/landscape_single_doe.npz, whose
+    `loss` array was produced by the reference's own function: batched (7 grid points per fused pass, ragged last chunk)
+    and point by point, same surface file contents."""
+    import types
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, STEQuantizedDOELayer
+    from quantizationawarethzdoe_b200.VisTools import calulate_single_element_loss_landscape, read_surface_file
+    g = golden("landscape_single_doe")
+    n = g["x"].shape[-1]
+
+    class Setup(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.input_field = ElectricField(data=g["x"].to(dev), wavelengths=g["wavelength"], spacing=g["spacing"], device=dev)
+            self.doe = STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=g["spacing"], doe_level=4, look_up_table=None, num_unit=None,
+                                                 height_constraint_max=1 * mm, tolerance=None, material=[2.66, 0.03]), {}, device=dev)
+            prop = ASM_prop(z_distance=g["z"], bandlimit_type='exact', padding_scale=None, bandlimit_kernel=True, device=dev)
+            prop.check_Zc = False
+            if batched:
+                self.asm_prop3 = prop          # the notebook's attribute name: picked up by the batched path
+            else:
+                self.prop = prop
+
+        def forward(self, iter_frac):
+            return (self.asm_prop3 if batched else self.prop)(self.doe(self.input_field, iter_frac))
+
+    model = Setup()
+    with torch.no_grad():
+        model.doe.weight_height_map.copy_(g["w0"].to(dev))
+    a = g["args"].tolist()
+    args = types.SimpleNamespace(xmin=a[0], xmax=a[1], xnum=int(a[2]), ymin=a[3], ymax=a[4], ynum=int(a[5]))
+    directions = [[g["dx"].to(dev)], [g["dy"].to(dev)]]
+    lib = __import__("quantizationawarethzdoe_b200")._native.lib()
+    l0 = lib.thz_launch_count_class(0)
+    path = calulate_single_element_loss_landscape(args, model, g["target"].to(dev), loss_f=torch.nn.MSELoss(), directions=directions,
+                                                  save_path=str(tmp_path), batch=7)
+    row_launches = lib.thz_launch_count_class(0) - l0
+    assert row_launches == (3 if batched else 20)          # 20 grid points: ceil(20 / 7) fused passes, or one per point
+    out = read_surface_file(path)
+    assert np.array_equal(out["xcoordinates"], g["xcoordinates"].numpy()) and np.array_equal(out["ycoordinates"], g["ycoordinates"].numpy())
+    err = float(np.abs(out["loss"] - g["loss"].numpy()).max() / np.abs(g["loss"].numpy()).max())
+    record("loss_landscape", batched=batched, max_rel_err=err)
+    assert out["loss"].shape == (5, 4) and err < 1e-5
+    assert torch.equal(model.doe.weight_height_map.detach().cpu(), g["w0"])          # weights restored
