@@ -54,13 +54,15 @@ def _default_device(device):
 class _DeferredModulation:
     """x * p(h), not yet evaluated.  ASM_prop consumes (x, height_map, coef) directly."""
 
-    def __init__(self, x, height_map, coef):
+    def __init__(self, x, height_map, coef, rows=None):
         self.x, self.height_map, self.coef = x, height_map, coef
         self.shape = x.shape
         self.device = x.device
+        self.rows = rows          # (lo, hi): x holds only these rows of the grid the height map covers (slab-decomposed fields)
 
     def materialise(self):
-        return Fn.DoeModulateFn.apply(self.x, self.height_map, self.coef)
+        hm = self.height_map if self.rows is None else self.height_map[self.rows[0]:self.rows[1]]
+        return Fn.DoeModulateFn.apply(self.x, hm, self.coef)
 
 
 class DOELayer(nn.Module):
@@ -105,13 +107,17 @@ class DOELayer(nn.Module):
     def modulate(self, input_field, preprocessed_height_map, height_tolerance, epsilon, tand):
         """Components/QuantizedDOE.py:92-126, deferred (see module docstring)."""
         hm = self.add_height_map_noise(preprocessed_height_map, tolerance=height_tolerance)
-        if input_field.height != hm.shape[0] or input_field.width != hm.shape[1]:
-            hm = nn.functional.interpolate(hm[None, None, :, :], size=[input_field.height, input_field.width], mode='nearest')
+        # a row slab of a grid distributed over several GPUs (parallel.shard_rows): the map covers the WHOLE grid
+        slab = getattr(input_field, "_row_slab", None)
+        full_h = input_field.height * slab[1] if slab is not None else input_field.height
+        if full_h != hm.shape[0] or input_field.width != hm.shape[1]:
+            hm = nn.functional.interpolate(hm[None, None, :, :], size=[full_h, input_field.width], mode='nearest')
         self._height_map_ = torch.squeeze(hm, (0, 1)) if hm.ndim == 4 else hm
         x = input_field.data
         N.require_cuda(x, "field.data")
         coef = self._coef(input_field.wavelengths, epsilon, tand, x.device)
-        deferred = _DeferredModulation(x, self._height_map_.to(x.device), coef)
+        rows = (slab[0] * input_field.height, (slab[0] + 1) * input_field.height) if slab is not None else None
+        deferred = _DeferredModulation(x, self._height_map_.to(x.device), coef, rows=rows)
         return ElectricField._from_deferred(deferred, input_field)
 
 

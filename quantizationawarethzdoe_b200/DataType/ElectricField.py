@@ -40,6 +40,8 @@ class ElectricField:
         self._wavelengths = like.wavelengths
         self._deferred = deferred
         self._data = None
+        if getattr(like, "_row_slab", None) is not None:
+            self._row_slab = like._row_slab
         B = deferred.shape[0]
         self.field_type = "scalar" if B == 1 else ("vectorial" if B == 3 else "batch")
         return self

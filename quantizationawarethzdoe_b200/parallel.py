@@ -47,6 +47,20 @@ def shard_field(field, rank, world, axis="wavelength"):
     raise ValueError("axis must be 'wavelength' or 'batch'")
 
 
+def shard_rows(field, rank, world):
+    """This rank's row slab of a field whose grid is distributed over `world` GPUs (what SlabAsm consumes).  The returned
+    field remembers that it is a slab, so a DOE layer applied to it keeps its height map at the size of the WHOLE grid and
+    SlabAsm fuses the modulation (and its adjoint) into the slab pipeline."""
+    data = field.data
+    H = data.shape[2]
+    if H % world:
+        raise ValueError("rows (%d) must be divisible by the number of ranks (%d)" % (H, world))
+    lo, hi = shard_range(H, rank, world)
+    f = ElectricField(data[:, :, lo:hi].contiguous(), wavelengths=field.wavelengths, spacing=field.spacing, device=data.device)
+    f._row_slab = (rank, world)
+    return f
+
+
 def allreduce_gradients(params, group=None, average=False):
     """Sum (or average) .grad of the given parameters over the process group with ONE all-reduce of a
     flat fp32 bucket.  Parameters without a gradient contribute zeros (ranks must agree on the list)."""
@@ -105,7 +119,18 @@ def _mark(label):
         SLAB_TIMINGS.append((label, e))
 
 
-def _slab_run(x_local, p, conj, group):
+def _doe_kw(doe, stage):
+    """Descriptor fields of the fused DOE for one stage of a slab run.  doe = None or dict(mode=1|2, hmap=<this rank's rows of
+    the height map>, coef, xsaved=<this rank's rows of the saved field>, gh=<this rank's rows of grad_height>): the forward
+    multiplies by p(h) in the row-FFT prologue (stage 1), the adjoint runs conj(p) / grad_height in the row-iFFT epilogue
+    (stage 4) -- exactly where the single-GPU pipeline fuses them (thz_asm_desc.doe_mode)."""
+    if doe is not None and ((doe["mode"] == 1 and stage == 1) or (doe["mode"] == 2 and stage == 4)):
+        return dict(doe_mode=doe["mode"], doe_base=Fn.BASE_PLANE_THICKNESS, hmap=doe["hmap"], coef=doe["coef"],
+                    xsaved=doe.get("xsaved"), gh=doe.get("gh"))
+    return dict(doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None)
+
+
+def _slab_run(x_local, p, conj, group, doe=None):
     """One slab-decomposed propagation.  x_local [B,C,rows_local,cols] -> y_local [B,C,out_rows_local,out_cols]."""
     G, B, C = p.G, x_local.shape[0], p.C
     nbc = B * C
@@ -117,12 +142,12 @@ def _slab_run(x_local, p, conj, group):
     Hl, Ol, Wc, Wp = inH // G, outH // G, p.Wc, p.Wp
     assert x_local.shape[2] == Hl and x_local.shape[3] == inW, "local slab has the wrong shape"
     common = dict(B=B, C=C, Hp=p.Hp, tf_mode=p.tf_mode, tf_conj=1 if conj else 0, rowvec=p.rowvec, scal=p.scal,
-                  doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h, tf_row_chunked=p.row_chunked)
+                  tw_h=p.tw_h, tf_row_chunked=p.row_chunked)
     _mark("start")
     # ---- stage 1: row FFT of the local rows -> t1 [nbc, Hl, Wp]
     t1 = torch.empty(nbc * Hl * Wp, dtype=torch.complex64, device=dev)
     Fn._asm_call(AH.build_desc(x=x_local, y=None, inH=Hl, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Hl, outW=outW, out_r0=0,
-                               out_c0=out_c0, colvec=p.colvec, table=p.table, tw_w=p.tw_w, ws=t1, stages=1, **common), dev)
+                               out_c0=out_c0, colvec=p.colvec, table=p.table, tw_w=p.tw_w, ws=t1, stages=1, **common, **_doe_kw(doe, 1)), dev)
     _mark("row fft")
     # ---- transpose 1: rank j receives my rows of ITS column block
     send = t1.view(nbc, Hl, G, Wc).permute(2, 0, 1, 3).contiguous()               # [G, nbc, Hl, Wc]
@@ -133,7 +158,7 @@ def _slab_run(x_local, p, conj, group):
     _mark("transpose 1")
     # ---- stage 2: column FFT . H . column iFFT on the local columns (in place)
     Fn._asm_call(AH.build_desc(x=None, y=None, inH=inH, inW=min(inW, Wc), Wp=Wc, in_r0=in_r0, in_c0=0, outH=outH, outW=min(outW, Wc),
-                               out_r0=out_r0, out_c0=0, colvec=p.colvec, table=p.table, tw_w=p.tw_c, ws=t2, stages=2, **common), dev)
+                               out_r0=out_r0, out_c0=0, colvec=p.colvec, table=p.table, tw_w=p.tw_c, ws=t2, stages=2, **common, **_doe_kw(doe, 2)), dev)
     _mark("column pass")
     # ---- transpose 2: rank j receives its output rows of my column block
     send = t2[:, :outH].reshape(nbc, G, Ol, Wc).permute(1, 0, 2, 3).contiguous()  # [G, nbc, Ol, Wc]
@@ -141,9 +166,10 @@ def _slab_run(x_local, p, conj, group):
     t3 = recv.permute(1, 2, 0, 3).reshape(nbc * Ol * Wp).contiguous()             # [nbc, Ol, Wp]
     _mark("transpose 2")
     # ---- stage 3: row iFFT + crop of the local output rows
-    y = torch.empty(B, C, Ol, outW, dtype=torch.complex64, device=dev)
+    want_y = doe is None or doe["mode"] != 2 or doe.get("want_gx", True)
+    y = torch.empty(B, C, Ol, outW, dtype=torch.complex64, device=dev) if want_y else None
     Fn._asm_call(AH.build_desc(x=None, y=y, inH=Ol, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Ol, outW=outW, out_r0=0,
-                               out_c0=out_c0, colvec=p.colvec, table=p.table, tw_w=p.tw_w, ws=t3, stages=4, **common), dev)
+                               out_c0=out_c0, colvec=p.colvec, table=p.table, tw_w=p.tw_w, ws=t3, stages=4, **common, **_doe_kw(doe, 4)), dev)
     _mark("row ifft")
     return y
 
@@ -177,7 +203,7 @@ class _PeerSlabs:
 SLAB_BLOCKED = int(os.environ.get("THZ_SLAB_BLOCKED", "0"))   # 1: S1 slabs in 4-column blocks (32-byte remote stores: slower on NVLink)
 
 
-def _slab_stage_descs(p, x_local, y_local, rank, ptrs1, ptrs2, s1_local, conj):
+def _slab_stage_descs(p, x_local, y_local, rank, ptrs1, ptrs2, s1_local, conj, doe=None):
     """The three descriptors of one rank's part of a peer-memory slab propagation (stage 1 scatter into the S1 slabs, stage 2
     from the local S1 to the local S2, stage 4 gather from the S2 slabs).  ptrsK[d] = address of rank d's slab SK."""
     G, B, C = p.G, x_local.shape[0], p.C
@@ -188,23 +214,24 @@ def _slab_stage_descs(p, x_local, y_local, rank, ptrs1, ptrs2, s1_local, conj):
     Hl, Ol, Wc, Wp = inH // G, outH // G, p.Wc, p.Wp
     rowsT = max(inH, outH)
     common = dict(B=B, C=C, Hp=p.Hp, tf_mode=p.tf_mode, tf_conj=1 if conj else 0, rowvec=p.rowvec, scal=p.scal,
-                  doe_mode=0, doe_base=0.0, hmap=None, coef=None, xsaved=None, gh=None, tw_h=p.tw_h, colvec=p.colvec, table=p.table,
-                  tf_row_chunked=p.row_chunked)
+                  tw_h=p.tw_h, colvec=p.colvec, table=p.table, tf_row_chunked=p.row_chunked)
     d1 = AH.build_desc(x=x_local, y=None, inH=Hl, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Hl, outW=outW, out_r0=0, out_c0=out_c0,
-                       tw_w=p.tw_w, ws=None, stages=1, slab=(G, rank * Hl, rowsT, ptrs1, SLAB_BLOCKED), **common)
+                       tw_w=p.tw_w, ws=None, stages=1, slab=(G, rank * Hl, rowsT, ptrs1, SLAB_BLOCKED), **common, **_doe_kw(doe, 1))
     d2 = AH.build_desc(x=None, y=None, inH=inH, inW=min(inW, Wc), Wp=Wc, in_r0=in_r0, in_c0=0, outH=outH, outW=min(outW, Wc),
-                       out_r0=out_r0, out_c0=0, tw_w=p.tw_c, ws=s1_local, stages=2, slab=(G, 0, rowsT, [ptrs2[rank]], SLAB_BLOCKED), **common)
+                       out_r0=out_r0, out_c0=0, tw_w=p.tw_c, ws=s1_local, stages=2, slab=(G, 0, rowsT, [ptrs2[rank]], SLAB_BLOCKED),
+                       **common, **_doe_kw(doe, 2))
     d3 = AH.build_desc(x=None, y=y_local, inH=Ol, inW=inW, Wp=Wp, in_r0=0, in_c0=in_c0, outH=Ol, outW=outW, out_r0=0, out_c0=out_c0,
-                       tw_w=p.tw_w, ws=None, stages=4, slab=(G, rank * Ol, rowsT, ptrs2), **common)
+                       tw_w=p.tw_w, ws=None, stages=4, slab=(G, rank * Ol, rowsT, ptrs2), **common, **_doe_kw(doe, 4))
     return d1, d2, d3
 
 
-def _slab_run_peer(x_local, p, conj, slabs):
+def _slab_run_peer(x_local, p, conj, slabs, doe=None):
     """Slab-decomposed propagation with the transposes fused into the row kernels (see _PeerSlabs)."""
     B, C, dev = x_local.shape[0], p.C, x_local.device
     outH, outW = (p.outH, p.outW) if not conj else (p.H, p.W)
-    y = torch.empty(B, C, outH // p.G, outW, dtype=torch.complex64, device=dev)
-    d1, d2, d3 = _slab_stage_descs(p, x_local, y, p.rank, slabs.ptrs1, slabs.ptrs2, slabs.local(1), conj)
+    want_y = doe is None or doe["mode"] != 2 or doe.get("want_gx", True)
+    y = torch.empty(B, C, outH // p.G, outW, dtype=torch.complex64, device=dev) if want_y else None
+    d1, d2, d3 = _slab_stage_descs(p, x_local, y, p.rank, slabs.ptrs1, slabs.ptrs2, slabs.local(1), conj, doe)
     _mark("start")
     Fn._asm_call(d1, dev)                # row FFT; stores go to the owners of the column blocks (their S1)
     _mark("row fft + scatter")
@@ -217,9 +244,10 @@ def _slab_run_peer(x_local, p, conj, slabs):
     return y
 
 
-def slab_emulate_ranks(x_full, plans, conj=False):
+def slab_emulate_ranks(x_full, plans, conj=False, doe=None):
     """Test helper: run the G ranks of a peer-memory slab propagation one after the other in THIS process (all column
-    slabs on one device), exercising exactly the descriptors and kernels of `_slab_run_peer`.  x_full [B,C,H,W]."""
+    slabs on one device), exercising exactly the descriptors and kernels of `_slab_run_peer`.  x_full [B,C,H,W].
+    doe = dict(mode, hmap [H,W], coef[, xsaved [B,C,H,W], gh [H,W]]) with FULL tensors: each emulated rank gets its rows."""
     G, p0 = len(plans), plans[0]
     B, dev = x_full.shape[0], x_full.device
     inH = p0.H if not conj else p0.outH
@@ -232,7 +260,19 @@ def slab_emulate_ranks(x_full, plans, conj=False):
     Hl = inH // G
     ys = [torch.empty(B, p0.C, outH // G, outW, dtype=torch.complex64, device=dev) for _ in range(G)]
     xs = [x_full[:, :, r * Hl:(r + 1) * Hl].contiguous() for r in range(G)]
-    descs = [_slab_stage_descs(plans[r], xs[r], ys[r], r, ptrs1, ptrs2, s1[r], conj) for r in range(G)]
+    def rank_doe(r):
+        if doe is None:
+            return None
+        rows = (p0.H // G)
+        d = dict(mode=doe["mode"], coef=doe["coef"], hmap=doe["hmap"][r * rows:(r + 1) * rows].contiguous())
+        if doe["mode"] == 2:
+            d["xsaved"] = doe["xsaved"][:, :, r * rows:(r + 1) * rows].contiguous()
+            d["gh"] = doe["gh_parts"][r]
+        return d
+
+    if doe is not None and doe["mode"] == 2:
+        doe["gh_parts"] = [torch.empty(p0.H // G, p0.W, dtype=torch.float32, device=dev) for _ in range(G)]
+    descs = [_slab_stage_descs(plans[r], xs[r], ys[r], r, ptrs1, ptrs2, s1[r], conj, rank_doe(r)) for r in range(G)]
     for k in range(3):
         for r in range(G):
             Fn._asm_call(descs[r][k], dev)
@@ -257,6 +297,41 @@ class _SlabFn(torch.autograd.Function):
         g = Fn._c64(g, "grad_output")
         gx = _slab_run_peer(g, ctx.plan, True, ctx.slabs) if ctx.slabs is not None else _slab_run(g, ctx.plan, True, ctx.group)
         return gx, None, None, None
+
+
+class _SlabDoeFn(torch.autograd.Function):
+    """y_local = slab-ASM(x_local * p(h[local rows])) with the DOE fused into the slab pipeline's own kernels, as on one GPU:
+    forward = DOE phase in the row-FFT prologue; backward = conj(p) multiply and grad_height in the row-iFFT epilogue.
+    Every rank returns grad_height for ITS rows (zeros elsewhere); the caller's gradient all-reduce sums the slabs."""
+
+    @staticmethod
+    def forward(ctx, x_local, hmap, plan, group, slabs, coef):
+        x_local = Fn._c64(x_local, "field.data")
+        N.require_cuda(hmap, "height_map")
+        hmap = hmap.to(torch.float32).contiguous()
+        rows = plan.H // plan.G
+        h_loc = hmap[plan.rank * rows:(plan.rank + 1) * rows].contiguous()
+        doe = dict(mode=1, hmap=h_loc, coef=coef)
+        y = _slab_run_peer(x_local, plan, False, slabs, doe) if slabs is not None else _slab_run(x_local, plan, False, group, doe)
+        ctx.plan, ctx.group, ctx.slabs, ctx.coef, ctx.hshape = plan, group, slabs, coef, hmap.shape
+        ctx.save_for_backward(x_local, h_loc)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        plan = ctx.plan
+        x_local, h_loc = ctx.saved_tensors
+        g = Fn._c64(g, "grad_output")
+        rows = plan.H // plan.G
+        need_x, need_h = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gh_loc = torch.empty(rows, plan.W, dtype=torch.float32, device=g.device)
+        doe = dict(mode=2, hmap=h_loc, coef=ctx.coef, xsaved=x_local, gh=gh_loc, want_gx=need_x)
+        gx = _slab_run_peer(g, plan, True, ctx.slabs, doe) if ctx.slabs is not None else _slab_run(g, plan, True, ctx.group, doe)
+        gh = None
+        if need_h:
+            gh = torch.zeros(ctx.hshape, dtype=torch.float32, device=g.device)
+            gh[plan.rank * rows:(plan.rank + 1) * rows] = gh_loc
+        return (gx if need_x else None), gh, None, None, None, None
 
 
 class SlabAsm(torch.nn.Module):
@@ -299,7 +374,12 @@ class SlabAsm(torch.nn.Module):
 
     def forward(self, field):
         G, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        data = field.data
+        # a DOE layer's output arrives un-materialised (ElectricField._deferred): the slab pipeline fuses it like ASM_prop does.
+        # The layer holds the FULL height map [H, W] (replicated parameters), the field is this rank's row slab.
+        deferred = getattr(field, "_deferred", None) if getattr(field, "_data", None) is None else None
+        if deferred is not None and (deferred.rows is None or deferred.height_map.shape[0] != deferred.x.shape[2] * G):
+            deferred = None                     # not a row slab under a global map: materialise and propagate plainly
+        data = deferred.x if deferred is not None else field.data
         B, C, Hl, W = data.shape
         H = Hl * G
         # same tensor objects (unchanged in place) as last time -> same plan, no device->host reads (they would serialise
@@ -329,5 +409,11 @@ class SlabAsm(torch.nn.Module):
             self._slabs = self._make_slabs(B * C, data.device)
         elif self._slabs is not None and self._slabs.numel < B * C * max(self._plan.H, self._plan.outH) * self._plan.Wc:
             self._slabs = self._make_slabs(B * C, data.device)
-        out = _SlabFn.apply(data, self._plan, self.group, self._slabs)
-        return ElectricField(out, wavelengths=field.wavelengths, spacing=field.spacing, device=data.device)
+        if deferred is not None:
+            out = _SlabDoeFn.apply(data, deferred.height_map, self._plan, self.group, self._slabs, deferred.coef)
+        else:
+            out = _SlabFn.apply(data, self._plan, self.group, self._slabs)
+        res = ElectricField(out, wavelengths=field.wavelengths, spacing=field.spacing, device=data.device)
+        if self._plan.outH == self._plan.H:         # still a row slab of the same grid: a following DOE layer may fuse again
+            res._row_slab = (rank, G)
+        return res

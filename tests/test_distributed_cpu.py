@@ -42,7 +42,7 @@ def _worker(rank, world, port, which, out):
     try:
         torch.set_num_threads(2)
         _install_cpu_replay()
-        out[rank] = {"dp": _dp_case, "slab": _slab_case}[which](rank, world)
+        out[rank] = {"dp": _dp_case, "slab": _slab_case, "slab_doe": _slab_doe_case}[which](rank, world)
     finally:
         dist.destroy_process_group()
 
@@ -105,7 +105,44 @@ def _slab_case(rank, world):
     return max(errs)
 
 
-@pytest.mark.parametrize("which,tol", [("dp", 2e-6), ("slab", 2e-5)])
+def _slab_doe_case(rank, world):
+    """DOE layer + slab-decomposed ASM: the rank's row slab goes through a full-size (replicated) DOE whose modulation is
+    fused into the slab pipeline's row-FFT prologue, its adjoint (conj(p), grad_height of the local rows) into the row-iFFT
+    epilogue; the all-reduced weight gradient and the local input gradient == autograd through the oracle on the full grid."""
+    from oracle import asm_oracle as AO, doe_oracle as DO
+    from quantizationawarethzdoe_b200 import ElectricField, FullPrecisionDOELayer
+    from quantizationawarethzdoe_b200 import functional as Fn
+    from quantizationawarethzdoe_b200 import parallel as P
+    cpu = torch.device("cpu")
+    H, W, lams = 64, 48, [1 * mm, 1.05 * mm]
+    torch.manual_seed(0)
+    x = torch.randn(1, 2, H, W, dtype=torch.complex64)
+    g = torch.randn(1, 2, H, W, dtype=torch.complex64)
+    torch.manual_seed(1)
+    w = torch.randn(1, 1, H, W)
+    Fn.HeightFromWeightFn.apply = staticmethod(lambda ww, hmax, c: DO.sigmoid_height(ww, hmax, c))
+    doe = FullPrecisionDOELayer(dict(doe_size=[H, W], doe_dxy=0.5 * mm, height_constraint_max=1 * mm, tolerance=None,
+                                     material=[2.66, 0.003]), device=cpu)
+    with torch.no_grad():
+        doe.weight_height_map.copy_(w)
+    lo, hi = P.shard_range(H, rank, world)
+    slab = P.SlabAsm(z_distance=0.1, kernel_mode="cached")
+    xf = x.clone().requires_grad_(True)
+    mine = P.shard_rows(ElectricField(xf, wavelengths=lams, spacing=0.5 * mm, device=cpu), rank, world)
+    u = doe(mine)
+    assert u._data is None and u._deferred.rows == (lo, hi)            # modulation deferred, map kept at full size
+    yl = slab(u).data
+    gxf, gw = torch.autograd.grad(yl, (xf, doe.weight_height_map), g[:, :, lo:hi].contiguous())
+    doe.weight_height_map.grad = gw
+    P.allreduce_gradients(doe.parameters())
+    xo, wo = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yo = AO.asm_forward(DO.modulate(xo, DO.sigmoid_height(wo[0, 0], 1 * mm), lams, 2.66, 0.003), lams, 0.5 * mm, 0.1)
+    gxo, gwo = torch.autograd.grad(yo, (xo, wo), g)
+    return max(rel_l2(yl.detach(), yo.detach()[:, :, lo:hi]), rel_l2(gxf[:, :, lo:hi], gxo[:, :, lo:hi]),
+               rel_l2(doe.weight_height_map.grad, gwo))
+
+
+@pytest.mark.parametrize("which,tol", [("dp", 2e-6), ("slab", 2e-5), ("slab_doe", 2e-6)])
 def test_two_rank_gloo(which, tol):
     port = _free_port()
     with mp.Manager() as mgr:

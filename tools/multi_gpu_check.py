@@ -79,6 +79,24 @@ if rank == 0:
     print("  rank 0 stages (ms):", stage_ms)
 ok &= bool(e.max() < 2e-6)
 
+# ---- DOE fused into the slab pipeline (prologue of the row-FFT kernel / epilogue of the row-iFFT kernel) vs one GPU
+torch.manual_seed(7)
+doe_s = STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=0.5 * mm, doe_level=4, height_constraint_max=1 * mm, tolerance=None,
+                                  material=[2.66, 0.003]), {}, device=dev)
+xs = x.clone().requires_grad_(True)
+mine = P.shard_rows(ElectricField(xs, wavelengths=lams, spacing=0.5 * mm, device=dev), rank, world)
+ys = slab(doe_s(mine)).data
+gxs, gws = torch.autograd.grad(ys, (xs, doe_s.weight_height_map), g[:, :, lo:hi].contiguous())
+dist.all_reduce(gws)                        # every rank holds the rows it owns; the sum is the full weight gradient
+xf2 = x.clone().requires_grad_(True)
+yf2 = asm(doe_s(ElectricField(xf2, wavelengths=lams, spacing=0.5 * mm, device=dev))).data
+gxf2, gwf2 = torch.autograd.grad(yf2, (xf2, doe_s.weight_height_map), g)
+e = torch.tensor([rel(ys.detach(), yf2.detach()[:, :, lo:hi]), rel(gxs[:, :, lo:hi], gxf2[:, :, lo:hi]), rel(gws, gwf2)], device=dev)
+dist.all_reduce(e, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("DOE-fused slab over %d GPUs vs single GPU: fwd %.2e grad_x %.2e grad_w %.2e" % (world, e[0], e[1], e[2]))
+ok &= bool(e.max() < 2e-6)
+
 # ---- data parallel over wavelengths
 C = 2 * world
 lam_all = [1 * mm * (1 + 0.01 * c) for c in range(C)]
