@@ -43,7 +43,7 @@ const char* thz_last_error(void);
  *   radices: host int32[16] out;  *nstages out.  Returns THZ_E_UNSUPPORTED if n has a prime factor > 7.
  * thz_fft_slot_to_bin: host int32[n] out; slot_to_bin[p] = DFT bin stored at slot p of a transformed
  *   line (the plans leave spectra in digit-reversed order; cached transfer-function tables must be
- *   laid out as table[c][slot_r][slot_c] = H'[c][bin(slot_r)][bin(slot_c)]).
+ *   laid out as table[c][slot_c][slot_r] = H'[c][bin(slot_r)][bin(slot_c)]).
  * thz_fft_twiddles: host float[2n] out; tw[m] = exp(-2 pi i m / n) rounded from float64.
  * ------------------------------------------------------------------------------------------- */
 int thz_fft_plan_info(int32_t n, int32_t* radices, int32_t* nstages);
@@ -99,7 +99,8 @@ typedef struct thz_asm_desc {
                                   fp32 op order, so the mask is bit-identical to the reference's               */
     const void* tf_colvec;     /* float32 [C,Wp]   Ky^2 in slot order                                           */
     const void* tf_scal;       /* float32 [C,2]    {klam^2, z}                                             */
-    const void* tf_table;      /* complex64 [C,Hp,Wp] in slot order (see thz_fft_slot_to_bin)              */
+    const void* tf_table;      /* complex64 [C,Wp,Hp] = table[c][slot_c][slot_r] (slot order, see thz_fft_slot_to_bin;
+                                  COLUMN-major: a thread of the column pass multiplies R consecutive rows of one column) */
     /* DOE */
     int32_t doe_mode;          /* 0 none; 1 multiply x by p(h) on load; 2 adjoint epilogue                 */
     float doe_base;            /* BASE_PLANE_THICKNESS (Components/QuantizedDOE.py:23)                     */

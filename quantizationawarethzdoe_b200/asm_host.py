@@ -265,11 +265,12 @@ def inregister_deviation_estimate(Hp, Wp, spacing, wavelengths, z, bandlimit=Tru
 
 
 def tf_table_slot_order(Hc, slot_to_bin_fn=None):
-    """Centred kernel [C,Hp,Wp] -> table[c][slot_r][slot_c] = ifftshift(Hc)[c][bin(slot_r)][bin(slot_c)]."""
+    """Centred kernel [C,Hp,Wp] -> table[c][slot_c][slot_r] = ifftshift(Hc)[c][bin(slot_r)][bin(slot_c)]  ([C,Wp,Hp]: column-major,
+    the order the column pass consumes it -- each thread multiplies R consecutive rows of one column with 16-byte loads)."""
     Hn = torch.fft.ifftshift(Hc, dim=(-2, -1))
     pr = N.slot_to_bin(Hn.shape[-2], slot_to_bin_fn)
     pc = N.slot_to_bin(Hn.shape[-1], slot_to_bin_fn)
-    return Hn[:, pr][:, :, pc].contiguous()
+    return Hn[:, pr][:, :, pc].transpose(1, 2).contiguous()
 
 
 def critical_distance(Hp, spacing, wavelengths):

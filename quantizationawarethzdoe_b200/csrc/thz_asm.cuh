@@ -172,6 +172,9 @@ struct ColArgs {
     cpx* Tout;                // separate output buffer (NULL: in place in T)
     int half_in, half_out;    // 1: input / output rows are exactly [Hp/4, 3Hp/4): pruned first / last stage
     int tout_tiled;           // k > 0: Tout is blocked as well (experiment), 0: row-major
+    int fast;                 // 1: the configuration the specialised column kernel serves (thz_p2_k2f): centred 2x padding on
+                              //    the column axis (half_in && half_out), 4-column blocked input, row-major output in Tout,
+                              //    whole column tiles, first radix 16 -- every address offset is then a compile-time constant
 };
 
 THZ_HD void k2_load(const ColArgs& a, cpx* s, int bx, int by, int tid, int nthreads) {
@@ -208,10 +211,10 @@ THZ_HD void k2_middle_butterfly(const ColArgs& a, cpx* s, int l, int u, int col,
 #pragma unroll
             for (int q = 0; q < R; ++q) v[q] = cmul(v[q], thz_tf_value(rv[q], cv, sc, a.tf.conj));
         } else {
-            const cpx* tp = a.tf.table + ((size_t)c * a.Hp + p0) * a.Wp + col;
+            const cpx* tp = a.tf.table + ((size_t)c * a.Wp + col) * a.Hp + p0;     // table[c][slot_c][slot_r]: the R rows are contiguous
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-                cpx h = thz_ldg(tp + (size_t)q * a.Wp);
+                cpx h = thz_ldg(tp + q);
                 v[q] = a.tf.conj ? cmulc(v[q], h) : cmul(v[q], h);
             }
         }

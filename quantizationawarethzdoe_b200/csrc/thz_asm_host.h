@@ -84,6 +84,13 @@ static inline bool thz_asm_two_buffers(const thz_asm_desc* d) {
            !thz_env_is_1("THZ_NO_P2") && !thz_env_is_1("THZ_NO_TILED");
 }
 
+static inline bool p2_k2_fast_ok_rt(int n) {
+    if (!thz_sp_instantiated(n) || (n & (n - 1)) != 0 || n < 256) return false;
+#define THZ_SP_FASTCMP(NN) if (n == NN) return sp_k2_fast_ok_or_false<NN>();
+    THZ_SP_SIZES(THZ_SP_FASTCMP)
+#undef THZ_SP_FASTCMP
+    return false;
+}
 static inline int thz_p2_row_lines_rt(int n) { return p2_row_lines(n); }
 static inline int thz_p2_tw_count_rt(int n) { return p2_tw_count(n); }
 static inline int thz_p2_row_threads_rt(int n) { return p2_row_threads(n); }
@@ -300,6 +307,12 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k2.half_out = (on && 4 * d->out_r0 == d->Hp && 2 * d->outH == d->Hp) ? 1 : 0;
         L->k3.half_out = (on && 4 * d->out_c0 == d->Wp && 2 * d->outW == d->Wp) ? 1 : 0;
     }
+    // the specialised column kernel (thz_p2_k2f): centred 2x padding, blocked input, row-major output, whole tiles, static
+    // length with a radix-16 first stage, transfer function from chunked vectors / a table / none (THZ_NO_K2FAST=1: off)
+    L->k2.fast = (L->p2_h && L->k2.half_in && L->k2.half_out && L->k2.t_tiled == 2 && L->k2.tout_tiled == 0 && L->k2.Tout &&
+                  p2_k2_fast_ok_rt(d->Hp) && d->Wp % L->k2.cols == 0 && d->Wp % 4 == 0 &&
+                  (d->tf_mode != 0 || d->tf_row_chunked) && L->k2_threads == thz_p2_col_threads_rt(d->Hp) &&
+                  !thz_env_is_1("THZ_NO_K2FAST")) ? 1 : 0;
     if (d->slab_parts > 1 && (d->stages & 5) && !L->p2_w) return THZ_E_UNSUPPORTED;   // only the static row kernels scatter / gather slabs
     if (d->tf_row_chunked && d->tf_mode == 0 && !L->p2_h) return THZ_E_UNSUPPORTED;   // chunked row vectors: static column kernels only
     return THZ_OK;

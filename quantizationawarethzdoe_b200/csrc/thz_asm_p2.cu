@@ -91,6 +91,24 @@ __global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     p2k2_last<N, COLS>(a, s, tws, bx, by, tid, nt);
 }
 
+// fast path of the column kernel (ColArgs.fast, see thz_asm_p2.cuh): same phases, everything static
+template <int N, int TFM>
+__global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k2f(const __grid_constant__ ColArgs a) {
+    constexpr int COLS = p2_col_cols(N), NS = p2_stages(N), NT = p2_col_threads(N);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx* s = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tws = s + COLS * p2_pitch(N);
+    const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+    p2_tw_fill<N>(tws, a.tw, tid, NT);
+    p2k2f_first<N, COLS, NT>(a, s, bx, by, tid);
+    __syncthreads();
+    fwd_cols<N, 1, NS - 1, COLS>(s, tid, NT, tws);
+    p2k2f_middle<N, COLS, NT, TFM>(a, s, bx, by, tid);
+    __syncthreads();
+    inv_cols<N, NS - 2, 1, COLS>(s, tid, NT, tws);
+    p2k2f_last<N, COLS, NT>(a, s, tws, bx, by, tid);
+}
+
 template <int N>
 __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k3(const __grid_constant__ RowInvArgs a) {
     constexpr int NACC = p2k3_acc<N>(), LINES = p2_row_lines(N), BUF = LINES * p2_pitch(N);
@@ -171,7 +189,23 @@ int thz_p2_launch_k1(const RowFwdArgs& a, int grid, int threads, size_t smem, cu
     THZ_P2_SWITCH(thz_p2_k1, a.Wp, THZ_KC_ROW_FWD, grid, threads, smem, stream, a)
 #undef THZ_P2_X
 }
+template <int N>
+static int launch_k2f(const ColArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream) {
+    if constexpr (p2_k2_fast_ok(N)) {
+        if (a.tf.mode == 0) return launch_p2(thz_p2_k2f<N, 0>, "thz_p2_k2f", THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a);
+        if (a.tf.mode == 1) return launch_p2(thz_p2_k2f<N, 1>, "thz_p2_k2f", THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a);
+        return launch_p2(thz_p2_k2f<N, 2>, "thz_p2_k2f", THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a);
+    } else {
+        return thz_set_error(THZ_E_UNSUPPORTED, "fast column path: size not served");
+    }
+}
+
 int thz_p2_launch_k2(const ColArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream) {
+    if (a.fast) {
+#define THZ_P2_X(NN) case NN: return launch_k2f<NN>(a, gridx, gridy, threads, smem, stream);
+        THZ_P2_SWITCH(thz_p2_k2f, a.Hp, THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a)
+#undef THZ_P2_X
+    }
 #define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k2<NN>, "thz_p2_k2", THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a);
     THZ_P2_SWITCH(thz_p2_k2, a.Hp, THZ_KC_COL, dim3(gridx, gridy), threads, smem, stream, a)
 #undef THZ_P2_X

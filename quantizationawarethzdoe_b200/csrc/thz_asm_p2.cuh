@@ -257,11 +257,15 @@ THZ_HD void p2k2_middle(const ColArgs& a, cpx* s, int bx, int by, int tid, int n
                     v[2 * q + 1] = cmul(v[2 * q + 1], thz_tf_value(cmake(rv4[q].z, rv4[q].w), cv, sc, a.tf.conj));
                 }
             } else {
-                const cpx* tp = a.tf.table + ((size_t)c_chan * N + p0) * a.Wp + col;
+                // table[c][slot_c][slot_r]: this thread's R rows are R * 8 contiguous bytes (R even: 16-byte loads)
+                const float4* tp = reinterpret_cast<const float4*>(a.tf.table + ((size_t)c_chan * a.Wp + col) * N + p0);
+                static_assert(R % 2 == 0 || R == 1, "static column kernels end in an even radix");
 #pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    const cpx h = thz_ldg(tp + (size_t)q * a.Wp);
-                    v[q] = a.tf.conj ? cmulc(v[q], h) : cmul(v[q], h);
+                for (int q = 0; q < R / 2; ++q) {
+                    const float4 h2 = thz_ldg(tp + q);
+                    const cpx h0 = cmake(h2.x, h2.y), h1 = cmake(h2.z, h2.w);
+                    v[2 * q] = a.tf.conj ? cmulc(v[2 * q], h0) : cmul(v[2 * q], h0);
+                    v[2 * q + 1] = a.tf.conj ? cmulc(v[2 * q + 1], h1) : cmul(v[2 * q + 1], h1);
                 }
             }
         }
@@ -285,6 +289,134 @@ THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, const cpx* tw, int bx, int
         st.Wp = a.tout_tiled ? (1 << a.tout_tiled) : a.Wp;
         if (a.half_out) p2_last_inverse_stage_to<N, COLS, true>(s + l, j, tw, st);
         else p2_last_inverse_stage_to<N, COLS>(s + l, j, tw, st);
+    }
+}
+
+// =============================================================================== K2 fast path <N, COLS, NT[, TFM]>
+// The column kernel of the benchmarked configuration (ColArgs.fast): centred 2x padding on the column axis, input in the
+// 4-column blocked intermediate, row-major output, whole tiles.  Same arithmetic, same order, same results as the general
+// phases above (the parity tests run both), but every decision the general code takes at run time is a constant here:
+// the work loops have compile-time trip counts (NT = block size), the 8 live first-stage inputs of a butterfly sit at
+// immediate offsets from one pointer (rows j + t N/16 of a 32-byte-pitch column), the 8 live outputs advance one 64-bit
+// pointer by a precomputed step, and no bounds check survives.  profiles/README.md (round 2): the general kernel spends
+// 35 % / 27 % of its first / last phase on integer and control instructions; this path removes most of them.
+#ifndef THZ_K2F_UNROLL
+#define THZ_K2F_UNROLL 1
+#endif
+constexpr int K2F_UNROLL = THZ_K2F_UNROLL;
+THZ_HD constexpr bool p2_k2_fast_ok(int N) {
+    return (N & (N - 1)) == 0 && N >= 256 && p2_radix(N, 0) == 16 && (p2_col_cols(N) * (N / 16)) % p2_col_threads(N) == 0 &&
+           (p2_col_cols(N) * (N / p2_radix(N, p2_stages(N) - 1))) % p2_col_threads(N) == 0;
+}
+
+template <int N>
+THZ_HD constexpr bool sp_k2_fast_ok_or_false() { return p2_k2_fast_ok(N); }
+
+template <int N, int COLS, int NT>
+THZ_HD void p2k2f_first(const ColArgs& a, cpx* s, int bx, int by, int tid) {
+    typedef P2Stage<N, 0> St;
+    constexpr int NB = St::NB, M = St::M, ITEMS = COLS * NB / NT;
+    static_assert(St::R == 16 && (COLS * NB) % NT == 0 && 4 * M == N / 4, "fast column path: radix-16 first stage");
+    const cpx* tile = a.T + ((((size_t)by * (a.Wp >> 2) + ((bx * COLS) >> 2)) * a.rowsT) << 2) + ((bx * COLS) & 3);
+    // one butterfly after the other: with both butterflies' 16 loads in flight per thread the L1 request queue backs up and the
+    // kernel is SLOWER (measured twice, profiles/README.md), so the item loop is deliberately not unrolled
+#pragma unroll K2F_UNROLL
+    for (int k = 0; k < ITEMS; ++k) {
+        const int w = tid + k * NT;
+        const int j = w / COLS, l = w % COLS;
+        // element 4 + t of butterfly j is canvas row j + (4 + t) M = live row j + t M; rows are 4 complex (32 bytes) apart
+        const cpx* p0 = tile + (COLS > 4 ? (((size_t)(l >> 2) * a.rowsT) << 2) + (l & 3) : (size_t)l) + (size_t)j * 4;
+        cpx in[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) in[t] = p0[t * M * 4];
+        cpx v[16];
+        dft16_half_in<false>(in, v);
+        p2_apply_twiddles<16>(v, thz_ldg(a.tw + j));
+        cpx* p = s + (j + (j >> 4)) * COLS + l;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) p[p2_coff(M, t) * COLS] = v[t];
+    }
+}
+
+template <int N, int COLS, int NT, int TFM>
+THZ_HD void p2k2f_middle(const ColArgs& a, cpx* s, int bx, int by, int tid) {
+    constexpr int S = p2_stages(N) - 1;
+    typedef P2Stage<N, S> St;
+    constexpr int R = St::R, NB = St::NB, ITEMS = COLS * NB / NT;
+    static_assert(St::M == 1 && (COLS * NB) % NT == 0 && R % 2 == 0, "fast column path: unit last stage, even radix");
+    const int c_chan = (a.c0 + by) % a.C;
+#pragma unroll 1
+    for (int k = 0; k < ITEMS; ++k) {
+        const int w = tid + k * NT;
+        const int u = w / COLS, l = w % COLS;
+        const int col = bx * COLS + l;
+        const int p0 = u * R;
+        cpx* p = s + (p0 + (p0 >> 4)) * COLS + l;
+        cpx v[R];
+        float4 h4[R / 2];           // TFM 0: {Kx^2, tau} of two rows per entry; TFM 1: two complex table entries per entry
+        float cv = 0.f;
+        float2 sc = cmake(0.f, 0.f);
+        if constexpr (TFM == 0) {
+            const float4* rvp = reinterpret_cast<const float4*>(a.tf.rowvec + (size_t)c_chan * N) + u;      // chunked layout
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) h4[q] = thz_ldg(rvp + (size_t)q * NB);
+            cv = thz_ldg(a.tf.colvec + (size_t)c_chan * a.Wp + col);
+            sc = thz_ldg(a.tf.scal + c_chan);
+        } else if constexpr (TFM == 1) {
+            const float4* tp = reinterpret_cast<const float4*>(a.tf.table + ((size_t)c_chan * a.Wp + col) * N + p0);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) h4[q] = thz_ldg(tp + q);
+        }
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = p[t * COLS];
+        Dft<R, false>::run(v);
+        if constexpr (TFM == 0) {
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+                v[2 * q] = cmul(v[2 * q], thz_tf_value(cmake(h4[q].x, h4[q].y), cv, sc, a.tf.conj));
+                v[2 * q + 1] = cmul(v[2 * q + 1], thz_tf_value(cmake(h4[q].z, h4[q].w), cv, sc, a.tf.conj));
+            }
+        } else if constexpr (TFM == 1) {
+            if (a.tf.conj) {
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    v[2 * q] = cmulc(v[2 * q], cmake(h4[q].x, h4[q].y));
+                    v[2 * q + 1] = cmulc(v[2 * q + 1], cmake(h4[q].z, h4[q].w));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    v[2 * q] = cmul(v[2 * q], cmake(h4[q].x, h4[q].y));
+                    v[2 * q + 1] = cmul(v[2 * q + 1], cmake(h4[q].z, h4[q].w));
+                }
+            }
+        }
+        Dft<R, true>::run(v);
+#pragma unroll
+        for (int t = 0; t < R; ++t) p[t * COLS] = v[t];
+    }
+}
+
+template <int N, int COLS, int NT>
+THZ_HD void p2k2f_last(const ColArgs& a, const cpx* s, const cpx* tws, int bx, int by, int tid) {
+    typedef P2Stage<N, 0> St;
+    constexpr int NB = St::NB, M = St::M, ITEMS = COLS * NB / NT;
+    cpx* tile = a.Tout + (size_t)by * a.rowsT * a.Wp + (size_t)bx * COLS;       // row-major, row 0 = canvas row N / 4
+    const size_t step = (size_t)M * a.Wp;
+#pragma unroll K2F_UNROLL
+    for (int k = 0; k < ITEMS; ++k) {
+        const int w = tid + k * NT;
+        const int j = w / COLS, l = w % COLS;
+        const cpx* p = s + (j + (j >> 4)) * COLS + l;
+        cpx v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = p[p2_coff(M, t) * COLS];
+        p2_apply_twiddles<16>(v, cconj(tws[p2_twi(j)]));
+        cpx o[8];
+        dft16_half_out<true>(v, o);
+        cpx* q = tile + (size_t)j * a.Wp + l;             // output 4 + t is canvas row j + (4 + t) M = live row j + t M
+#pragma unroll
+        for (int t = 0; t < 8; ++t, q += step) *q = o[t];
     }
 }
 

@@ -103,7 +103,7 @@ class _SlabPlan:
         self.rowvec = rowvec.to(device) if rowvec is not None else None
         self.colvec = colvec[:, c0:c0 + self.Wc].contiguous().to(device) if colvec is not None else None
         self.scal = scal.to(device) if scal is not None else None
-        self.table = table[:, :, c0:c0 + self.Wc].contiguous().to(device) if table is not None else None
+        self.table = table[:, c0:c0 + self.Wc].contiguous().to(device) if table is not None else None      # [C, slot_c, slot_r]
         self.tf_mode = tf_mode
         self.row_chunked = 1 if (row_chunked and tf_mode == 0) else 0
         self.tw_h, self.tw_w, self.tw_c = N.twiddles(Hp, device), N.twiddles(Wp, device), N.twiddles(self.Wc, device)

@@ -153,6 +153,19 @@ static void run_p2_k2(const ColArgs& a, int gx, int gy, int nt, size_t smem) {
     cpx* s = (cpx*)buf.data();
     for (int by = 0; by < gy; ++by)
         for (int bx = 0; bx < gx; ++bx) {
+            if constexpr (p2_k2_fast_ok(N)) {
+                if (a.fast) {          // the specialised column kernel thz_p2_k2f
+                    constexpr int NT = p2_col_threads(N);
+                    for_threads(nt, [&](int t) { p2k2f_first<N, COLS, NT>(a, s, bx, by, t); });
+                    e_fwd_cols<N, 1, NS - 1, COLS>(s, nt, tws.data());
+                    if (a.tf.mode == 0) for_threads(nt, [&](int t) { p2k2f_middle<N, COLS, NT, 0>(a, s, bx, by, t); });
+                    else if (a.tf.mode == 1) for_threads(nt, [&](int t) { p2k2f_middle<N, COLS, NT, 1>(a, s, bx, by, t); });
+                    else for_threads(nt, [&](int t) { p2k2f_middle<N, COLS, NT, 2>(a, s, bx, by, t); });
+                    e_inv_cols<N, NS - 2, 1, COLS>(s, nt, tws.data());
+                    for_threads(nt, [&](int t) { p2k2f_last<N, COLS, NT>(a, s, tws.data(), bx, by, t); });
+                    continue;
+                }
+            }
             for_threads(nt, [&](int t) { p2k2_first<N, COLS>(a, s, bx, by, t, nt); });
             e_fwd_cols<N, 1, NS - 1, COLS>(s, nt, tws.data());
             for_threads(nt, [&](int t) { p2k2_middle<N, COLS>(a, s, bx, by, t, nt); });

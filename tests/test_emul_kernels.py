@@ -218,7 +218,7 @@ def test_slab_descriptor_is_validated():
 
 
 @pytest.mark.parametrize("env", [dict(THZ_NO_TILED="1"), dict(THZ_NO_PRUNE="1"), dict(THZ_T1_LOG2="3"), dict(THZ_T1_LOG2="2", THZ_T2_LOG2="3"),
-                                 dict(THZ_T2_LOG2="2"), dict(THZ_NO_P2="1")], ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+                                 dict(THZ_T2_LOG2="2"), dict(THZ_NO_P2="1"), dict(THZ_NO_K2FAST="1"), dict(THZ_NO_K2FAST="1", MODE0="1")], ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_layout_and_pruning_switches_do_not_change_the_result(env, monkeypatch):
     """The A/B switches of DESIGN 3.5 (row-major / blocked intermediates of either width, full instead of pruned stages,
     runtime-planned engine) select different code for the same arithmetic: forward and DOE adjoint must agree with the default
@@ -231,8 +231,10 @@ def test_layout_and_pruning_switches_do_not_change_the_result(env, monkeypatch):
     h = torch.rand(H, W) * 1e-3
     coef = AH.doe_coefficients(lams, 2.66, 0.003)
 
+    mode = 0 if env.get("MODE0") else 1          # THZ_NO_K2FAST: the general column kernel instead of thz_p2_k2f, table and vectors
+
     def run():
-        base, _ = _setup(B, C, H, W, None, lams, dxy, z, mode=1)
+        base, _ = _setup(B, C, H, W, None, lams, dxy, z, mode=mode)
         y = torch.zeros_like(x)
         _run(x, dict(base, x=x, y=y, doe_mode=1, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef))
         gx, gh = torch.zeros_like(x), torch.zeros(H, W)
