@@ -336,6 +336,36 @@ def secondary_multi(dev, rank, world, lib, sm_mhz, hbm_peak):
         "rank0_stage_ms": stages}
     del slab, xl, fl
     torch.cuda.empty_cache()
+    # ---- C3 sharded over wavelengths: the 16 lambda of config 3 dealt over the ranks (strong scaling, no collective forward)
+    from quantizationawarethzdoe_b200 import CZT_prop
+    H, M, C = 2048, 1024, 16
+    if C % world == 0:
+        clo, chi = P.shard_range(C, rank, world)
+        lam_all = wavelengths(C)
+        torch.manual_seed(300)
+        xc = torch.randn(1, chi - clo, H, H, dtype=torch.complex64, device=dev)
+        prop = CZT_prop(z_distance=0.5, device=dev)
+        fc = ElectricField(xc, wavelengths=torch.tensor(lam_all[clo:chi], dtype=torch.float32, device=dev), spacing=sp, device=dev)
+        tc0, simt0 = lib.thz_launch_count_class(8), lib.thz_launch_count_class(6)
+        for _ in range(2):
+            prop(fc, M, M, 0.1 * mm, 0.1 * mm)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        e0.record()
+        for _ in range(5):
+            prop(fc, M, M, 0.1 * mm, 0.1 * mm)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = max_ms(e0.elapsed_time(e1) / 5)
+        flops = 8.0 * (M * H * H + M * H * M) * C
+        bf16, bf16_src = _bf16_peak()
+        tfl = 3 * flops / (ms * 1e-3) / 1e12
+        out["c3_czt_16lambda_sharded"] = {
+            "forward_ms": ms, "scaling": "strong", "n_gpus": world, "wavelengths_per_gpu": chi - clo, "tensor_tflops_3xtf32_aggregate": tfl,
+            "frac_of_aggregate_tf32_peak": tfl / (0.5 * bf16 * world), "peak_source": "1/2 x " + bf16_src,
+            "kernel": "tcgen05 3xTF32" if lib.thz_launch_count_class(8) > tc0 and lib.thz_launch_count_class(6) == simt0 else "CUDA-core fp32"}
+        del xc, fc, prop
+        torch.cuda.empty_cache()
     # ---- C4 data parallel
     n, B, layers = 200, 1024, 3
     torch.manual_seed(0)

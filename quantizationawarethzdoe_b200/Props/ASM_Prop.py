@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from .. import asm_host as AH
+from .. import bluestein as BL
 from .. import functional as Fn
 from ..DataType.ElectricField import ElectricField
 
@@ -162,6 +163,17 @@ class ASM_prop(nn.Module):
                 else:
                     print("The critical distance is {} m, the TF will be fine during the sampling !".format(Zc.numpy()))
                 self.check_Zc = False
+            if not (BL.length_supported(Hp) and BL.length_supported(Wp)):
+                # an edge length with a prime factor > 7 (the reference's torch.fft takes any size): chirp-z on the fused
+                # pipeline, transfer function = the reference's own (host-built, as in 'cached')
+                Hc = AH.tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
+                unpad = bool(self.do_padding and self.do_unpad_after_pad)
+                self._plan = BL.BluesteinAsmPlan(C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, torch.fft.ifftshift(Hc, dim=(-2, -1)))
+                self.resolved_kernel_mode = 'cached (chirp-z, length %d x %d)' % (Hp, Wp)
+                self._plan_key = key
+                self._fast_key = fast
+                self._fast_refs = (spacing, wavelengths)
+                return self._plan
             rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
             table, mode = None, 0
             chunked = AH.row_vectors_chunked(Hp)
@@ -199,6 +211,9 @@ class ASM_prop(nn.Module):
             B, C, H, W = data.shape
             dev = data.device
         plan = self._get_plan(B, C, H, W, field.spacing, wavelengths, dev)
+        if isinstance(plan, BL.BluesteinAsmPlan):      # DOE modulation (if any) is materialised by its own kernel first
+            out = BL.BluesteinAsmFn.apply(field.data, plan)
+            return ElectricField(data=out, wavelengths=wavelengths, spacing=field.spacing, device=dev)
         if deferred is not None:
             out = Fn.DoeAsmFn.apply(deferred.x, deferred.height_map, plan, deferred.coef)
         else:

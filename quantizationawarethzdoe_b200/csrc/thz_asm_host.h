@@ -116,9 +116,26 @@ static inline void thz_asm_apply_p2(const thz_asm_desc* d, int nbc, int sm_count
         L->k3.lines = lines;
         L->k3_threads = threads;
         L->k3_gridx = (d->outH + lines - 1) / lines;
+        // Split of the field axis over gridDim.y.  Each CTA walks bc_per_cta fields (register accumulators for grad_height, the
+        // next field's rows prefetched), so the cost of a launch is  waves x bc_per_cta  with waves counted against the CTAs
+        // that are resident at once (3 per SM, 1 for the 8192+ lines): pick the split that minimises it.  The old rule
+        // (double until the grid reaches 4 x SMs) gave 640 CTAs on 444 slots for the 400-point lines of the DONN config --
+        // 1.44 waves, the second one less than half full (profiles/r02_donn_ncu_summary.txt).
+        const long resident = (long)sm_count * (d->Wp >= 8192 ? 1 : 3);
         int gy = 1;
-        while (gy < nbc && (long)L->k3_gridx * gy < 4L * sm_count) gy <<= 1;
-        gy = thz_imin(gy, nbc);
+        if (L->k3_gridx < resident && nbc > 1) {
+            long best = -1;
+            const int gy_max = thz_imin(nbc, (int)(4 * resident / L->k3_gridx) + 1);
+            for (int cand = 1; cand <= gy_max; ++cand) {
+                const int per = (nbc + cand - 1) / cand, eff = (nbc + per - 1) / per;
+                const long waves = ((long)L->k3_gridx * eff + resident - 1) / resident;
+                const long cost = waves * per;
+                if (best < 0 || cost < best) {
+                    best = cost;
+                    gy = eff;
+                }
+            }
+        }
         L->k3.bc_per_cta = (nbc + gy - 1) / gy;
         L->k3_gridy = (nbc + L->k3.bc_per_cta - 1) / L->k3.bc_per_cta;
         L->k3_smem = (p2_row_pipelined(d->Wp) ? 2 * smem : smem) + tw_bytes;   // double-buffered line (thz_p2_k3 prefetches the next field)

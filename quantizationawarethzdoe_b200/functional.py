@@ -473,10 +473,21 @@ class FieldMulFn(torch.autograd.Function):
         return FieldMulFn._run(_c64(g, "grad_output"), ctx.m, ctx.real, ctx.per_channel, 1), None
 
 
+_bluestein_fft2 = {}
+
+
 def fft2_c2c(x, inverse=False, ortho=False):
-    """Stand-alone natural-order batched 2-D FFT over the last two dims (thz_fft2_c2c)."""
+    """Stand-alone natural-order batched 2-D FFT over the last two dims (thz_fft2_c2c); sizes with a prime factor > 7 go
+    through the chirp-z path (bluestein.BluesteinFft2) -- any size torch.fft.fft2 takes, up to 8192 per edge."""
     x = _c64(x, "input")
     H, W = x.shape[-2], x.shape[-1]
+    from . import bluestein as BL
+    if not (BL.length_supported(H) and BL.length_supported(W)):
+        key = (H, W, bool(inverse), bool(ortho), str(x.device))
+        plan = _bluestein_fft2.get(key)
+        if plan is None:
+            plan = _bluestein_fft2[key] = BL.BluesteinFft2(H, W, bool(inverse), bool(ortho), x.device)
+        return plan(x)
     batch = x.numel() // (H * W)
     y = torch.empty_like(x)
     ws = _workspace(batch * H * W, x.device)

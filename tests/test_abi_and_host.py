@@ -187,3 +187,24 @@ def test_loss_landscape_host_helpers(tmp_path):
     assert torch.allclose(m.weight.data, w0[0])                 # 0.5 * 1 - 0.25 * 2 = 0
     CL.overwrite_weights(m, w0, [[torch.ones(2, 2)], [2 * torch.ones(2, 2)]], (1.0, 1.0))
     assert torch.allclose(m.weight.data, w0[0] + 3)
+
+
+def test_chirp_z_host_tables():
+    """bluestein.py host math, no GPU: exact chirp phases, convolution length, and the kernel spectrum reproduces a DFT when the
+    convolution is carried out with numpy."""
+    from quantizationawarethzdoe_b200 import bluestein as BL
+    assert BL.conv_length(202) == 512 and BL.conv_length(8) == 16 and BL.conv_length(8192) == 16384
+    with pytest.raises(NotImplementedError, match="chirp convolution"):
+        BL.conv_length(8209)
+    n = 101
+    w = BL.chirp(n)
+    j = np.arange(n)
+    assert np.allclose(w, np.exp(-1j * np.pi * (j.astype(np.float64) ** 2) / n), atol=1e-12)
+    rng = np.random.default_rng(0)
+    H, W = 13, 10
+    x = rng.standard_normal((H, W)) + 1j * rng.standard_normal((H, W))
+    L1, L2 = BL.conv_length(H), BL.conv_length(W)
+    a = np.zeros((L1, L2), complex)
+    a[:H, :W] = x * np.outer(BL.chirp(H), BL.chirp(W))
+    b = np.fft.ifft2(np.fft.fft2(a) * BL.kernel_spectrum(H, W, L1, L2))[:H, :W]
+    assert np.allclose(b * np.outer(BL.chirp(H), BL.chirp(W)), np.fft.fft2(x), atol=1e-10)

@@ -323,3 +323,69 @@ def test_score_thickness_body_replay(func):
     assert E.thz_emul_score_thickness(P(t.contiguous()), P(lut), 4, s, ["sigmoid", "log", "poly", "sine", "chirp"].index(func), P(out),
                                       2, 63) == 0
     assert rel_l2(out, ref) < 2e-6
+
+
+def _install_bluestein_cpu(monkeypatch):
+    """Kernel replay for thz_asm_propagate + a torch twin of the pointwise multiply kernel (thz_field_mul has no replay)."""
+    import ctypes
+    from quantizationawarethzdoe_b200 import _native as Nn, functional as Fn
+    E = emul_lib()
+
+    def call(desc, device):
+        rc = E.thz_emul_asm_propagate(ctypes.byref(desc), 148)
+        assert rc == 0, rc
+
+    def field_mul(x, m, real, per_channel, conj):
+        B, C, H, W = x.shape
+        mm_ = m.reshape((C if per_channel else 1), H, W)
+        return x * (mm_.conj() if (conj and not real) else mm_)[None]
+
+    monkeypatch.setattr(Fn, "_asm_call", call)
+    monkeypatch.setattr(Fn.FieldMulFn, "_run", staticmethod(field_mul))
+    monkeypatch.setattr(Nn, "require_cuda", lambda t, name="tensor": None)
+    monkeypatch.setattr(Nn, "twiddles", lambda n, device: Nn.twiddles_host(n))
+    monkeypatch.setattr(Nn, "slot_to_bin", lambda n, fn=None, _orig=Nn.slot_to_bin: _orig(n, E.thz_emul_slot_to_bin))
+
+
+@pytest.mark.parametrize("H,W,scale", [(26, 17, None),       # 52 x 34: 13 and 17 are beyond the radix plans
+                                       (11, 32, 2)])         # 33 x 96: one unsupported edge is enough
+def test_any_length_asm_through_chirp_z(H, W, scale, monkeypatch):
+    """Grids whose padded edge has a prime factor > 7 (the reference's torch.fft takes any size): the chirp-z path
+    (bluestein.py: pointwise chirp -> fused convolution -> transfer function -> fused convolution -> chirp) against the
+    oracle, forward and adjoint, with the real kernel bodies replayed on the CPU."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, bluestein as BL
+    _install_bluestein_cpu(monkeypatch)
+    monkeypatch.setattr(BL, "length_supported", lambda n: E_plan_ok(n))
+    lams, dxy, z = [1e-3, 1.04e-3], 0.5e-3, 0.05
+    torch.manual_seed(0)
+    x = torch.randn(2, 2, H, W, dtype=torch.complex64)
+    g = torch.randn(2, 2, H, W, dtype=torch.complex64)
+    asm = ASM_prop(z_distance=z, padding_scale=scale, device=torch.device("cpu"))
+    asm.check_Zc = False
+    xr = x.clone().requires_grad_(True)
+    y = asm(ElectricField(xr, wavelengths=lams, spacing=dxy, device=torch.device("cpu"))).data
+    assert "chirp-z" in asm.resolved_kernel_mode
+    (gx,) = torch.autograd.grad(y, xr, g)
+    xo = x.clone().requires_grad_(True)
+    yo = AO.asm_forward(xo, lams, dxy, z, padding_scale=scale)
+    (gxo,) = torch.autograd.grad(yo, xo, g)
+    assert rel_l2(y.detach(), yo.detach()) < TOL and rel_l2(gx, gxo) < TOL
+
+
+def E_plan_ok(n):
+    import ctypes
+    E = emul_lib()
+    rad, ns = (ctypes.c_int32 * 16)(), ctypes.c_int32(0)
+    return E.thz_emul_plan_info(int(n), rad, ctypes.byref(ns)) == 0
+
+
+@pytest.mark.parametrize("H,W", [(13, 22), (34, 19)])
+def test_any_length_fft2_through_chirp_z(H, W, monkeypatch):
+    from quantizationawarethzdoe_b200 import bluestein as BL
+    _install_bluestein_cpu(monkeypatch)
+    torch.manual_seed(1)
+    x = torch.randn(3, 1, H, W, dtype=torch.complex64)
+    for inverse, ortho in ((False, False), (True, False), (False, True), (True, True)):
+        ref = (torch.fft.ifft2 if inverse else torch.fft.fft2)(x, norm="ortho" if ortho else "backward")
+        got = BL.BluesteinFft2(H, W, inverse, ortho, torch.device("cpu"))(x)
+        assert rel_l2(got, ref) < 3e-6, (inverse, ortho)

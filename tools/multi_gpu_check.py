@@ -97,6 +97,24 @@ if rank == 0:
     print("DOE-fused slab over %d GPUs vs single GPU: fwd %.2e grad_x %.2e grad_w %.2e" % (world, e[0], e[1], e[2]))
 ok &= bool(e.max() < 2e-6)
 
+# ---- chirp-z propagation sharded over wavelengths (independent units, no collective) vs all wavelengths on one GPU
+from quantizationawarethzdoe_b200 import CZT_prop  # noqa: E402
+Cz = 2 * world
+lam_z = [1 * mm * (1 + 0.02 * c) for c in range(Cz)]
+torch.manual_seed(11)
+xz = torch.randn(1, Cz, 256, 256, dtype=torch.complex64, device=dev)
+czt = CZT_prop(z_distance=0.4, device=dev)
+mine_z = P.shard_field(ElectricField(xz, wavelengths=lam_z, spacing=0.5 * mm, device=dev), rank, world)
+yz = czt(mine_z, 128, 128, 0.2 * mm, 0.2 * mm).data
+czt_full = CZT_prop(z_distance=0.4, device=dev)
+yz_full = czt_full(ElectricField(xz, wavelengths=lam_z, spacing=0.5 * mm, device=dev), 128, 128, 0.2 * mm, 0.2 * mm).data
+zlo, zhi = P.shard_range(Cz, rank, world)
+e = torch.tensor([rel(yz, yz_full[:, zlo:zhi])], device=dev)
+dist.all_reduce(e, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("CZT sharded over %d x %d wavelengths vs one GPU: %.2e" % (world, Cz // world, e[0]))
+ok &= bool(e.max() < 1e-6)
+
 # ---- data parallel over wavelengths
 C = 2 * world
 lam_all = [1 * mm * (1 + 0.01 * c) for c in range(C)]
