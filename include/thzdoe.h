@@ -146,6 +146,15 @@ typedef struct thz_asm_desc {
        entries, doe_hmap = float32 [B][inH][inW] -- B candidate DOEs evaluated in one pass (loss-landscape sweeps,
        VisTools/calc_loss.py:8-55).  The adjoint (doe_mode 2) takes a shared map only. */
     int64_t doe_hmap_bstride;
+    /* Fixed pointwise optical elements in FRONT of the (DOE +) propagation, fused like the DOE instead of a pass of their
+       own: an aperture mask (Components/Aperture.py:105-135) and / or a thin-lens kernel per wavelength
+       (Components/Thin_Lens.py:31-85).  elem_mode 0: none; 1 (forward calls): x is multiplied by mask * mul on load, before
+       the DOE phase; 2 (adjoint calls): the output is multiplied by mask * conj(mul) and, with doe_mode 2, grad_height is
+       formed against xsaved * mask * mul.  Sizes follow the region they apply to (forward: inH x inW, adjoint: outH x outW). */
+    int32_t elem_mode;
+    int32_t reserved3;
+    const void* elem_mask;     /* float32 [H,W] or NULL      */
+    const void* elem_mul;      /* complex64 [C,H,W] or NULL  */
 } thz_asm_desc;
 
 /* Bytes of `ws` a call with this descriptor needs (uses B, C, inH, outH, Hp, Wp, bc_chunk, stages, slab_parts): one

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fn
-from ..DataType.ElectricField import ElectricField
+from ..DataType.ElectricField import DeferredElements, ElectricField
 
 
 class ApertureElement(nn.Module):
@@ -53,7 +53,9 @@ class ApertureElement(nn.Module):
         return torch.where((torch.abs(X) <= rect_width / 2) & (torch.abs(Y) <= rect_height / 2), 1, 0)[None, None]
 
     def forward(self, field):
-        data = field.data
+        pend = DeferredElements.pending(field)
+        data = pend.x if pend is not None else field.data
+        Fn.N.require_cuda(data, "field.data")
         key = (tuple(data.shape[-2:]), tuple(field.spacing.detach().cpu().tolist()), self.aperture_type,
                None if self.aperture_size is None else float(self.aperture_size), str(data.device))
         if key != self._key:
@@ -68,5 +70,16 @@ class ApertureElement(nn.Module):
             self.aperture = mask.to(data.device)
             self._mask_f32 = mask[0, 0].to(torch.float32).to(data.device).contiguous()
             self._key = key
-        out = Fn.FieldMulFn.apply(data, self._mask_f32)
-        return ElectricField(data=out, wavelengths=field.wavelengths, spacing=field.spacing, device=out.device)
+        # deferred: folded into the next propagation's prologue (or evaluated by thz_field_mul when someone reads `.data`)
+        if pend is not None:
+            mask = self._mask_f32 if pend.mask is None else self._combined(pend.mask, self._mask_f32)
+            d = DeferredElements(pend.x, mask, pend.mul)
+        else:
+            d = DeferredElements(data, self._mask_f32, None)
+        return ElectricField._from_deferred(d, field)
+
+    def _combined(self, a, b):
+        key = (id(a), a._version, id(b), b._version)
+        if getattr(self, "_comb_key", None) != key:
+            self._comb, self._comb_key, self._comb_refs = (a * b).contiguous(), key, (a, b)
+        return self._comb

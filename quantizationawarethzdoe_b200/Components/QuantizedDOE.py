@@ -52,17 +52,23 @@ def _default_device(device):
 
 
 class _DeferredModulation:
-    """x * p(h), not yet evaluated.  ASM_prop consumes (x, height_map, coef) directly."""
+    """x * [mask * mul] * p(h), not yet evaluated.  ASM_prop consumes (x, height_map, coef, mask, mul) directly."""
 
-    def __init__(self, x, height_map, coef, rows=None):
+    def __init__(self, x, height_map, coef, rows=None, mask=None, mul=None):
         self.x, self.height_map, self.coef = x, height_map, coef
         self.shape = x.shape
         self.device = x.device
         self.rows = rows          # (lo, hi): x holds only these rows of the grid the height map covers (slab-decomposed fields)
+        self.mask, self.mul = mask, mul       # pointwise elements in front of the DOE (DataType.ElectricField.DeferredElements)
 
     def materialise(self):
         hm = self.height_map if self.rows is None else self.height_map[self.rows[0]:self.rows[1]]
-        return Fn.DoeModulateFn.apply(self.x, hm, self.coef)
+        x = self.x
+        if self.mask is not None:
+            x = Fn.FieldMulFn.apply(x, self.mask)
+        if self.mul is not None:
+            x = Fn.FieldMulFn.apply(x, self.mul)
+        return Fn.DoeModulateFn.apply(x, hm, self.coef)
 
 
 class DOELayer(nn.Module):
@@ -113,11 +119,17 @@ class DOELayer(nn.Module):
         if full_h != hm.shape[0] or input_field.width != hm.shape[1]:
             hm = nn.functional.interpolate(hm[None, None, :, :], size=[full_h, input_field.width], mode='nearest')
         self._height_map_ = torch.squeeze(hm, (0, 1)) if hm.ndim == 4 else hm
-        x = input_field.data
+        # an aperture / lens applied just before (still un-evaluated) rides along: x m p(h) in one fused prologue
+        pend = getattr(input_field, "_deferred", None) if getattr(input_field, "_data", None) is None else None
+        mask = mul = None
+        if pend is not None and getattr(pend, "is_elements", False) and slab is None:
+            x, mask, mul = pend.x, pend.mask, pend.mul
+        else:
+            x = input_field.data
         N.require_cuda(x, "field.data")
         coef = self._coef(input_field.wavelengths, epsilon, tand, x.device)
         rows = (slab[0] * input_field.height, (slab[0] + 1) * input_field.height) if slab is not None else None
-        deferred = _DeferredModulation(x, self._height_map_.to(x.device), coef, rows=rows)
+        deferred = _DeferredModulation(x, self._height_map_.to(x.device), coef, rows=rows, mask=mask, mul=mul)
         return ElectricField._from_deferred(deferred, input_field)
 
 

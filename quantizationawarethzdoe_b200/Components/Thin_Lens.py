@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fn
-from ..DataType.ElectricField import ElectricField
+from ..DataType.ElectricField import DeferredElements, ElectricField
 
 
 class Thin_LensElement(nn.Module):
@@ -39,6 +39,22 @@ class Thin_LensElement(nn.Module):
         return self._ker
 
     def forward(self, field):
-        ker = self.create_lens_phase_shift_kernel(field)
-        out = Fn.FieldMulFn.apply(field.data, ker[0])
-        return ElectricField(data=out, wavelengths=field.wavelengths, spacing=field.spacing, device=out.device)
+        """Deferred: the multiply is folded into the next propagation's prologue (or evaluated by thz_field_mul when someone
+        reads `.data`)."""
+        ker = self.create_lens_phase_shift_kernel(field)[0]
+        pend = DeferredElements.pending(field)
+        if pend is not None:
+            mul = ker if pend.mul is None else self._combined(pend.mul, ker)
+            d = DeferredElements(pend.x, pend.mask, mul)
+        else:
+            data = field.data
+            Fn.N.require_cuda(data, "field.data")
+            d = DeferredElements(data, None, ker)
+        return ElectricField._from_deferred(d, field)
+
+    def _combined(self, a, b):
+        """Product of two per-wavelength kernels, formed once per pair of tensors (stacked lenses)."""
+        key = (id(a), a._version, id(b), b._version)
+        if getattr(self, "_comb_key", None) != key:
+            self._comb, self._comb_key, self._comb_refs = (a * b).contiguous(), key, (a, b)
+        return self._comb

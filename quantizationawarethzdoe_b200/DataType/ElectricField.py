@@ -14,6 +14,34 @@ from __future__ import annotations
 import torch
 
 
+class DeferredElements:
+    """x * mask * mul, not yet evaluated: the output of an aperture / thin lens.  The next consumer fuses it --
+    ASM_prop multiplies on load in its row-FFT prologue (and by the conjugate in the adjoint's epilogue), a DOE layer passes
+    it on in front of its own phase; reading `.data` evaluates it with the stand-alone kernel.  Pointwise factors commute,
+    so further elements simply fold into `mask` (float32 [H,W]) and `mul` (complex64 [C,H,W])."""
+    is_elements = True
+
+    def __init__(self, x, mask=None, mul=None):
+        self.x, self.mask, self.mul = x, mask, mul
+        self.shape = x.shape
+        self.device = x.device
+
+    def materialise(self):
+        from .. import functional as Fn
+        x = self.x
+        if self.mask is not None:
+            x = Fn.FieldMulFn.apply(x, self.mask)
+        if self.mul is not None:
+            x = Fn.FieldMulFn.apply(x, self.mul)
+        return x
+
+    @staticmethod
+    def pending(field):
+        """The un-evaluated element chain `field` carries, or None."""
+        d = getattr(field, "_deferred", None) if getattr(field, "_data", None) is None else None
+        return d if (d is not None and getattr(d, "is_elements", False)) else None
+
+
 class ElectricField:
     _BATCH = 0
     _WAVELENGTH = 1

@@ -214,8 +214,10 @@ class ASM_prop(nn.Module):
         if isinstance(plan, BL.BluesteinAsmPlan):      # DOE modulation (if any) is materialised by its own kernel first
             out = BL.BluesteinAsmFn.apply(field.data, plan)
             return ElectricField(data=out, wavelengths=wavelengths, spacing=field.spacing, device=dev)
-        if deferred is not None:
-            out = Fn.DoeAsmFn.apply(deferred.x, deferred.height_map, plan, deferred.coef)
+        if deferred is not None and getattr(deferred, "is_elements", False):        # aperture / lens only: fused on load
+            out = Fn.AsmPropagateFn.apply(deferred.x, plan, deferred.mask, deferred.mul)
+        elif deferred is not None:                                                  # [aperture / lens +] DOE: fused on load
+            out = Fn.DoeAsmFn.apply(deferred.x, deferred.height_map, plan, deferred.coef, deferred.mask, deferred.mul)
         else:
             out = Fn.AsmPropagateFn.apply(data, plan)
         return ElectricField(data=out, wavelengths=wavelengths, spacing=field.spacing, device=dev)

@@ -144,7 +144,8 @@ def calulate_single_element_loss_landscape(args, model, target, loss_f=nn.MSELos
     parts = _parts(model)
     if parts is not None:
         field, doe, prop = parts
-        x = field.data.contiguous()
+        pend = getattr(field, "_deferred", None) if getattr(field, "_data", None) is None else None
+        x = (pend.x if (pend is not None and getattr(pend, "is_elements", False)) else field.data).contiguous()
         if x.shape[0] != 1 or not hasattr(prop, "_get_plan") or not hasattr(prop, "kernel_mode"):
             parts = None                # a batch of input fields / not an ASM propagator: evaluate point by point
     if parts is not None:
@@ -161,7 +162,7 @@ def calulate_single_element_loss_landscape(args, model, target, loss_f=nn.MSELos
                 maps.append(d.height_map.to(torch.float32))
                 coef = d.coef
             hm = torch.stack(maps).contiguous()                  # [Bc, H, W]
-            out = Fn.doe_asm_sweep(x, hm, prop, coef, field.spacing, field.wavelengths)
+            out = Fn.doe_asm_sweep(x, hm, prop, coef, field.spacing, field.wavelengths, d.mask, d.mul)
             vec[sel] = _losses_of(out, target, loss_f)
     else:
         for k in mine:

@@ -48,6 +48,8 @@ class AsmDesc(ctypes.Structure):
         ("slab_ptrs", ctypes.c_void_p * 8),
         ("tf_row_chunked", ctypes.c_int32), ("reserved2", ctypes.c_int32),
         ("doe_hmap_bstride", ctypes.c_int64),
+        ("elem_mode", ctypes.c_int32), ("reserved3", ctypes.c_int32),
+        ("elem_mask", ctypes.c_void_p), ("elem_mul", ctypes.c_void_p),
     ]
 
 

@@ -189,6 +189,8 @@ extern "C" int thz_fft2_c2c(const void* x, void* y, int32_t batch, int32_t H, in
     a1.plan = pw;
     a1.tw = (const cpx*)tw_w;
     a1.doe.hmap = nullptr;
+    a1.elem.mask = nullptr;
+    a1.elem.mul = nullptr;
     a1.doe.hstride = 0;
     a1.doe.b0 = 0;
     a1.conj_in = inverse ? 1 : 0;

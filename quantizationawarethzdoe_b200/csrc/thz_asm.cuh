@@ -33,6 +33,22 @@ struct DoeArgs {
     long long hstride;        // 0: one map for every batch entry; else floats between the maps of consecutive batch entries
                               // (forward only: a sweep of DOE candidates over one input field)
 };
+// Fixed pointwise optical elements in front of the (DOE +) propagation -- aperture masks and thin-lens kernels
+// (Components/Aperture.py:105-135, Components/Thin_Lens.py:31-85) -- folded into the row-FFT prologue (forward:
+// x m) and the row-iFFT epilogue of the adjoint (gx conj(m); the DOE's grad_height sees x m), instead of a pass of their own.
+struct ElemArgs {
+    const float* mask;        // real [H][W] or NULL
+    const cpx* mul;           // complex [C][H][W], one kernel per wavelength, or NULL
+};
+THZ_HD cpx thz_elem_apply(const ElemArgs& e, cpx v, int chan, size_t hw, size_t rc, bool conj) {
+    if (e.mask) v = cscale(v, thz_ldg(e.mask + rc));
+    if (e.mul) {
+        const cpx m = thz_ldg(e.mul + (size_t)chan * hw + rc);
+        v = conj ? cmulc(v, m) : cmul(v, m);
+    }
+    return v;
+}
+
 // height map of field i of a chunk whose first field has wavelength index c0 (batch entry b0 + (c0 + i) / C)
 THZ_HD const float* thz_doe_map(const DoeArgs& d, int c0, int C, int i) {
     return d.hstride ? d.hmap + (size_t)(d.b0 + (c0 + i) / C) * (size_t)d.hstride : d.hmap;
@@ -106,6 +122,7 @@ struct RowFwdArgs {
     FftPlan plan;             // length Wp
     const cpx* tw;
     DoeArgs doe;
+    ElemArgs elem;            // pointwise elements applied on load (forward passes only)
     int conj_in;              // conjugate on load (inverse transforms via conj . FFT . conj)
     SlabArgs slab;            // parts > 1: scatter the output rows into column slabs instead of T
     int half_in;              // 1: the input columns are exactly [Wp/4, 3Wp/4) (centred 2x padding): pruned first stage
@@ -130,12 +147,14 @@ THZ_HD void k1_load(const RowFwdArgs& a, cpx* s, int bx, int tid, int nthreads) 
             cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
             hr = thz_doe_map(a.doe, a.c0, a.C, f) + (size_t)r * a.inW;
         }
+        const bool has_elem = a.elem.mask || a.elem.mul;
         for (int p = tid; p < a.Wp; p += nthreads) {
             const int c = p - a.in_c0;
             cpx v = cmake(0.f, 0.f);
             if (c >= 0 && c < a.inW) {
                 v = xr[c];
                 if (a.conj_in) v.y = -v.y;
+                if (has_elem) v = thz_elem_apply(a.elem, v, (a.c0 + f) % a.C, (size_t)a.inH * a.inW, (size_t)r * a.inW + c, false);
                 if (hr) v = cmul(v, thz_doe_phase(thz_ldg(hr + c), cf, a.doe.base));
             }
             sl[thz_pad(p)] = v;
@@ -289,6 +308,7 @@ struct RowInvArgs {
     const cpx* xsaved;        // [nbc][outH][outW] field that entered the DOE
     float* gh;                // [outH][outW]
     int gh_atomic;            // 1: several CTAs contribute to one gh element -> atomicAdd
+    ElemArgs elem;            // adjoint passes: gx gets conj(m), the DOE's grad_height sees the saved field times m
     SlabArgs slab;            // parts > 1: gather the input rows from column slabs instead of T
     int half_out;             // 1: the output columns are exactly [Wp/4, 3Wp/4): pruned last stage
     int t_tiled;              // k > 0: T is stored in 2^k-column blocks (experiment)
@@ -320,12 +340,17 @@ THZ_HD void k3_epilogue(const RowInvArgs& a, const cpx* s, int bx, int f, int ti
         // gamma_c = -k (0.5 tand sqrt(eps) + i (sqrt(eps) - 1))
         gamma = cmake(-cf.x * (0.5f * cf.y * cf.z), -cf.x * cf.w);
     }
-    if (!a.doe.hmap) {   // plain forward output: no accumulators, any block size
+    const bool has_elem = a.elem.mask || a.elem.mul;
+    const int chan = (a.c0 + f) % a.C;
+    const size_t hw = (size_t)a.outH * a.outW;
+    if (!a.doe.hmap) {   // plain output (or the adjoint of pointwise elements only): no accumulators, any block size
         for (int e = tid; e < block_elems; e += nthreads) {
             const int l = e / a.outW, c = e - l * a.outW;
             const int r = bx * a.lines + l;
             if (r >= a.outH) break;
-            a.y[((size_t)f * a.outH + r) * a.outW + c] = cscale(s[l * pitch + thz_pad(c + a.out_c0)], a.scale);
+            cpx v = cscale(s[l * pitch + thz_pad(c + a.out_c0)], a.scale);
+            if (has_elem) v = thz_elem_apply(a.elem, v, chan, hw, (size_t)r * a.outW + c, true);
+            a.y[((size_t)f * a.outH + r) * a.outW + c] = v;
         }
         return;
     }
@@ -339,9 +364,15 @@ THZ_HD void k3_epilogue(const RowInvArgs& a, const cpx* s, int bx, int f, int ti
         const cpx v = cscale(s[l * pitch + thz_pad(c + a.out_c0)], a.scale);
         const size_t o = ((size_t)f * a.outH + r) * a.outW + c;
         const cpx p = thz_doe_phase(thz_ldg(a.doe.hmap + (size_t)r * a.outW + c), cf, a.doe.base);
-        if (a.y) a.y[o] = cmulc(v, p);                       // gx = g' conj(p)
-        const cpx xp = cmul(cmul(a.xsaved[o], p), gamma);    // x p gamma
-        acc[k] += v.x * xp.x + v.y * xp.y;                   // Re(conj(g') x p gamma)
+        cpx xs = a.xsaved[o];
+        if (has_elem) xs = thz_elem_apply(a.elem, xs, chan, hw, (size_t)r * a.outW + c, false);     // the DOE saw x m
+        if (a.y) {                                           // gx = g' conj(p) conj(m)
+            cpx q = cmulc(v, p);
+            if (has_elem) q = thz_elem_apply(a.elem, q, chan, hw, (size_t)r * a.outW + c, true);
+            a.y[o] = q;
+        }
+        const cpx xp = cmul(cmul(xs, p), gamma);             // x m p gamma
+        acc[k] += v.x * xp.x + v.y * xp.y;                   // Re(conj(g') x m p gamma)
     }
 }
 

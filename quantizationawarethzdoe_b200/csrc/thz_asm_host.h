@@ -40,6 +40,8 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     if (d->doe_mode < 0 || d->doe_mode > 2) return THZ_E_SHAPE;
     if (d->doe_mode != 0 && (!d->doe_hmap || !d->doe_coef)) return THZ_E_NULL;
     if ((st & 4) && d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
+    if (d->elem_mode < 0 || d->elem_mode > 2 || (d->elem_mode != 0 && !d->elem_mask && !d->elem_mul)) return THZ_E_SHAPE;
+    if (d->elem_mode != 0 && d->slab_parts > 1) return THZ_E_UNSUPPORTED;      // the slab pipeline fuses the DOE only
     if (d->doe_hmap_bstride < 0 || (d->doe_hmap_bstride != 0 && d->doe_mode != 1)) return THZ_E_SHAPE;   // per-entry maps: forward only
     if ((st & 4) && d->doe_mode != 2 && !d->y) return THZ_E_NULL;
     if (d->slab_parts > 1) {
@@ -180,6 +182,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a1.doe.base = d->doe_base;
     a1.doe.b0 = f0 / d->C;
     a1.doe.hstride = d->doe_mode == 1 ? d->doe_hmap_bstride : 0;
+    a1.elem.mask = d->elem_mode == 1 ? (const float*)d->elem_mask : nullptr;
+    a1.elem.mul = d->elem_mode == 1 ? (const cpx*)d->elem_mul : nullptr;
     a1.conj_in = 0;
     memset(&a1.slab, 0, sizeof(a1.slab));
     memset(&L->k3.slab, 0, sizeof(L->k3.slab));
@@ -266,6 +270,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a3.doe.base = d->doe_base;
     a3.doe.b0 = 0;
     a3.doe.hstride = 0;
+    a3.elem.mask = d->elem_mode == 2 ? (const float*)d->elem_mask : nullptr;
+    a3.elem.mul = d->elem_mode == 2 ? (const cpx*)d->elem_mul : nullptr;
     a3.xsaved = d->doe_mode == 2 ? (const cpx*)d->doe_xsaved + (size_t)f0 * d->outH * d->outW : nullptr;
     a3.gh = (float*)d->doe_gh;
     {

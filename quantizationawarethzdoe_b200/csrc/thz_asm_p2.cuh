@@ -42,14 +42,22 @@ THZ_HD constexpr bool p2_row_pipelined(int N) { return N <= 8192; }
 struct K1Loader {
     const cpx* xr;      // row of x (NULL: line beyond the end of the batch)
     const float* hr;    // row of the height map (NULL: no DOE)
+    const float* mr;    // row of the aperture mask (NULL: none)
+    const cpx* kr;      // row of this wavelength's lens kernel (NULL: none)
     float4 cf;
     float base;
     int in_c0, inW, conj_in;
+    THZ_HD cpx elem(cpx v, int c) const {
+        if (mr) v = cscale(v, thz_ldg(mr + c));
+        if (kr) v = cmul(v, thz_ldg(kr + c));
+        return v;
+    }
     THZ_HD cpx operator()(int pos) const {
         const int c = pos - in_c0;
         if (xr == nullptr || (unsigned)c >= (unsigned)inW) return cmake(0.f, 0.f);   // one compare: c < 0 wraps
         cpx v = xr[c];
         if (conj_in) v.y = -v.y;
+        v = elem(v, c);
         if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
         return v;
     }
@@ -58,10 +66,16 @@ struct K1Loader {
         const int c = pos - in_c0;
         cpx v = xr[c];
         if (conj_in) v.y = -v.y;
+        v = elem(v, c);
         if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
         return v;
     }
 };
+// rows of the pointwise elements for line gl of a row kernel's chunk (field f = gl / inH, row r)
+THZ_HD void p2k1_elem_rows(const RowFwdArgs& a, K1Loader& ld, int f, int r) {
+    ld.mr = a.elem.mask ? a.elem.mask + (size_t)r * a.inW : nullptr;
+    ld.kr = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.inH + r) * a.inW : nullptr;
+}
 
 template <int N>
 THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
@@ -73,6 +87,8 @@ THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
         K1Loader ld;
         ld.xr = nullptr;
         ld.hr = nullptr;
+        ld.mr = nullptr;
+        ld.kr = nullptr;
         ld.cf = cmake4(0.f);
         ld.base = a.doe.base;
         ld.in_c0 = a.in_c0;
@@ -80,6 +96,7 @@ THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
         ld.conj_in = a.conj_in;
         if (gl < total_lines) {
             const int f = gl / a.inH, r = gl - f * a.inH;
+            p2k1_elem_rows(a, ld, f, r);
             ld.xr = a.x + (size_t)gl * a.inW;
             if (a.doe.hmap) {
                 ld.cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
@@ -130,12 +147,15 @@ THZ_HD void p2k1_first_staged(const RowFwdArgs& a, cpx* s, const cpx* xs, const 
         K1Loader ld;
         ld.xr = nullptr;
         ld.hr = nullptr;
+        ld.mr = nullptr;
+        ld.kr = nullptr;
         ld.cf = cmake4(0.f);
         ld.base = a.doe.base;
         ld.in_c0 = a.in_c0;
         ld.inW = a.inW;
         ld.conj_in = a.conj_in;
         if (gl < total_lines) {
+            p2k1_elem_rows(a, ld, gl / a.inH, gl % a.inH);
             ld.xr = xs + (size_t)line * a.inW;
             if (a.doe.hmap) {
                 ld.cf = thz_ldg(a.doe.coef + (a.c0 + gl / a.inH) % a.C);
@@ -480,6 +500,8 @@ struct K3Storer {
     cpx* yrow;            // output row (forward output or grad wrt field; may be NULL in DOE mode)
     const cpx* xrow;      // saved input row (DOE mode)
     const float* hrow;    // height-map row (DOE mode; NULL = plain forward)
+    const float* mrow;    // aperture-mask row (adjoint of pointwise elements; NULL: none)
+    const cpx* krow;      // lens-kernel row of this wavelength (NULL: none)
     float4 cf;
     cpx gamma;
     float base, scale;
@@ -507,17 +529,25 @@ struct K3Storer {
         if ((unsigned)c >= (unsigned)outW) return;
         emit(c, t, t, v);
     }
+    THZ_HD cpx elem(cpx v, int c, bool conj) const {     // pointwise elements in front of the DOE (thz_elem_apply per row)
+        if (mrow) v = cscale(v, thz_ldg(mrow + c));
+        if (krow) {
+            const cpx m = thz_ldg(krow + c);
+            v = conj ? cmulc(v, m) : cmul(v, m);
+        }
+        return v;
+    }
     THZ_HD void emit(int c, int slot, int t, cpx v) {
         v = cscale(v, scale);
         if (hrow == nullptr) {
-            yrow[c] = v;
+            yrow[c] = elem(v, c, true);            // plain output, or the adjoint of pointwise elements alone
             return;
         }
         const cpx p = thz_doe_phase(hq[slot % PF], cf, base);
-        const cpx q = cmulc(v, p);                 // grad wrt the field that entered the DOE
-        if (yrow) yrow[c] = q;
-        // gh += Re(conj(v) x p gamma) = Re(conj(q) x gamma)
-        const cpx xg = cmul(xq[slot % PF], gamma);
+        const cpx q = cmulc(v, p);                 // grad wrt the field that entered the DOE (= x m)
+        if (yrow) yrow[c] = elem(q, c, true);      // grad wrt x: conj(m) on top
+        // gh += Re(conj(v) (x m) p gamma) = Re(conj(q) (x m) gamma)
+        const cpx xg = cmul(elem(xq[slot % PF], c, false), gamma);
         acc[t] += q.x * xg.x + q.y * xg.y;
     }
 };
@@ -571,6 +601,8 @@ THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, 
         st.yrow = a.y ? a.y + o : nullptr;
         st.xrow = a.xsaved ? a.xsaved + o : nullptr;
         st.hrow = a.doe.hmap ? a.doe.hmap + (size_t)r * a.outW : nullptr;
+        st.mrow = a.elem.mask ? a.elem.mask + (size_t)r * a.outW : nullptr;
+        st.krow = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.outH + r) * a.outW : nullptr;
         st.acc = &acc[k * R];
         if (a.half_out) p2_last_inverse_stage_to<N, 1, true>(s + line * PITCH, j, tw, st);
         else p2_last_inverse_stage_to<N, 1>(s + line * PITCH, j, tw, st);

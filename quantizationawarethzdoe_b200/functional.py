@@ -80,7 +80,7 @@ class AsmPlan:
         self.tw_w = N.twiddles(Wp, device)
         self._descs = {}
 
-    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None, hmap_bstride=0):
+    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None, hmap_bstride=0, elem=None):
         """One thz_asm_propagate call.  Forward: x [B,C,H,W] -> y [B,C,outH,outW].
         Adjoint (conj=1): x = grad [B,C,outH,outW] -> y [B,C,H,W] (regions swapped)."""
         B, C = self.B, self.C
@@ -106,6 +106,11 @@ class AsmPlan:
         d.x, d.y, d.ws, d.ws_bytes = N.ptr(x), N.ptr(y), N.ptr(ws), ws.numel() * 8
         d.doe_hmap, d.doe_coef, d.doe_xsaved, d.doe_gh = N.ptr(hmap), N.ptr(coef), N.ptr(xsaved), N.ptr(gh)
         d.doe_hmap_bstride = int(hmap_bstride)
+        # pointwise elements in front of the propagation (aperture mask, lens kernel): on load in a forward pass, conjugated in
+        # the epilogue of an adjoint pass (thz_asm_desc.elem_*)
+        mask, mul = elem if elem is not None else (None, None)
+        d.elem_mode = 0 if (mask is None and mul is None) else (2 if conj else 1)
+        d.elem_mask, d.elem_mul = N.ptr(mask), N.ptr(mul)
         _asm_call(d, x.device)
         return y
 
@@ -114,11 +119,12 @@ class AsmPropagateFn(torch.autograd.Function):
     """y = ASM(x).  Backward = the adjoint pipeline with conj(H) (explicit kernel, not autograd replay)."""
 
     @staticmethod
-    def forward(ctx, x, plan):
+    def forward(ctx, x, plan, mask=None, mul=None):
+        """mask (float32 [H,W]) / mul (complex64 [C,H,W]): fixed pointwise elements in front of the propagation, fused."""
         x = _c64(x, "field.data")
         y = torch.empty(x.shape[0], plan.C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
-        plan.run(x, y, conj=0)
-        ctx.plan = plan
+        plan.run(x, y, conj=0, elem=(mask, mul))
+        ctx.plan, ctx.elem = plan, (mask, mul)
         return y
 
     @staticmethod
@@ -126,21 +132,21 @@ class AsmPropagateFn(torch.autograd.Function):
         plan = ctx.plan
         g = _c64(g, "grad_output")
         gx = torch.empty(g.shape[0], plan.C, plan.H, plan.W, dtype=torch.complex64, device=g.device)
-        plan.run(g, gx, conj=1)
-        return gx, None
+        plan.run(g, gx, conj=1, elem=ctx.elem)
+        return gx, None, None, None
 
 
 class DoeAsmFn(torch.autograd.Function):
     """y = ASM(x * p(h)) in one fused pipeline; backward returns grad wrt x (if needed) and wrt h."""
 
     @staticmethod
-    def forward(ctx, x, hmap, plan, coef):
+    def forward(ctx, x, hmap, plan, coef, mask=None, mul=None):
         x = _c64(x, "field.data")
         N.require_cuda(hmap, "height_map")
         hmap = hmap.to(torch.float32).contiguous()
         y = torch.empty(x.shape[0], plan.C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
-        plan.run(x, y, conj=0, doe_mode=1, hmap=hmap, coef=coef)
-        ctx.plan, ctx.coef = plan, coef
+        plan.run(x, y, conj=0, doe_mode=1, hmap=hmap, coef=coef, elem=(mask, mul))
+        ctx.plan, ctx.coef, ctx.elem = plan, coef, (mask, mul)
         ctx.save_for_backward(x, hmap)
         return y
 
@@ -153,19 +159,19 @@ class DoeAsmFn(torch.autograd.Function):
         gx = torch.empty_like(x) if need_x else None
         if need_h:
             gh = torch.empty(plan.H, plan.W, dtype=torch.float32, device=g.device)
-            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=gh)
+            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=gh, elem=ctx.elem)
         else:
             gh = None
-            # grad wrt x only: adjoint ASM then conj(p) multiply
+            # grad wrt x only: adjoint ASM (conj(m) of the pointwise elements in its epilogue), then the conj(p) multiply
             gtmp = torch.empty_like(x)
-            plan.run(g, gtmp, conj=1)
+            plan.run(g, gtmp, conj=1, elem=ctx.elem)
             N.check(N.lib().thz_doe_modulate_bwd(N.ptr(gtmp), None, N.ptr(hmap), N.ptr(coef), BASE_PLANE_THICKNESS,
                                                  N.ptr(gx), None, x.shape[0], x.shape[1], x.shape[2], x.shape[3],
                                                  N.current_stream_ptr(g.device)), "thz_doe_modulate_bwd")
-        return gx, gh, None, None
+        return gx, gh, None, None, None, None
 
 
-def doe_asm_sweep(x, hmaps, prop, coef, spacing, wavelengths):
+def doe_asm_sweep(x, hmaps, prop, coef, spacing, wavelengths, mask=None, mul=None):
     """B candidate DOEs over ONE input field in a single fused pass (forward only; loss-landscape sweeps):
     x complex64 [1,C,H,W], hmaps float32 [Bc,H,W] -> prop(x * p(hmaps[b])) for every b, complex64 [Bc,C,outH,outW].
     The field is broadcast over the candidates; the height map is per entry (thz_asm_desc.doe_hmap_bstride)."""
@@ -179,7 +185,7 @@ def doe_asm_sweep(x, hmaps, prop, coef, spacing, wavelengths):
     plan = prop._get_plan(Bc, C, H, W, spacing, wavelengths, x.device)
     xb = x.expand(Bc, C, H, W).contiguous()
     y = torch.empty(Bc, C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
-    plan.run(xb, y, conj=0, doe_mode=1, hmap=hmaps, coef=coef, hmap_bstride=H * W)
+    plan.run(xb, y, conj=0, doe_mode=1, hmap=hmaps, coef=coef, hmap_bstride=H * W, elem=(mask, mul))
     return y
 
 

@@ -377,7 +377,8 @@ class SlabAsm(torch.nn.Module):
         # a DOE layer's output arrives un-materialised (ElectricField._deferred): the slab pipeline fuses it like ASM_prop does.
         # The layer holds the FULL height map [H, W] (replicated parameters), the field is this rank's row slab.
         deferred = getattr(field, "_deferred", None) if getattr(field, "_data", None) is None else None
-        if deferred is not None and (deferred.rows is None or deferred.height_map.shape[0] != deferred.x.shape[2] * G):
+        if deferred is not None and (getattr(deferred, 'rows', None) is None or deferred.mask is not None or deferred.mul is not None or
+                                     deferred.height_map.shape[0] != deferred.x.shape[2] * G):
             deferred = None                     # not a row slab under a global map: materialise and propagate plainly
         data = deferred.x if deferred is not None else field.data
         B, C, Hl, W = data.shape

@@ -389,3 +389,45 @@ def test_any_length_fft2_through_chirp_z(H, W, monkeypatch):
         ref = (torch.fft.ifft2 if inverse else torch.fft.fft2)(x, norm="ortho" if ortho else "backward")
         got = BL.BluesteinFft2(H, W, inverse, ortho, torch.device("cpu"))(x)
         assert rel_l2(got, ref) < 3e-6, (inverse, ortho)
+
+
+@pytest.mark.parametrize("H,W,scale,with_doe", [(48, 40, None, True),        # runtime-planned engine (96 x 80)
+                                                (128, 256, None, True),      # static kernels, pruned stages (256 x 512)
+                                                (128, 256, None, False),     # aperture + lens only (no DOE): adjoint = conj multiply
+                                                (200, 200, None, True)])     # 400 x 400 mixed radix
+def test_pointwise_elements_fused_into_the_row_kernels(H, W, scale, with_doe):
+    """Aperture mask + thin-lens kernel in front of the (DOE +) propagation, fused into the row-FFT prologue
+    (forward) and the row-iFFT epilogue (adjoint): replayed kernel bodies vs autograd through the oracle."""
+    B, C = 2, 2
+    lams = [1e-3, 1.03e-3]
+    dxy, z, eps, tand = 0.5e-3, 0.1, 2.66, 0.003
+    torch.manual_seed(0)
+    x = torch.randn(B, C, H, W, dtype=torch.complex64)
+    g = torch.randn(B, C, H, W, dtype=torch.complex64)
+    h = torch.rand(H, W) * 1e-3
+    mask = (torch.rand(H, W) > 0.3).float()
+    mul = torch.exp(1j * torch.randn(C, H, W)).to(torch.complex64).contiguous()
+    base, _ = _setup(B, C, H, W, scale, lams, dxy, z, mode=1)
+    coef = AH.doe_coefficients(lams, eps, tand)
+    y = torch.zeros_like(x)
+    fwd = dict(base, x=x, y=y, elem_mode=1, elem_mask=mask, elem_mul=mul)
+    if with_doe:
+        fwd.update(doe_mode=1, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef)
+    _run(x, fwd)
+    xr, hr = x.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    u = xr * mask[None, None] * mul[None]
+    if with_doe:
+        u = DO.modulate(u, hr, lams, eps, tand)
+    yo = AO.asm_forward(u, lams, dxy, z, padding_scale=scale)
+    assert rel_l2(y, yo.detach()) < TOL_TABLE
+    gx, gh = torch.zeros_like(x), torch.full((H, W), 7.0)
+    adj = dict(base, x=g, y=gx, tf_conj=1, elem_mode=2, elem_mask=mask, elem_mul=mul)
+    if with_doe:
+        adj.update(doe_mode=2, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef, xsaved=x, gh=gh)
+        gxo, gho = torch.autograd.grad(yo, (xr, hr), g)
+    else:
+        (gxo,) = torch.autograd.grad(yo, xr, g)
+    _run(g, adj)
+    assert rel_l2(gx, gxo) < TOL_TABLE
+    if with_doe:
+        assert rel_l2(gh, gho) < TOL_TABLE

@@ -831,6 +831,57 @@ def test_lens_and_apertures_match_reference(dev):
                                                                spacing=g["spacing"].float(), device=dev))
 
 
+def test_lens_and_aperture_are_fused_into_the_next_propagation(dev):
+    """aperture -> lens -> DOE -> ASM runs as ONE fused pipeline (elements multiplied on load in the row-FFT
+    kernel, their conjugates in the adjoint's epilogue): no stand-alone pointwise launch, same field / gradients as the
+    oracle chain; and aperture -> ASM without a DOE."""
+    from oracle import asm_oracle as AO, doe_oracle as DO, element_oracle as EO
+    from quantizationawarethzdoe_b200 import (ASM_prop, ApertureElement, ElectricField, STEQuantizedDOELayer, Thin_LensElement,
+                                              _native as N)
+    n, C, lams, dxy, z = 256, 2, [1 * mm, 1.04 * mm], 0.5 * mm, 0.1
+    torch.manual_seed(0)
+    x = torch.randn(2, C, n, n, dtype=torch.complex64)
+    g = torch.randn(2, C, n, n, dtype=torch.complex64)
+    torch.manual_seed(1)
+    doe = STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=dxy, doe_level=4, height_constraint_max=1 * mm, tolerance=None,
+                                    material=[2.66, 0.003]), {}, device=dev)
+    ap, lens = ApertureElement("circ", 0.05, device=dev), Thin_LensElement(focal_length=0.2, device=dev)
+    asm = ASM_prop(z_distance=z, device=dev, kernel_mode="cached")
+    asm.check_Zc = False
+    lib = N.lib()
+    xd = x.to(dev).requires_grad_(True)
+    f0 = ElectricField(xd, wavelengths=lams, spacing=dxy, device=dev)
+    asm(doe(lens(ap(f0))))                                 # warm-up: builds masks, kernels, plans
+    l4 = lib.thz_launch_count_class(4)
+    u = doe(lens(ap(f0)))
+    assert u._data is None and u._deferred.mask is not None and u._deferred.mul is not None
+    y = asm(u).data
+    gx, gw = torch.autograd.grad(y, (xd, doe.weight_height_map), g.to(dev))
+    torch.cuda.synchronize()
+    assert lib.thz_launch_count_class(4) == l4, "a stand-alone pointwise kernel ran: the elements were not fused"
+    mask = EO.circ_mask(n, n, torch.tensor([dxy, dxy]), 0.05).float()
+    ker = EO.lens_kernel(n, n, torch.tensor([dxy, dxy]), torch.tensor(lams), 0.2)
+    xo = x.clone().requires_grad_(True)
+    wo = doe.weight_height_map.detach().cpu().clone().requires_grad_(True)
+    h = DO.ste_quantize(DO.sigmoid_height(wo[0, 0], 1 * mm), DO.linear_lut(1 * mm, 4))
+    yo = AO.asm_forward(DO.modulate(xo * mask.reshape(1, 1, n, n) * ker.reshape(1, C, n, n), h, lams, 2.66, 0.003), lams, dxy, z)
+    gxo, gwo = torch.autograd.grad(yo, (xo, wo), g)
+    e = [rel_l2(y.detach().cpu(), yo.detach()), rel_l2(gx.cpu(), gxo), rel_l2(gw.cpu(), gwo)]
+    record("fused_elements", y=e[0], gx=e[1], gw=e[2])
+    assert max(e) < TOL
+    # aperture only, then propagation (the DONN's encode_object): fused too; materialised path gives the same numbers
+    xd2 = x.to(dev).requires_grad_(True)
+    y2 = asm(ap(ElectricField(xd2, wavelengths=lams, spacing=dxy, device=dev))).data
+    (gx2,) = torch.autograd.grad(y2, xd2, g.to(dev))
+    xo2 = x.clone().requires_grad_(True)
+    yo2 = AO.asm_forward(xo2 * mask.reshape(1, 1, n, n), lams, dxy, z)
+    (gxo2,) = torch.autograd.grad(yo2, xo2, g)
+    assert rel_l2(y2.detach().cpu(), yo2.detach()) < TOL and rel_l2(gx2.cpu(), gxo2) < TOL
+    assert lib.thz_launch_count_class(4) == l4
+    mat = ap(ElectricField(x.to(dev), wavelengths=lams, spacing=dxy, device=dev)).data       # someone reads .data: stand-alone kernel
+    assert lib.thz_launch_count_class(4) == l4 + 1 and rel_l2(mat.cpu(), x * mask.reshape(1, 1, n, n)) == 0.0
+
+
 def test_notebook_setup_end_to_end(dev):
     """The whole set-up of experiment_four_focal_spots.ipynb (cells 2-8, STE layer) from this package alone:
     Gaussian beam -> ASM 127 mm (padding_scale 2) -> thin lens -> rect aperture -> 4-level STE DOE -> ASM 200 mm ->
