@@ -38,7 +38,7 @@ __device__ __forceinline__ void inv_cols(cpx* s, int tid, int nt, const cpx* tw)
 }
 
 // ------------------------------------------------------------------------------- kernels
-template <int N>
+template <int N, bool ELEM>
 __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k1(const __grid_constant__ RowFwdArgs a) {
     constexpr int LINES = p2_row_lines(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     p2_tw_fill<N>(tws, a.tw, tid, nt);                                  // visible after the first barrier below
     if constexpr (!p2_row_pipelined(N)) {     // no room for staging: plain load -> transform -> store per group
         for (; grp < ngroups; grp += gridDim.x) {
-            p2k1_first<N>(a, s, grp, tid, nt);
+            p2k1_first<N, ELEM>(a, s, grp, tid, nt);
             __syncthreads();
             fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, tws);
             p2k1_store<N>(a, s, grp, tid, nt);
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     for (; grp < ngroups; grp += gridDim.x) {
         thz_cp_async_wait_all();
         __syncthreads();                      // staging complete; previous group's store has drained the line buffer
-        p2k1_first_staged<N>(a, s, xs, hs, grp, tid, nt);
+        p2k1_first_staged<N, ELEM>(a, s, xs, hs, grp, tid, nt);
         __syncthreads();                      // staging consumed
         if (grp + (int)gridDim.x < ngroups) p2k1_prefetch<N>(a, xs, hs, grp + gridDim.x, tid, nt);
         thz_cp_async_commit();
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     p2k2f_last<N, COLS, NT>(a, s, tws, bx, by, tid);
 }
 
-template <int N>
+template <int N, bool ELEM>
 __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k3(const __grid_constant__ RowInvArgs a) {
     constexpr int NACC = p2k3_acc<N>(), LINES = p2_row_lines(N), BUF = LINES * p2_pitch(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
             p2k3_load<N>(a, s, bx, f, tid, nt);
             __syncthreads();
             inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, tid, nt, tws);
-            p2k3_last<N, NACC>(a, s, tws, bx, f, tid, nt, acc);
+            p2k3_last<N, NACC, ELEM>(a, s, tws, bx, f, tid, nt, acc);
             __syncthreads();
         }
         p2k3_flush<N, NACC>(a, bx, tid, nt, acc);
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
         if (f + 1 < f_hi) p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, tid, nt, 1, 2);
         thz_cp_async_commit();
         inv_rows<N, p2_stages(N) - 2, 1, LINES>(sc, tid, nt, tws);
-        p2k3_last<N, NACC>(a, sc, tws, bx, f, tid, nt, acc);
+        p2k3_last<N, NACC, ELEM>(a, sc, tws, bx, f, tid, nt, acc);
     }
     p2k3_flush<N, NACC>(a, bx, tid, nt, acc);
 }
@@ -185,7 +185,12 @@ int thz_p2_launch_k1(const RowFwdArgs& a, int grid, int threads, size_t smem, cu
     // persistent CTAs: a few per SM, each walking line groups bx, bx + grid, ... (software pipeline inside)
     const int resident = thz_sm_count() * (a.Wp >= 8192 ? 1 : 3);
     if (grid > resident) grid = resident;
-#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k1<NN>, "thz_p2_k1", THZ_KC_ROW_FWD, dim3(grid), threads, smem, stream, a);
+    if (a.elem.mask || a.elem.mul) {       // pointwise elements in front: the instantiation that multiplies on load
+#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k1<NN, true>, "thz_p2_k1", THZ_KC_ROW_FWD, dim3(grid), threads, smem, stream, a);
+        THZ_P2_SWITCH(thz_p2_k1, a.Wp, THZ_KC_ROW_FWD, grid, threads, smem, stream, a)
+#undef THZ_P2_X
+    }
+#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k1<NN, false>, "thz_p2_k1", THZ_KC_ROW_FWD, dim3(grid), threads, smem, stream, a);
     THZ_P2_SWITCH(thz_p2_k1, a.Wp, THZ_KC_ROW_FWD, grid, threads, smem, stream, a)
 #undef THZ_P2_X
 }
@@ -211,7 +216,12 @@ int thz_p2_launch_k2(const ColArgs& a, int gridx, int gridy, int threads, size_t
 #undef THZ_P2_X
 }
 int thz_p2_launch_k3(const RowInvArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream) {
-#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k3<NN>, "thz_p2_k3", THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a);
+    if (a.elem.mask || a.elem.mul) {       // adjoint of pointwise elements: conjugate multiply in the epilogue
+#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k3<NN, true>, "thz_p2_k3", THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a);
+        THZ_P2_SWITCH(thz_p2_k3, a.Wp, THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a)
+#undef THZ_P2_X
+    }
+#define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k3<NN, false>, "thz_p2_k3", THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a);
     THZ_P2_SWITCH(thz_p2_k3, a.Wp, THZ_KC_ROW_INV, dim3(gridx, gridy), threads, smem, stream, a)
 #undef THZ_P2_X
 }

@@ -39,6 +39,7 @@ THZ_HD constexpr int p2_pitch(int N) { return N + (N >> 4); }
 THZ_HD constexpr bool p2_row_pipelined(int N) { return N <= 8192; }
 
 // =============================================================================== K1<N>
+template <bool ELEM>    // ELEM: pointwise elements in front (separate kernel instantiation: the common case pays nothing)
 struct K1Loader {
     const cpx* xr;      // row of x (NULL: line beyond the end of the batch)
     const float* hr;    // row of the height map (NULL: no DOE)
@@ -48,8 +49,10 @@ struct K1Loader {
     float base;
     int in_c0, inW, conj_in;
     THZ_HD cpx elem(cpx v, int c) const {
-        if (mr) v = cscale(v, thz_ldg(mr + c));
-        if (kr) v = cmul(v, thz_ldg(kr + c));
+        if constexpr (ELEM) {
+            if (mr) v = cscale(v, thz_ldg(mr + c));
+            if (kr) v = cmul(v, thz_ldg(kr + c));
+        }
         return v;
     }
     THZ_HD cpx operator()(int pos) const {
@@ -72,19 +75,22 @@ struct K1Loader {
     }
 };
 // rows of the pointwise elements for line gl of a row kernel's chunk (field f = gl / inH, row r)
-THZ_HD void p2k1_elem_rows(const RowFwdArgs& a, K1Loader& ld, int f, int r) {
-    ld.mr = a.elem.mask ? a.elem.mask + (size_t)r * a.inW : nullptr;
-    ld.kr = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.inH + r) * a.inW : nullptr;
+template <bool ELEM>
+THZ_HD void p2k1_elem_rows(const RowFwdArgs& a, K1Loader<ELEM>& ld, int f, int r) {
+    if constexpr (ELEM) {
+        ld.mr = a.elem.mask ? a.elem.mask + (size_t)r * a.inW : nullptr;
+        ld.kr = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.inH + r) * a.inW : nullptr;
+    }
 }
 
-template <int N>
+template <int N, bool ELEM = false>
 THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N);
     const int total_lines = a.nbc * a.inH;
     for (int w = tid; w < LINES * NB; w += nt) {
         const int line = w / NB, j = w % NB;
         const int gl = bx * LINES + line;
-        K1Loader ld;
+        K1Loader<ELEM> ld;
         ld.xr = nullptr;
         ld.hr = nullptr;
         ld.mr = nullptr;
@@ -137,14 +143,14 @@ THZ_HD void p2k1_prefetch(const RowFwdArgs& a, cpx* xs, float* hs, int grp, int 
     }
 }
 
-template <int N>
+template <int N, bool ELEM = false>
 THZ_HD void p2k1_first_staged(const RowFwdArgs& a, cpx* s, const cpx* xs, const float* hs, int grp, int tid, int nt) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N);
     const int total_lines = a.nbc * a.inH;
     for (int w = tid; w < LINES * NB; w += nt) {
         const int line = w / NB, j = w % NB;
         const int gl = grp * LINES + line;
-        K1Loader ld;
+        K1Loader<ELEM> ld;
         ld.xr = nullptr;
         ld.hr = nullptr;
         ld.mr = nullptr;
@@ -494,7 +500,7 @@ THZ_HD constexpr int p2k3_acc() {
     return ((p2_row_lines(N) * P2Stage<N, 0>::NB + p2_row_threads(N) - 1) / p2_row_threads(N)) * P2Stage<N, 0>::R;
 }
 
-template <int PF_>
+template <int PF_, bool ELEM = false>
 struct K3Storer {
     static constexpr int PF = PF_;   // epilogue loads (saved field, height map) run this many outputs ahead
     cpx* yrow;            // output row (forward output or grad wrt field; may be NULL in DOE mode)
@@ -530,10 +536,12 @@ struct K3Storer {
         emit(c, t, t, v);
     }
     THZ_HD cpx elem(cpx v, int c, bool conj) const {     // pointwise elements in front of the DOE (thz_elem_apply per row)
-        if (mrow) v = cscale(v, thz_ldg(mrow + c));
-        if (krow) {
-            const cpx m = thz_ldg(krow + c);
-            v = conj ? cmulc(v, m) : cmul(v, m);
+        if constexpr (ELEM) {
+            if (mrow) v = cscale(v, thz_ldg(mrow + c));
+            if (krow) {
+                const cpx m = thz_ldg(krow + c);
+                v = conj ? cmulc(v, m) : cmul(v, m);
+            }
         }
         return v;
     }
@@ -575,10 +583,10 @@ THZ_HD void p2k3_prefetch_epilogue(const RowInvArgs& a, int bx, int f, int tid, 
 }
 
 // inverse stage 0 + crop + scale + epilogue for field f; acc has p2k3_acc<N>() entries
-template <int N, int NACC>
+template <int N, int NACC, bool ELEM = false>
 THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, int f, int tid, int nt, float (&acc)[NACC]) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N), R = P2Stage<N, 0>::R;
-    K3Storer<(R <= 16 ? 4 : 1)> st;     // radix-25 butterflies have no registers to spare for a deeper ring
+    K3Storer<(R <= 16 ? 4 : 1), ELEM> st;     // radix-25 butterflies have no registers to spare for a deeper ring
     st.cf = cmake4(0.f);
     st.gamma = cmake(0.f, 0.f);
     if (a.doe.hmap) {
@@ -601,8 +609,10 @@ THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, 
         st.yrow = a.y ? a.y + o : nullptr;
         st.xrow = a.xsaved ? a.xsaved + o : nullptr;
         st.hrow = a.doe.hmap ? a.doe.hmap + (size_t)r * a.outW : nullptr;
-        st.mrow = a.elem.mask ? a.elem.mask + (size_t)r * a.outW : nullptr;
-        st.krow = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.outH + r) * a.outW : nullptr;
+        if constexpr (ELEM) {
+            st.mrow = a.elem.mask ? a.elem.mask + (size_t)r * a.outW : nullptr;
+            st.krow = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.outH + r) * a.outW : nullptr;
+        }
         st.acc = &acc[k * R];
         if (a.half_out) p2_last_inverse_stage_to<N, 1, true>(s + line * PITCH, j, tw, st);
         else p2_last_inverse_stage_to<N, 1>(s + line * PITCH, j, tw, st);
