@@ -46,7 +46,12 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     cpx* tws = s + LINES * p2_pitch(N);                                  // shared-memory copy of the stage twiddles
     cpx* xs = tws + p2_tw_count(N);                                      // staged raw rows
     float* hs = reinterpret_cast<float*>(xs + (size_t)LINES * a.inW);      // staged height-map rows
-    const int tid = threadIdx.x, nt = blockDim.x;
+    // the launch always uses p2_row_threads(N) threads (thz_asm_apply_p2): a compile-time block size lets every work loop
+    // of the phase functions resolve its trip count
+    // (measured: helps the radix-16 lengths, hurts the radix-25 ones -- more unrolling, more register pressure -- so those
+    // keep the run-time value)
+    const int nt = p2_radix(N, 0) == 16 ? p2_row_threads(N) : (int)blockDim.x;
+    const int tid = threadIdx.x;
     const int ngroups = (a.nbc * a.inH + LINES - 1) / LINES;
     int grp = blockIdx.x;
     p2_tw_fill<N>(tws, a.tw, tid, nt);                                  // visible after the first barrier below
@@ -115,7 +120,8 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);      // two line buffers: [0, BUF) and [BUF, 2 BUF)
     cpx* tws = s + (p2_row_pipelined(N) ? 2 : 1) * BUF;                  // shared-memory copy of the stage twiddles
-    const int tid = threadIdx.x, nt = blockDim.x, bx = blockIdx.x;
+    constexpr int nt = p2_row_threads(N);
+    const int tid = threadIdx.x, bx = blockIdx.x;
     p2_tw_fill<N>(tws, a.tw, tid, nt);                                  // visible after the first barrier below
     float acc[NACC];
 #pragma unroll
