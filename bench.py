@@ -246,6 +246,23 @@ def secondary_single(dev, lib, sm_mhz, hbm_peak):
         "kernel": "tcgen05 3xTF32 (thz_k_toeplitz_gemm_tc)" if tc_l and not simt_l else "CUDA-core fp32 (thz_k_toeplitz_gemm)",
         "tcgen05_launches": int(tc_l), "cuda_core_gemm_launches": int(simt_l)}
     del xc, fc, prop
+    # ---- C5 on ONE GPU: the reference point of the slab-decomposed runs at N > 1 (same grid, forward + adjoint)
+    n5 = int(os.environ.get("THZ_BENCH_SLAB_N", "8192"))
+    x5 = torch.randn(1, 1, n5, n5, dtype=torch.complex64, device=dev).requires_grad_(True)
+    asm5 = ASM_prop(z_distance=Z, device=dev, kernel_mode="inregister")
+    asm5.check_Zc = False
+    f5 = ElectricField(x5, wavelengths=lam1, spacing=sp, device=dev)
+
+    def c5_step():
+        y = asm5(f5).data
+        torch.autograd.grad(y, x5, y.detach())
+
+    ms = _event_ms(c5_step, 5, 2, dev)
+    smp = (2 * n5) ** 2
+    out["c5_single_gpu_%d_padded" % (2 * n5)] = {"fwd_bwd_ms": ms, "Msamples_per_s": smp / ms / 1e3,
+                                                 "hbm_frac": 40.0 * smp / (ms * 1e-3) / 1e9 / hbm_peak}
+    del x5, f5, asm5
+    torch.cuda.empty_cache()
     # ---- C4
     n, B, layers = 200, 1024, 3
     does = [STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=SPACING, doe_level=4, height_constraint_max=HMAX, tolerance=None,

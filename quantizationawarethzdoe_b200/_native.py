@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libthzdoe.so")
+LIB_PATH = os.environ.get("THZ_LIB") or os.path.join(_HERE, "csrc", "libthzdoe.so")      # THZ_LIB: A/B builds (tools/build_variant.sh)
 
 THZ_OK = 0
 THZ_E_UNSUPPORTED = -3

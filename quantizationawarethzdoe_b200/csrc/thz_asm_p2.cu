@@ -65,15 +65,54 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
         }
         return;
     }
-    if (grp < ngroups) p2k1_prefetch<N>(a, xs, hs, grp, tid, nt);
-    thz_cp_async_commit();
+    // Staging of the next group's raw rows.  When the rows are 16-byte granular (even width, width % 4 == 0 with a height map,
+    // aligned bases) ONE thread hands them to the TMA copy engine -- a single cp.async.bulk for the x rows of the group (they
+    // are contiguous) and one per height-map row -- and everybody waits on an mbarrier phase; otherwise every thread issues
+    // 16 / 8 / 4-byte cp.async copies as before.
+    __shared__ unsigned long long bar;
+    const bool bulk = (a.inW % 2 == 0) && (((size_t)a.x & 15) == 0) &&
+                      (!a.doe.hmap || (a.inW % 4 == 0 && ((size_t)a.doe.hmap & 15) == 0 && (a.doe.hstride % 4) == 0));
+    const int total_lines = a.nbc * a.inH;
+    auto stage_bulk = [&](int g) {                     // called by thread 0 only
+        const int gl0 = g * LINES;
+        const int nvalid = min(LINES, total_lines - gl0);
+        const unsigned xbytes = (unsigned)nvalid * a.inW * sizeof(cpx);
+        const unsigned hbytes = a.doe.hmap ? (unsigned)nvalid * a.inW * sizeof(float) : 0u;
+        thz_mbar_expect_tx(&bar, xbytes + hbytes);
+        thz_bulk_g2s(xs, a.x + (size_t)gl0 * a.inW, xbytes, &bar);
+        if (a.doe.hmap)
+            for (int line = 0; line < nvalid; ++line) {
+                const int gl = gl0 + line;
+                thz_bulk_g2s(hs + (size_t)line * a.inW, thz_doe_map(a.doe, a.c0, a.C, gl / a.inH) + (size_t)(gl % a.inH) * a.inW,
+                             a.inW * (unsigned)sizeof(float), &bar);
+            }
+    };
+    unsigned parity = 0;
+    if (bulk) {
+        if (tid == 0) thz_mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0 && grp < ngroups) stage_bulk(grp);
+    } else {
+        if (grp < ngroups) p2k1_prefetch<N>(a, xs, hs, grp, tid, nt);
+        thz_cp_async_commit();
+    }
     for (; grp < ngroups; grp += gridDim.x) {
-        thz_cp_async_wait_all();
+        if (bulk) {
+            thz_mbar_wait(&bar, parity);
+            parity ^= 1u;
+        } else {
+            thz_cp_async_wait_all();
+        }
         __syncthreads();                      // staging complete; previous group's store has drained the line buffer
         p2k1_first_staged<N, ELEM>(a, s, xs, hs, grp, tid, nt);
         __syncthreads();                      // staging consumed
-        if (grp + (int)gridDim.x < ngroups) p2k1_prefetch<N>(a, xs, hs, grp + gridDim.x, tid, nt);
-        thz_cp_async_commit();
+        const int next = grp + (int)gridDim.x;
+        if (bulk) {
+            if (tid == 0 && next < ngroups) stage_bulk(next);
+        } else {
+            if (next < ngroups) p2k1_prefetch<N>(a, xs, hs, next, tid, nt);
+            thz_cp_async_commit();
+        }
         fwd_rows<N, 1, p2_stages(N), LINES>(s, tid, nt, tws);
         p2k1_store<N>(a, s, grp, tid, nt);
     }

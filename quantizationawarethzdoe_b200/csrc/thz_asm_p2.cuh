@@ -354,7 +354,7 @@ THZ_HD void p2k2f_first(const ColArgs& a, cpx* s, int bx, int by, int tid) {
         const cpx* p0 = tile + (COLS > 4 ? (((size_t)(l >> 2) * a.rowsT) << 2) + (l & 3) : (size_t)l) + (size_t)j * 4;
         cpx in[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) in[t] = p0[t * M * 4];
+        for (int t = 0; t < 8; ++t) in[t] = thz_ld_stream(p0 + t * M * 4);
         cpx v[16];
         dft16_half_in<false>(in, v);
         p2_apply_twiddles<16>(v, thz_ldg(a.tw + j));
@@ -385,7 +385,7 @@ THZ_HD void p2k2f_middle(const ColArgs& a, cpx* s, int bx, int by, int tid) {
         if constexpr (TFM == 0) {
             const float4* rvp = reinterpret_cast<const float4*>(a.tf.rowvec + (size_t)c_chan * N) + u;      // chunked layout
 #pragma unroll
-            for (int q = 0; q < R / 2; ++q) h4[q] = thz_ldg(rvp + (size_t)q * NB);
+            for (int q = 0; q < R / 2; ++q) h4[q] = thz_ldg_keep(rvp + (size_t)q * NB);
             cv = thz_ldg(a.tf.colvec + (size_t)c_chan * a.Wp + col);
             sc = thz_ldg(a.tf.scal + c_chan);
         } else if constexpr (TFM == 1) {
@@ -442,7 +442,7 @@ THZ_HD void p2k2f_last(const ColArgs& a, const cpx* s, const cpx* tws, int bx, i
         dft16_half_out<true>(v, o);
         cpx* q = tile + (size_t)j * a.Wp + l;             // output 4 + t is canvas row j + (4 + t) M = live row j + t M
 #pragma unroll
-        for (int t = 0; t < 8; ++t, q += step) *q = o[t];
+        for (int t = 0; t < 8; ++t, q += step) thz_st_stream(q, o[t]);
     }
 }
 
