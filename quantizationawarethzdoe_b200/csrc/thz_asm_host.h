@@ -93,6 +93,12 @@ static inline bool p2_k2_fast_ok_rt(int n) {
 #undef THZ_SP_FASTCMP
     return false;
 }
+static inline int thz_p2_min_blocks_rt(int n) {
+#define THZ_SP_MB(NN) if (n == NN) return p2_min_blocks(NN);
+    THZ_SP_SIZES(THZ_SP_MB)
+#undef THZ_SP_MB
+    return 3;
+}
 static inline int thz_p2_row_lines_rt(int n) { return p2_row_lines(n); }
 static inline int thz_p2_tw_count_rt(int n) { return p2_tw_count(n); }
 static inline int thz_p2_row_threads_rt(int n) { return p2_row_threads(n); }
@@ -123,7 +129,7 @@ static inline void thz_asm_apply_p2(const thz_asm_desc* d, int nbc, int sm_count
         // that are resident at once (3 per SM, 1 for the 8192+ lines): pick the split that minimises it.  The old rule
         // (double until the grid reaches 4 x SMs) gave 640 CTAs on 444 slots for the 400-point lines of the DONN config --
         // 1.44 waves, the second one less than half full (profiles/r02_donn_ncu_summary.txt).
-        const long resident = (long)sm_count * (d->Wp >= 8192 ? 1 : 3);
+        const long resident = (long)sm_count * thz_p2_min_blocks_rt(d->Wp);
         int gy = 1;
         if (L->k3_gridx < resident && nbc > 1) {
             long best = -1;

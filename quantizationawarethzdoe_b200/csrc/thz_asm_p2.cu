@@ -39,7 +39,7 @@ __device__ __forceinline__ void inv_cols(cpx* s, int tid, int nt, const cpx* tw)
 
 // ------------------------------------------------------------------------------- kernels
 template <int N, bool ELEM>
-__global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k1(const __grid_constant__ RowFwdArgs a) {
+__global__ void __launch_bounds__(p2_row_threads(N), p2_min_blocks(N)) thz_p2_k1(const __grid_constant__ RowFwdArgs a) {
     constexpr int LINES = p2_row_lines(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
 }
 
 template <int N>
-__global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k2(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(p2_col_threads(N), p2_min_blocks(N)) thz_p2_k2(const __grid_constant__ ColArgs a) {
     constexpr int COLS = p2_col_cols(N), NS = p2_stages(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
 
 // fast path of the column kernel (ColArgs.fast, see thz_asm_p2.cuh): same phases, everything static
 template <int N, int TFM>
-__global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k2f(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(p2_col_threads(N), p2_min_blocks(N)) thz_p2_k2f(const __grid_constant__ ColArgs a) {
     constexpr int COLS = p2_col_cols(N), NS = p2_stages(N), NT = p2_col_threads(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(p2_col_threads(N), N >= 8192 ? 1 : 3) thz_p2_k
 }
 
 template <int N, bool ELEM>
-__global__ void __launch_bounds__(p2_row_threads(N), N >= 8192 ? 1 : 3) thz_p2_k3(const __grid_constant__ RowInvArgs a) {
+__global__ void __launch_bounds__(p2_row_threads(N), p2_min_blocks(N)) thz_p2_k3(const __grid_constant__ RowInvArgs a) {
     constexpr int NACC = p2k3_acc<N>(), LINES = p2_row_lines(N), BUF = LINES * p2_pitch(N);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* s = reinterpret_cast<cpx*>(smem_raw);      // two line buffers: [0, BUF) and [BUF, 2 BUF)
@@ -228,7 +228,7 @@ static int launch_p2(K kernel, const char* name, int cls, dim3 grid, int block, 
 
 int thz_p2_launch_k1(const RowFwdArgs& a, int grid, int threads, size_t smem, cudaStream_t stream) {
     // persistent CTAs: a few per SM, each walking line groups bx, bx + grid, ... (software pipeline inside)
-    const int resident = thz_sm_count() * (a.Wp >= 8192 ? 1 : 3);
+    const int resident = thz_sm_count() * thz_p2_min_blocks_rt(a.Wp);
     if (grid > resident) grid = resident;
     if (a.elem.mask || a.elem.mul) {       // pointwise elements in front: the instantiation that multiplies on load
 #define THZ_P2_X(NN) case NN: return launch_p2(thz_p2_k1<NN, true>, "thz_p2_k1", THZ_KC_ROW_FWD, dim3(grid), threads, smem, stream, a);

@@ -30,6 +30,17 @@ THZ_HD constexpr bool thz_sp_instantiated(int n) {
     return false;
 }
 
+// CTAs per SM the static kernels are compiled for (register cap = 65536 / (threads x this)): 3 (80 registers) for the
+// radix-16 lengths; the lengths with a radix-25 stage hold 25 complex values per butterfly and spill at 80 registers
+#ifndef THZ_R25_BLOCKS
+#define THZ_R25_BLOCKS 3
+#endif
+THZ_HD constexpr bool p2_has_radix25(int N) {
+    for (int s = 0; s < p2_stages(N); ++s)
+        if (p2_radix(N, s) == 25) return true;
+    return false;
+}
+THZ_HD constexpr int p2_min_blocks(int N) { return N >= 8192 ? 1 : (p2_has_radix25(N) ? THZ_R25_BLOCKS : 3); }
 THZ_HD constexpr int p2_row_lines(int N) { return N >= 4096 ? 1 : 4096 / N; }        // lines per CTA, row kernels
 THZ_HD constexpr int p2_row_threads(int N) { return N >= 8192 ? 512 : 256; }
 THZ_HD constexpr int p2_col_cols(int N) { return N > 8192 ? 1 : (N > 2048 ? 2 : (N > 1024 ? 4 : (N > 512 ? 8 : 16))); }
