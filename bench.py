@@ -279,10 +279,8 @@ def secondary_single(dev, lib, sm_mhz, hbm_peak):
         y = f.data
         torch.autograd.grad(y, [d.weight_height_map for d in does], y.detach())
 
-    sm0 = lib.thz_launch_count_class(9)
     ms = _event_ms(donn_step, 10, 3, dev)
     out["c4_donn_3layer_200_batch1024"] = _donn_report(ms, B, n, layers, hbm_peak, _fp32_peak(dev, sm_mhz))
-    out["c4_donn_3layer_200_batch1024"]["small_grid_kernel_launches"] = int(lib.thz_launch_count_class(9) - sm0)
     return out
 
 
@@ -547,7 +545,7 @@ def run_ours(args, rank, local_rank, world):
         lib.thz_profile_read(10, ms_sum, cnt)
         lib.thz_profile_enable(0)
         names = ["row_fft_fwd", "column_fft_H_ifft", "row_ifft_epilogue", "fft2_col", "doe_modulate", "quantizer", "czt_cuda_core",
-                 "train", "czt_tcgen05", "small_grid"]
+                 "train", "czt_tcgen05", "reserved"]
         fields_per_step = B * C
         # algorithmic bytes per field per launch class (fwd + bwd launches pooled), complex64, 2x pad
         alg = {"row_fft_fwd": 8 * (n * n + n * Np), "column_fft_H_ifft": 16 * n * Np, "row_ifft_epilogue": 8 * (n * Np + 1.5 * n * n)}

@@ -15,7 +15,7 @@ int thz_sm_count(void);
 // THZ_KC_CZT = the CUDA-core Toeplitz GEMM (+ the prologue multiply), THZ_KC_CZT_TC = the tcgen05 kernel: separate classes so
 // that a caller can tell which implementation produced a result (thz_launch_count_class).
 enum { THZ_KC_ROW_FWD = 0, THZ_KC_COL = 1, THZ_KC_ROW_INV = 2, THZ_KC_FFT2_COL = 3, THZ_KC_DOE = 4, THZ_KC_QUANT = 5,
-       THZ_KC_CZT = 6, THZ_KC_TRAIN = 7, THZ_KC_CZT_TC = 8, THZ_KC_SMALL = 9, THZ_KC_COUNT = 10 };
+       THZ_KC_CZT = 6, THZ_KC_TRAIN = 7, THZ_KC_CZT_TC = 8, THZ_KC_RESERVED = 9, THZ_KC_COUNT = 10 };
 // Called around every kernel launch: counts it and, when profiling is enabled, brackets it with CUDA events
 // recorded on the launching stream.
 void thz_launch_begin(cudaStream_t stream, int kernel_class);

@@ -55,7 +55,7 @@ if a.events:
     ms, cnt = (ctypes.c_float * 10)(), (ctypes.c_int32 * 10)()
     lib.thz_profile_read(10, ms, cnt)
     lib.thz_profile_enable(0)
-    names = ["row_fft_fwd", "column_pass", "row_ifft", "fft2_col", "doe", "quant", "czt", "train", "czt_tc", "small"]
+    names = ["row_fft_fwd", "column_pass", "row_ifft", "fft2_col", "doe", "quant", "czt", "train", "czt_tc", "reserved"]
     print("B=%d step %.3f ms (with event overhead)" % (B, e0.elapsed_time(e1) / reps),
           {nm: (round(ms[i] / reps, 4), cnt[i] // reps) for i, nm in enumerate(names) if cnt[i]}, "modes", [p.resolved_kernel_mode for p in asms])
 print("ok", float(g[0].abs().mean()))
