@@ -29,3 +29,33 @@ def test_slab_and_data_parallel_equal_single_gpu(transport):
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert ("[%s transport]" % transport) in r.stdout
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+def test_modules_on_a_non_current_device():
+    """the library used the calling thread's CURRENT device for launches, attributes and the SM count.  Every entry
+    point now makes the device that owns its pointers current for the call: a pipeline built on cuda:1 runs, and matches the
+    same pipeline on cuda:0 bit for bit, while the current device stays 0."""
+    from quantizationawarethzdoe_b200 import ASM_prop, CZT_prop, ElectricField, STEQuantizedDOELayer
+    mm = 1e-3
+    torch.cuda.set_device(0)
+    outs = []
+    for dev in (torch.device("cuda:0"), torch.device("cuda:1")):
+        torch.manual_seed(0)
+        x = torch.randn(1, 2, 256, 256, dtype=torch.complex64)
+        torch.manual_seed(1)
+        doe = STEQuantizedDOELayer(dict(doe_size=[256, 256], doe_dxy=0.5 * mm, doe_level=4, height_constraint_max=1 * mm, tolerance=None,
+                                        material=[2.66, 0.003]), {}, device=dev)
+        asm = ASM_prop(z_distance=0.1, device=dev)
+        asm.check_Zc = False
+        xd = x.to(dev).requires_grad_(True)
+        y = asm(doe(ElectricField(xd, wavelengths=[1 * mm, 1.03 * mm], spacing=0.5 * mm, device=dev))).data
+        gx, gw = torch.autograd.grad(y, (xd, doe.weight_height_map), y.detach())
+        c = CZT_prop(z_distance=0.4, device=dev)(ElectricField(xd.detach(), wavelengths=[1 * mm, 1.03 * mm], spacing=0.5 * mm, device=dev),
+                                                128, 128, 0.2 * mm, 0.2 * mm).data
+        torch.cuda.synchronize(dev)
+        assert y.device == dev and c.device == dev
+        outs.append((y.detach().cpu(), gx.cpu(), gw.cpu(), c.cpu()))
+    assert torch.cuda.current_device() == 0
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
