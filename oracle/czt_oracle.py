@@ -12,7 +12,7 @@ import this module.  Restates (torch CPU, reference dtype rules and op order):
 `czt_forward` is the FFT-based algorithm exactly as the reference runs it; `czt_forward_dense`
 is the algebraically equivalent separable dense form  F0 * (Wy . (x*F) . Wx^T) * s_c  that the
 CUDA GEMM path implements, built from the same reference-order chirp vectors.
-Parity is PINNED by tests/test_oracle_vs_reference.py and tests/golden/czt_*.npz.
+Parity is PINNED by tests/test_oracle_golden.py and tests/golden/czt_*.npz.
 """
 import numpy as np
 import torch

@@ -12,7 +12,7 @@ import this module.  Restates (torch CPU, fp32, reference op order):
   Components/QuantizedDOE.py:1022-1031  NaiveGumbelQuantizedDOELayer.preprocessed_height_map
   Components/quantization.py:12-21,36-161 tau_iter, score_thickness, NearestNeighbor*, SoftmaxBasedQuantization
   utils/Helper_Functions.py:371-398     lut_mid, nearest_idx
-Parity is PINNED by tests/test_oracle_vs_reference.py (reference imported when present) and
+Parity is PINNED by tests/test_oracle_golden.py (reference imported when present) and
 tests/golden/*.npz (reference outputs; generator oracle/make_golden.py), plus the known-answer
 values of Components/test_all.ipynb cells 13-21.
 """
