@@ -161,6 +161,13 @@ typedef struct thz_asm_desc {
  * intermediate of the live rows, [fields][max(inH, outH)][Wp] complex64 -- or two of them when both transform lengths are
  * served by the static kernels and the whole pipeline runs (the row spectra are then kept in 4-column blocks for the
  * column kernel, whose row-major output goes to the second half). */
+/* thz_tf_table_from_angles: builds the tf_mode 1 table on the device from the reference's phase angles evaluated on the HOST
+ * for the unique quarter of the (even) frequency grid: angq float32 [C][Hp/2+1][Wp/2+1] = z * sqrt(klam^2 - Kx^2[|i|] - Ky^2[|j|])
+ * computed with the reference's own library (Props/ASM_Prop.py:257).  rowtau float32 [C][Hp][2] = {Kx^2, tau} and colk2
+ * float32 [C][Wp] in slot order as for tf_mode 0 (the keep mask Ky^2 <= tau is bit-identical to the reference's); rabs int32
+ * [Hp] / cabs int32 [Wp] = |centred frequency index| of every slot.  table complex64 [C][Wp][Hp] (out). */
+int thz_tf_table_from_angles(const void* angq, int32_t C, int32_t Hu, int32_t Wu, const void* rowtau, const void* colk2,
+                             const void* rabs, const void* cabs, int32_t Hp, int32_t Wp, void* table, void* stream);
 uint64_t thz_asm_workspace_bytes(const thz_asm_desc* desc);
 int thz_asm_propagate(const thz_asm_desc* desc, void* stream);
 

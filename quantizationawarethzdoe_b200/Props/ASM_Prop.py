@@ -179,16 +179,22 @@ class ASM_prop(nn.Module):
             chunked = AH.row_vectors_chunked(Hp)
             mode_ = self.kernel_mode
             if mode_ == 'auto':
-                self.inregister_estimate = AH.inregister_deviation_estimate(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel,
-                                                                            self.bandlimit_type)
+                self.inregister_estimate = AH.inregister_estimate_for(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel,
+                                                                      self.bandlimit_type)
                 mode_ = 'inregister' if self.inregister_estimate <= AH.INREGISTER_BUDGET else 'cached'
             dv = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked) if mode_ == 'inregister' else None
             if dv is not None:
                 rowvec, colvec, scal = dv
             self.resolved_kernel_mode = 'inregister' if dv is not None else 'cached'
             if mode_ == 'cached' or dv is None:
-                Hc = AH.tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
-                table, mode = AH.tf_table_slot_order(Hc), 1
+                # the reference's own angles (host, unique quarter) expanded on the device; whole table on the host only if the
+                # mask cannot be folded into thresholds
+                table = AH.tf_table_device(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type, device) \
+                    if device.type == "cuda" else None
+                if table is None:
+                    Hc = AH.tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
+                    table = AH.tf_table_slot_order(Hc)
+                mode = 1
             unpad = bool(self.do_padding and self.do_unpad_after_pad)
             self._plan = Fn.AsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, rowvec, colvec, scal, table, mode,
                                     row_chunked=chunked)

@@ -463,6 +463,44 @@ extern "C" int thz_score_thickness(const void* thickness, const void* lut, int32
     return THZ_OK;
 }
 
+// ------------------------------------------------------------------------------- cached transfer-function table from angles
+// kernel_mode 'cached' streams H' from a table that must carry the REFERENCE's own phase angles z sqrt(klam^2 - Kx^2 - Ky^2)
+// (torch's CPU sqrt is not correctly rounded, see asm_host.inregister_deviation_estimate).  Kx^2 and Ky^2 are even in the
+// frequency index, so the host evaluates the angles with the reference's library on the unique quarter only
+// ([C][Hp/2+1][Wp/2+1], 4x less host work and upload) and this kernel expands it into the column-major slot-order table the
+// column pass reads: table[c][sc][sr] = keep ? exp(i ang[c][|bin(sr)|][|bin(sc)|]) : 0, keep <=> Ky^2[sc] <= tau[sr] (the same
+// bit-exact mask as the in-register mode).
+__global__ void __launch_bounds__(256) thz_k_tf_table(const float* __restrict__ angq, int Hu, int Wu, const float2* __restrict__ rowtau,
+                                                      const float* __restrict__ colk2, const int* __restrict__ rabs,
+                                                      const int* __restrict__ cabs, int Hp, int Wp, cpx* __restrict__ table) {
+    const int c = blockIdx.z, sc = blockIdx.y;
+    const float ky2 = colk2[(size_t)c * Wp + sc];
+    const float* aq = angq + (size_t)c * Hu * Wu + cabs[sc];
+    cpx* out = table + ((size_t)c * Wp + sc) * Hp;
+    for (int sr = blockIdx.x * blockDim.x + threadIdx.x; sr < Hp; sr += gridDim.x * blockDim.x) {
+        const bool keep = ky2 <= rowtau[(size_t)c * Hp + sr].y;
+        float sn = 0.f, cs = 0.f;
+        if (keep) sincosf(aq[(size_t)rabs[sr] * Wu], &sn, &cs);
+        out[sr] = cmake(cs, sn);
+    }
+}
+
+extern "C" int thz_tf_table_from_angles(const void* angq, int32_t C, int32_t Hu, int32_t Wu, const void* rowtau, const void* colk2,
+                                        const void* rabs, const void* cabs, int32_t Hp, int32_t Wp, void* table, void* stream_) {
+    ThzDeviceGuard dev_guard(table);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C < 1 || Hp < 1 || Wp < 1 || Hu != Hp / 2 + 1 || Wu != Wp / 2 + 1) return thz_set_error(THZ_E_SHAPE, "thz_tf_table_from_angles: bad sizes");
+    if (!angq || !rowtau || !colk2 || !rabs || !cabs || !table) return thz_set_error(THZ_E_NULL, "thz_tf_table_from_angles: null pointer");
+    if (Wp > 65535 || C > 65535) return thz_set_error(THZ_E_SHAPE, "thz_tf_table_from_angles: grid too large");
+    dim3 grid((Hp + 255) / 256 > 8 ? 8 : (Hp + 255) / 256, Wp, C);
+    thz_launch_begin(stream, THZ_KC_DOE);
+    thz_k_tf_table<<<grid, 256, 0, stream>>>((const float*)angq, Hu, Wu, (const float2*)rowtau, (const float*)colk2, (const int*)rabs,
+                                             (const int*)cabs, Hp, Wp, (cpx*)table);
+    thz_launch_end(stream, THZ_KC_DOE);
+    THZ_CHECK_LAUNCH("thz_k_tf_table");
+    return THZ_OK;
+}
+
 // ------------------------------------------------------------------------------- pointwise optical elements
 // y[f, p] = x[f, p] * m[(f % C) * per_channel, p]  (m complex, optionally conjugated) or  * mask[p]  (real):
 // thin lens (Components/Thin_Lens.py:66-72) and aperture (Components/Aperture.py:126), forward and adjoint.

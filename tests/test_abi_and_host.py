@@ -208,3 +208,21 @@ def test_chirp_z_host_tables():
     a[:H, :W] = x * np.outer(BL.chirp(H), BL.chirp(W))
     b = np.fft.ifft2(np.fft.fft2(a) * BL.kernel_spectrum(H, W, L1, L2))[:H, :W]
     assert np.allclose(b * np.outer(BL.chirp(H), BL.chirp(W)), np.fft.fft2(x), atol=1e-10)
+
+
+@pytest.mark.parametrize("Hp,Wp,bt,z", [(64, 96, "exact", 0.1), (60, 45, "exact", 0.26), (50, 36, "approx", 0.05), (35, 27, "exact", 0.3)])
+def test_quarter_angles_rebuild_the_reference_table(Hp, Wp, bt, z):
+    """kernel_mode 'cached': the host evaluates the reference's phase angles on the unique quarter of the frequency grid only
+    and the device expands them (thz_tf_table_from_angles).  Restated here with torch on the CPU -- same index maps, same
+    threshold mask -- the expansion must equal the table made from the reference's full-grid kernel bit for bit."""
+    from quantizationawarethzdoe_b200 import asm_host as AH
+    sp, lam, zt = torch.tensor([0.5e-3, 0.7e-3]), torch.tensor([1e-3, 1.06e-3]), torch.tensor(z)
+    fn = None            # the library's own host-side planning helper (no GPU involved)
+    ref = AH.tf_table_slot_order(AH.tf_centred_reference_order(Hp, Wp, sp, lam, zt, True, bt), fn)        # [C, Wp, Hp]
+    rowtau, colk2, _ = AH.tf_device_vectors(*AH.tf_vectors(Hp, Wp, sp, lam, zt, True, bt), fn, chunked=False)
+    angq = AH.tf_angle_quarter(Hp, Wp, sp, lam, zt)
+    ra, ca = AH.abs_bin_of_slots(Hp, fn).long(), AH.abs_bin_of_slots(Wp, fn).long()
+    ang = angq[:, ra][:, :, ca].transpose(1, 2)                         # [C, slot_c, slot_r]
+    keep = colk2[:, :, None] <= rowtau[:, None, :, 1]
+    tab = torch.where(keep, torch.exp(1j * ang), torch.zeros((), dtype=torch.complex64))
+    assert torch.equal(torch.view_as_real(tab), torch.view_as_real(ref))
