@@ -341,7 +341,7 @@ class SlabAsm(torch.nn.Module):
     slab of the propagated field.  Constructor arguments as ASM_prop (Props/ASM_Prop.py:19-27)."""
 
     def __init__(self, z_distance=0.0, do_padding=True, do_unpad_after_pad=True, padding_scale=None, bandlimit_kernel=True,
-                 bandlimit_type="exact", group=None, kernel_mode="inregister", transport="auto"):
+                 bandlimit_type="exact", group=None, kernel_mode="auto", transport="auto"):
         super().__init__()
         if transport not in ("auto", "peer", "nccl"):
             raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
@@ -398,12 +398,21 @@ class SlabAsm(torch.nn.Module):
             rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type)
             table, mode = None, 0
             chunked = AH.row_vectors_chunked(Hp)
-            dv = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked) if self.kernel_mode == "inregister" else None
+            mode_ = self.kernel_mode                 # as ASM_prop: 'auto' generates H in registers only where that keeps parity
+            if mode_ == "auto":
+                est = AH.inregister_estimate_for(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type)
+                mode_ = "inregister" if est <= AH.INREGISTER_BUDGET else "cached"
+            dv = AH.tf_device_vectors(rowvec, colvec, scal, chunked=chunked) if mode_ == "inregister" else None
+            self.resolved_kernel_mode = "inregister" if dv is not None else "cached"
             if dv is not None:
                 rowvec, colvec, scal = dv
             else:
-                Hc = AH.tf_centred_reference_order(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type)
-                table, mode = AH.tf_table_slot_order(Hc), 1
+                table = AH.tf_table_device(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type,
+                                           data.device) if data.device.type == "cuda" else None
+                if table is None:
+                    Hc = AH.tf_centred_reference_order(Hp, Wp, field.spacing, field.wavelengths, self.z, self.bandlimit_kernel, self.bandlimit_type)
+                    table = AH.tf_table_slot_order(Hc)
+                mode = 1
             self._plan = _SlabPlan(G, rank, C, H, W, pad_h, pad_w, Hp, Wp, bool(self.do_padding and self.do_unpad_after_pad),
                                    data.device, rowvec, colvec, scal, table, mode, row_chunked=chunked)
             self._key = key
