@@ -120,9 +120,10 @@ class DOELayer(nn.Module):
             hm = nn.functional.interpolate(hm[None, None, :, :], size=[full_h, input_field.width], mode='nearest')
         self._height_map_ = torch.squeeze(hm, (0, 1)) if hm.ndim == 4 else hm
         # an aperture / lens applied just before (still un-evaluated) rides along: x m p(h) in one fused prologue
-        pend = getattr(input_field, "_deferred", None) if getattr(input_field, "_data", None) is None else None
+        from ..DataType.ElectricField import DeferredElements
+        pend = DeferredElements.pending(input_field) if slab is None else None
         mask = mul = None
-        if pend is not None and getattr(pend, "is_elements", False) and slab is None:
+        if pend is not None:
             x, mask, mul = pend.x, pend.mask, pend.mul
         else:
             x = input_field.data

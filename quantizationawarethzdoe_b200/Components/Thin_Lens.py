@@ -22,7 +22,7 @@ class Thin_LensElement(nn.Module):
 
     def create_lens_phase_shift_kernel(self, field):
         """[1,C,H,W] complex64 lens kernel, Components/Thin_Lens.py:33-64 (cached)."""
-        pend = DeferredElements.pending(field)
+        pend = DeferredElements.peek(field)
         dev = pend.device if pend is not None else field.data.device       # reading .data would evaluate a pending aperture
         key = (tuple(field.shape[-2:]), tuple(field.spacing.detach().cpu().tolist()), tuple(field.wavelengths.detach().cpu().tolist()),
                float(self.focal_length), str(dev))

@@ -25,6 +25,7 @@ class DeferredElements:
         self.x, self.mask, self.mul = x, mask, mul
         self.shape = x.shape
         self.device = x.device
+        self.uses = 0
 
     def materialise(self):
         from .. import functional as Fn
@@ -36,10 +37,24 @@ class DeferredElements:
         return x
 
     @staticmethod
-    def pending(field):
-        """The un-evaluated element chain `field` carries, or None."""
+    def peek(field):
+        """The un-evaluated element chain `field` carries (None if there is none), without counting a use."""
         d = getattr(field, "_deferred", None) if getattr(field, "_data", None) is None else None
         return d if (d is not None and getattr(d, "is_elements", False)) else None
+
+    @staticmethod
+    def pending(field):
+        """The un-evaluated element chain `field` carries, or None.  A chain that is consumed a SECOND time (a fixed
+        field-in-front-of-the-DOE reused by every iteration of an optimisation loop, as the notebooks build it) is evaluated
+        once instead and served as a plain tensor from then on: fusing saves a pass per use only if the chain is used once."""
+        d = getattr(field, "_deferred", None) if getattr(field, "_data", None) is None else None
+        if d is None or not getattr(d, "is_elements", False):
+            return None
+        d.uses += 1
+        if d.uses > 1:
+            field.data            # materialise (cached in the field)
+            return None
+        return d
 
 
 class ElectricField:

@@ -26,7 +26,7 @@ import torch.nn as nn
 from .. import asm_host as AH
 from .. import bluestein as BL
 from .. import functional as Fn
-from ..DataType.ElectricField import ElectricField
+from ..DataType.ElectricField import DeferredElements, ElectricField
 
 
 class ASM_prop(nn.Module):
@@ -208,6 +208,8 @@ class ASM_prop(nn.Module):
     def forward(self, field):
         wavelengths = field.wavelengths
         deferred = getattr(field, "_deferred", None)
+        if deferred is not None and getattr(deferred, "is_elements", False):
+            deferred = DeferredElements.pending(field)          # counts the use; a re-used chain is evaluated once instead
         if deferred is not None and getattr(field, "_data", None) is None:
             B, C, H, W = deferred.shape
             dev = deferred.device

@@ -144,8 +144,7 @@ def calulate_single_element_loss_landscape(args, model, target, loss_f=nn.MSELos
     parts = _parts(model)
     if parts is not None:
         field, doe, prop = parts
-        pend = getattr(field, "_deferred", None) if getattr(field, "_data", None) is None else None
-        x = (pend.x if (pend is not None and getattr(pend, "is_elements", False)) else field.data).contiguous()
+        x = field.data.contiguous()                     # a fixed field in front of the DOE: evaluated once, reused by every grid point
         if x.shape[0] != 1 or not hasattr(prop, "_get_plan") or not hasattr(prop, "kernel_mode"):
             parts = None                # a batch of input fields / not an ASM propagator: evaluate point by point
     if parts is not None:
@@ -162,7 +161,7 @@ def calulate_single_element_loss_landscape(args, model, target, loss_f=nn.MSELos
                 maps.append(d.height_map.to(torch.float32))
                 coef = d.coef
             hm = torch.stack(maps).contiguous()                  # [Bc, H, W]
-            out = Fn.doe_asm_sweep(x, hm, prop, coef, field.spacing, field.wavelengths, d.mask, d.mul)
+            out = Fn.doe_asm_sweep(x, hm, prop, coef, field.spacing, field.wavelengths)
             vec[sel] = _losses_of(out, target, loss_f)
     else:
         for k in mine:

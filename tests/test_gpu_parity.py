@@ -880,6 +880,12 @@ def test_lens_and_aperture_are_fused_into_the_next_propagation(dev):
     assert lib.thz_launch_count_class(4) == l4
     mat = ap(ElectricField(x.to(dev), wavelengths=lams, spacing=dxy, device=dev)).data       # someone reads .data: stand-alone kernel
     assert lib.thz_launch_count_class(4) == l4 + 1 and rel_l2(mat.cpu(), x * mask.reshape(1, 1, n, n)) == 0.0
+    # a fixed field in front of the DOE that every iteration of a loop re-uses (the notebooks' field_before_DOE): fused on its first
+    # use, evaluated ONCE on the second, a plain tensor from then on
+    fixed = lens(ap(ElectricField(x.to(dev), wavelengths=lams, spacing=dxy, device=dev)))
+    outs = [asm(doe(fixed)).data.detach().clone() for _ in range(3)]
+    assert lib.thz_launch_count_class(4) == l4 + 3                   # + mask multiply + lens multiply, once
+    assert torch.equal(outs[1], outs[2]) and rel_l2(outs[0], outs[1]) < 1e-6 and fixed._data is not None
 
 
 def test_notebook_setup_end_to_end(dev):
