@@ -14,7 +14,7 @@
 //               -> ... -> inverse stage 0 -> registers -> cropped rows of T
 //   K3<N>       T row -> smem -> inverse stages ..1 -> inverse stage 0 -> registers -> crop/scale/epilogue -> y
 //
-// Every phase is a per-thread function; the __global__ wrappers (thz_asm_p2.cu) and the CPU replay
+// Every phase is a per-thread function; the __global__ wrappers (thz_asm_p2_kernels.inc) and the CPU replay
 // (tests/emul) put the barriers between them.
 #pragma once
 #include "thz_asm.cuh"

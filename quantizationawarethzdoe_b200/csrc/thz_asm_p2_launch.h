@@ -1,4 +1,4 @@
-// Launch entry points of the power-of-two fast path (defined in thz_asm_p2.cu, used by thz_asm.cu).
+// Launch entry points of the power-of-two fast path (defined in thz_asm_p2_k1.cu / _k2.cu / _k3.cu via thz_asm_p2_kernels.inc, used by thz_asm.cu).
 #pragma once
 #include <cuda_runtime.h>
 
