@@ -188,6 +188,28 @@ template <int N>
 THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int nt) {
     constexpr int LINES = p2_row_lines(N), PITCH = p2_pitch(N);
     const int total_lines = a.nbc * a.inH;
+    if constexpr (LINES > 1) {
+        // short lines, several per group: ONE flattened loop over the group's elements instead of a loop per line -- the
+        // per-line set-up (an integer division, a 64-bit block index) and the half-empty second trip of each line's loop
+        // were 36 instructions per stored element on the 400-point lines (profiles/r02_donn_*: 24 % of the kernel)
+        if (a.slab.parts <= 1 && a.t_tiled == 2) {
+            const int gl0 = bx * LINES;
+            const int f0 = gl0 / a.inH, r0 = gl0 - f0 * a.inH;
+            const int nvalid = (total_lines - gl0) < LINES ? (total_lines - gl0) : LINES;
+            const size_t fstride = (size_t)(N >> 2) * a.rowsT * 4;          // elements of one field in the blocked intermediate
+            const unsigned rs4 = (unsigned)a.rowsT * 4;
+            for (int e = tid; e < nvalid * N; e += nt) {
+                const int l = e / N, p = e - l * N;
+                int r = r0 + l, f = f0;
+                while (r >= a.inH) {
+                    r -= a.inH;
+                    ++f;
+                }
+                a.T[(size_t)f * fstride + (size_t)((unsigned)(p >> 2) * rs4 + (unsigned)((r << 2) + (p & 3)))] = s[l * PITCH + p + (p >> 4)];
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int l = 0; l < LINES; ++l) {
         const int gl = bx * LINES + l;
@@ -487,6 +509,19 @@ template <int N>
 THZ_HD void p2k3_prefetch(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nt, int part = 0, int nparts = 1) {
     constexpr int LINES = p2_row_lines(N), PITCH = p2_pitch(N);
     const int p_lo = tid + part * nt, p_step = nparts * nt;
+    if constexpr (LINES > 1) {
+        // short lines: the group's rows are ONE contiguous run of the row-major intermediate -- a single flattened loop
+        if (a.slab.parts <= 1 && !a.t_tiled) {
+            const int r0 = bx * LINES;
+            const int nvalid = (a.outH - r0) < LINES ? (a.outH - r0) : LINES;
+            const cpx* tb = a.T + ((size_t)f * a.rowsT + r0) * N;
+            for (int e = p_lo; e < nvalid * N; e += p_step) {
+                const int l = e / N, p = e - l * N;
+                thz_cp_async8(s + l * PITCH + p + (p >> 4), tb + e);
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int l = 0; l < LINES; ++l) {
         const int r = bx * LINES + l;
