@@ -198,6 +198,19 @@ THZ_HD void p2k1_store(const RowFwdArgs& a, const cpx* s, int bx, int tid, int n
             const int nvalid = (total_lines - gl0) < LINES ? (total_lines - gl0) : LINES;
             const size_t fstride = (size_t)(N >> 2) * a.rowsT * 4;          // elements of one field in the blocked intermediate
             const unsigned rs4 = (unsigned)a.rowsT * 4;
+            if (nvalid == LINES && r0 + LINES <= a.inH) {
+                // all lines of the group are consecutive rows of ONE field: in the blocked layout [c/4][r][c%4] the LINES rows
+                // of a 4-column block are LINES * 32 contiguous bytes, so walking (block, row, column) makes a warp's stores
+                // contiguous runs of 32 * LINES bytes instead of 32-byte pieces LINES rows apart
+                cpx* tb = a.T + (size_t)f0 * fstride + (size_t)r0 * 4;
+                constexpr int RUN = LINES * 4;
+                for (int e = tid; e < (N >> 2) * RUN; e += nt) {
+                    const int b = e / RUN, j = e - b * RUN;
+                    const int l = j >> 2, p = 4 * b + (j & 3);
+                    tb[(size_t)((unsigned)b * rs4 + (unsigned)j)] = s[l * PITCH + p + (p >> 4)];
+                }
+                return;
+            }
             for (int e = tid; e < nvalid * N; e += nt) {
                 const int l = e / N, p = e - l * N;
                 int r = r0 + l, f = f0;
