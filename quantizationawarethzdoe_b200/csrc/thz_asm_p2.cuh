@@ -625,6 +625,19 @@ template <int N>
 THZ_HD void p2k3_prefetch_epilogue(const RowInvArgs& a, int bx, int f, int tid, int nt) {
     if (!a.doe.hmap) return;
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, R = P2Stage<N, 0>::R, M = P2Stage<N, 0>::M;
+    if constexpr (LINES > 1) {
+        // short lines: the group's saved-field rows and height-map rows are contiguous runs -- one request per 32-byte sector
+        // in a flat loop (any thread may ask for any sector: the L2 is shared) instead of a 25-way per-butterfly index walk
+        const int r0 = bx * LINES;
+        const int nvalid = (a.outH - r0) < LINES ? (a.outH - r0) : LINES;
+        if (nvalid <= 0) return;
+        const cpx* xb = a.xsaved + ((size_t)f * a.outH + r0) * a.outW;
+        const float* hb = a.doe.hmap + (size_t)r0 * a.outW;
+        const int nx = nvalid * a.outW;
+        for (int e = tid * 4; e < nx; e += nt * 4) thz_prefetch_l2(xb + e);
+        for (int e = tid * 8; e < nx; e += nt * 8) thz_prefetch_l2(hb + e);
+        return;
+    }
     for (int w = tid; w < LINES * NB; w += nt) {
         const int line = w / NB, j = w % NB;
         const int r = bx * LINES + line;
