@@ -154,6 +154,19 @@ THZ_HD void p2_first_stage_from(cpx* base, int j, const cpx* __restrict__ tw, Lo
 #pragma unroll
         for (int t = 0; t < 8; ++t) in[t] = load.live(j + (4 + t) * M);
         dft16_half_in<false>(in, v);
+    } else if constexpr (HALF && R == 25 && M % 4 == 0) {
+        // centred 2x padding with a radix-25 first stage (N = 25 M: 400, 800, 1600, 2000, ...): element t is live iff
+        // 6.25 M <= j + t M < 18.75 M -- t = 7..17 always, t = 6 iff j >= M / 4, t = 18 iff j < 3 M / 4, the other 12 never:
+        // no bounds checks, no loads of padding (the butterfly itself is not pruned: a 3-of-5 sparse DFT5 costs what the
+        // full one does)
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            if (t >= 7 && t <= 17) v[t] = load.live(j + t * M);
+            else if (t == 6) v[t] = (j >= M / 4) ? load.live(j + t * M) : cmake(0.f, 0.f);
+            else if (t == 18) v[t] = (j < 3 * M / 4) ? load.live(j + t * M) : cmake(0.f, 0.f);
+            else v[t] = cmake(0.f, 0.f);
+        }
+        Dft<R, false>::run(v);
     } else {
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = load(j + t * M);
@@ -198,6 +211,25 @@ THZ_HD void p2_last_inverse_stage_to(const cpx* base, int j, const cpx* tw, Stor
             store.live(j + (4 + t) * M, t, 4 + t, out[t]);
             if constexpr (PF > 0) {
                 if (t + PF < 8) store.prefetch_live(j + (4 + t + PF) * M, t + PF);
+            }
+        }
+    } else if constexpr (HALF && R == 25 && M % 4 == 0 && PF <= 1) {
+        // centred crop with a radix-25 last stage: outputs t = 7..17 always survive, t = 6 iff j >= M / 4, t = 18 iff
+        // j < 3 M / 4, the rest never (see p2_first_stage_from): no bounds checks, no divergent skips
+        const bool lo = j >= M / 4, hi = j < 3 * M / 4;
+        if constexpr (PF > 0) {
+            if (lo) store.prefetch_live(j + 6 * M, 0);
+            else store.prefetch_live(j + 7 * M, 0);
+        }
+        p2_apply_twiddles<R>(v, cconj(tw[p2_twi(j)]));
+        Dft<R, true>::run(v);
+#pragma unroll
+        for (int t = 6; t <= 18; ++t) {
+            if (t == 6 && !lo) continue;
+            if (t == 18 && !hi) continue;
+            store.live(j + t * M, 0, t, v[t]);
+            if constexpr (PF > 0) {
+                if (t < 17 || (t == 17 && hi)) store.prefetch_live(j + (t + 1) * M, 0);
             }
         }
     } else {
