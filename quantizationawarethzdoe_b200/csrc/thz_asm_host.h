@@ -87,7 +87,7 @@ static inline bool thz_asm_two_buffers(const thz_asm_desc* d) {
 }
 
 static inline bool p2_k2_fast_ok_rt(int n) {
-    if (!thz_sp_instantiated(n) || (n & (n - 1)) != 0 || n < 256) return false;
+    if (!thz_sp_instantiated(n) || n < 256) return false;
 #define THZ_SP_FASTCMP(NN) if (n == NN) return sp_k2_fast_ok_or_false<NN>();
     THZ_SP_SIZES(THZ_SP_FASTCMP)
 #undef THZ_SP_FASTCMP

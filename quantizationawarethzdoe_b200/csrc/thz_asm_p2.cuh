@@ -377,9 +377,29 @@ THZ_HD void p2k2_last(const ColArgs& a, const cpx* s, const cpx* tw, int bx, int
 #endif
 constexpr int K2F_UNROLL = THZ_K2F_UNROLL;
 THZ_HD constexpr bool p2_k2_fast_ok(int N) {
-    return (N & (N - 1)) == 0 && N >= 256 && p2_radix(N, 0) == 16 && (p2_col_cols(N) * (N / 16)) % p2_col_threads(N) == 0 &&
-           (p2_col_cols(N) * (N / p2_radix(N, p2_stages(N) - 1))) % p2_col_threads(N) == 0;
+    // radix-16 first stage (pruned half butterflies) or radix-25 first stage with M % 4 == 0 (static liveness, see
+    // p2_first_stage_from); an even last radix (16-byte transfer-function loads)
+    return sp_static_ok(N) && N >= 256 && (p2_radix(N, 0) == 16 || (p2_radix(N, 0) == 25 && (N / 25) % 4 == 0)) &&
+           p2_radix(N, p2_stages(N) - 1) % 2 == 0;
 }
+
+// loads / stores of the fast column path: row 0 of the tile is canvas row N / 4, rows are 4 complex apart on the way in
+// (blocked intermediate) and `rs` complex apart on the way out (row-major)
+template <int N>
+struct K2FastLoader {
+    const cpx* p0;
+    THZ_HD cpx live(int pos) const { return thz_ld_stream(p0 + (pos - N / 4) * 4); }
+    THZ_HD cpx operator()(int pos) const { return (unsigned)(pos - N / 4) < (unsigned)(N / 2) ? live(pos) : cmake(0.f, 0.f); }
+};
+template <int N>
+struct K2FastStorer {
+    cpx* q0;
+    size_t rs;
+    THZ_HD void live(int pos, int, int, cpx v) const { thz_st_stream(q0 + (size_t)(pos - N / 4) * rs, v); }
+    THZ_HD void operator()(int pos, int, cpx v) const {
+        if ((unsigned)(pos - N / 4) < (unsigned)(N / 2)) live(pos, 0, 0, v);
+    }
+};
 
 template <int N>
 THZ_HD constexpr bool sp_k2_fast_ok_or_false() { return p2_k2_fast_ok(N); }
@@ -387,26 +407,34 @@ THZ_HD constexpr bool sp_k2_fast_ok_or_false() { return p2_k2_fast_ok(N); }
 template <int N, int COLS, int NT>
 THZ_HD void p2k2f_first(const ColArgs& a, cpx* s, int bx, int by, int tid) {
     typedef P2Stage<N, 0> St;
-    constexpr int NB = St::NB, M = St::M, ITEMS = COLS * NB / NT;
-    static_assert(St::R == 16 && (COLS * NB) % NT == 0 && 4 * M == N / 4, "fast column path: radix-16 first stage");
+    constexpr int NB = St::NB, M = St::M, ITEMS = (COLS * NB + NT - 1) / NT;
     const cpx* tile = a.T + ((((size_t)by * (a.Wp >> 2) + ((bx * COLS) >> 2)) * a.rowsT) << 2) + ((bx * COLS) & 3);
     // one butterfly after the other: with both butterflies' 16 loads in flight per thread the L1 request queue backs up and the
     // kernel is SLOWER (measured twice, profiles/README.md), so the item loop is deliberately not unrolled
 #pragma unroll K2F_UNROLL
     for (int k = 0; k < ITEMS; ++k) {
         const int w = tid + k * NT;
+        if ((COLS * NB) % NT != 0 && w >= COLS * NB) break;
         const int j = w / COLS, l = w % COLS;
         // element 4 + t of butterfly j is canvas row j + (4 + t) M = live row j + t M; rows are 4 complex (32 bytes) apart
-        const cpx* p0 = tile + (COLS > 4 ? (((size_t)(l >> 2) * a.rowsT) << 2) + (l & 3) : (size_t)l) + (size_t)j * 4;
-        cpx in[8];
+        const cpx* p0 = tile + (COLS > 4 ? (((size_t)(l >> 2) * a.rowsT) << 2) + (l & 3) : (size_t)l);
+        if constexpr (St::R == 16) {
+            static_assert(4 * M == N / 4, "radix-16 first stage: live elements 4..11");
+            p0 += (size_t)j * 4;
+            cpx in[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) in[t] = thz_ld_stream(p0 + t * M * 4);
-        cpx v[16];
-        dft16_half_in<false>(in, v);
-        p2_apply_twiddles<16>(v, thz_ldg(a.tw + j));
-        cpx* p = s + (j + (j >> 4)) * COLS + l;
+            for (int t = 0; t < 8; ++t) in[t] = thz_ld_stream(p0 + t * M * 4);
+            cpx v[16];
+            dft16_half_in<false>(in, v);
+            p2_apply_twiddles<16>(v, thz_ldg(a.tw + j));
+            cpx* p = s + (j + (j >> 4)) * COLS + l;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) p[p2_coff(M, t) * COLS] = v[t];
+            for (int t = 0; t < 16; ++t) p[p2_coff(M, t) * COLS] = v[t];
+        } else {        // radix-25 first stage: the general stage function with the static-address loader
+            K2FastLoader<N> ld;
+            ld.p0 = p0;
+            p2_first_stage_from<N, COLS, true>(s + l, j, a.tw, ld);
+        }
     }
 }
 
@@ -414,12 +442,13 @@ template <int N, int COLS, int NT, int TFM>
 THZ_HD void p2k2f_middle(const ColArgs& a, cpx* s, int bx, int by, int tid) {
     constexpr int S = p2_stages(N) - 1;
     typedef P2Stage<N, S> St;
-    constexpr int R = St::R, NB = St::NB, ITEMS = COLS * NB / NT;
-    static_assert(St::M == 1 && (COLS * NB) % NT == 0 && R % 2 == 0, "fast column path: unit last stage, even radix");
+    constexpr int R = St::R, NB = St::NB, ITEMS = (COLS * NB + NT - 1) / NT;
+    static_assert(St::M == 1 && R % 2 == 0, "fast column path: unit last stage, even radix");
     const int c_chan = (a.c0 + by) % a.C;
 #pragma unroll 1
     for (int k = 0; k < ITEMS; ++k) {
         const int w = tid + k * NT;
+        if ((COLS * NB) % NT != 0 && w >= COLS * NB) break;
         const int u = w / COLS, l = w % COLS;
         const int col = bx * COLS + l;
         const int p0 = u * R;
@@ -472,23 +501,31 @@ THZ_HD void p2k2f_middle(const ColArgs& a, cpx* s, int bx, int by, int tid) {
 template <int N, int COLS, int NT>
 THZ_HD void p2k2f_last(const ColArgs& a, const cpx* s, const cpx* tws, int bx, int by, int tid) {
     typedef P2Stage<N, 0> St;
-    constexpr int NB = St::NB, M = St::M, ITEMS = COLS * NB / NT;
+    constexpr int NB = St::NB, M = St::M, ITEMS = (COLS * NB + NT - 1) / NT;
     cpx* tile = a.Tout + (size_t)by * a.rowsT * a.Wp + (size_t)bx * COLS;       // row-major, row 0 = canvas row N / 4
     const size_t step = (size_t)M * a.Wp;
 #pragma unroll K2F_UNROLL
     for (int k = 0; k < ITEMS; ++k) {
         const int w = tid + k * NT;
+        if ((COLS * NB) % NT != 0 && w >= COLS * NB) break;
         const int j = w / COLS, l = w % COLS;
-        const cpx* p = s + (j + (j >> 4)) * COLS + l;
-        cpx v[16];
+        if constexpr (St::R == 16) {
+            const cpx* p = s + (j + (j >> 4)) * COLS + l;
+            cpx v[16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] = p[p2_coff(M, t) * COLS];
-        p2_apply_twiddles<16>(v, cconj(tws[p2_twi(j)]));
-        cpx o[8];
-        dft16_half_out<true>(v, o);
-        cpx* q = tile + (size_t)j * a.Wp + l;             // output 4 + t is canvas row j + (4 + t) M = live row j + t M
+            for (int t = 0; t < 16; ++t) v[t] = p[p2_coff(M, t) * COLS];
+            p2_apply_twiddles<16>(v, cconj(tws[p2_twi(j)]));
+            cpx o[8];
+            dft16_half_out<true>(v, o);
+            cpx* q = tile + (size_t)j * a.Wp + l;             // output 4 + t is canvas row j + (4 + t) M = live row j + t M
 #pragma unroll
-        for (int t = 0; t < 8; ++t, q += step) thz_st_stream(q, o[t]);
+            for (int t = 0; t < 8; ++t, q += step) thz_st_stream(q, o[t]);
+        } else {        // radix-25: the general stage function with the static-address storer
+            K2FastStorer<N> st;
+            st.q0 = tile + l;
+            st.rs = (size_t)a.Wp;
+            p2_last_inverse_stage_to<N, COLS, true>(s + l, j, tws, st);
+        }
     }
 }
 
