@@ -263,6 +263,26 @@ def secondary_single(dev, lib, sm_mhz, hbm_peak):
                                                  "hbm_frac": 40.0 * smp / (ms * 1e-3) / 1e9 / hbm_peak}
     del x5, f5, asm5
     torch.cuda.empty_cache()
+    # ---- beyond the shared-memory line: one 16384^2 field on a 32768^2 canvas (longline.py: 2 x 2 split around the fused pipeline)
+    if os.environ.get("THZ_BENCH_LONG", "1") == "1" and torch.cuda.mem_get_info(dev)[0] > (64 << 30):
+        n6 = 16384
+        x6 = torch.randn(1, 1, n6, n6, dtype=torch.complex64, device=dev).requires_grad_(True)
+        asm6 = ASM_prop(z_distance=Z, device=dev)
+        asm6.check_Zc = False
+        f6 = ElectricField(x6, wavelengths=lam1, spacing=sp, device=dev)
+        g6 = torch.randn(1, 1, n6, n6, dtype=torch.complex64, device=dev)
+
+        def c6_step():
+            y = asm6(f6).data
+            torch.autograd.grad(y, x6, g6)
+
+        ms = _event_ms(c6_step, 3, 1, dev)
+        smp = (2 * n6) ** 2
+        out["long_canvas_%d_padded" % (2 * n6)] = {"fwd_bwd_ms": ms, "Msamples_per_s": smp / ms / 1e3,
+                                                   "kernel_mode": asm6.resolved_kernel_mode,
+                                                   "peak_gpu_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)}
+        del x6, f6, g6, asm6
+        torch.cuda.empty_cache()
     # ---- C4
     n, B, layers = 200, 1024, 3
     does = [STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=SPACING, doe_level=4, height_constraint_max=HMAX, tolerance=None,

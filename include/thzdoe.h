@@ -165,11 +165,32 @@ typedef struct thz_asm_desc {
  * for the unique quarter of the (even) frequency grid: angq float32 [C][Hp/2+1][Wp/2+1] = z * sqrt(klam^2 - Kx^2[|i|] - Ky^2[|j|])
  * computed with the reference's own library (Props/ASM_Prop.py:257).  rowtau float32 [C][Hp][2] = {Kx^2, tau} and colk2
  * float32 [C][Wp] in slot order as for tf_mode 0 (the keep mask Ky^2 <= tau is bit-identical to the reference's); rabs int32
- * [Hp] / cabs int32 [Wp] = |centred frequency index| of every slot.  table complex64 [C][Wp][Hp] (out). */
+ * [Hp] / cabs int32 [Wp] = |centred frequency index| of every slot.  table complex64 [C][Wp][Hp] (out).  Hu x Wu is the extent of
+ * angq and must cover every rabs / cabs entry; it equals (Hp/2+1) x (Wp/2+1) for a whole grid and is larger when the table is a
+ * decimated sub-grid of a longer canvas (thz_split_pre below). */
 int thz_tf_table_from_angles(const void* angq, int32_t C, int32_t Hu, int32_t Wu, const void* rowtau, const void* colk2,
                              const void* rabs, const void* cabs, int32_t Hp, int32_t Wp, void* table, void* stream);
 uint64_t thz_asm_workspace_bytes(const thz_asm_desc* desc);
 int thz_asm_propagate(const thz_asm_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * thz_split_pre / thz_split_post -- the outer decimation step for canvases with an edge above 16384 points (the longest line
+ * the in-shared-memory plans hold).  The reference hands any size to torch.fft.fft2 / ifft2 (utils/Helper_Functions.py:141-150,
+ * Props/ASM_Prop.py:329-341); here an edge N = P M (P = 1, 2 or 4 per axis) is split into P interleaved length-M problems
+ *     X[P k + a] = FFT_M(u_a)[k],    u_a[n] = sum_s x[n + s M] w_N^{a (n + s M)},    w_N = exp(-2 pi i / N)
+ * so that  ifft2(H . fft2(pad(x)))  becomes Pr Pc independent un-padded thz_asm_propagate problems of size Mr x Mc (one extra
+ * "channel" per (a, b), transfer function = the decimated one), between
+ *   thz_split_pre : x complex64 [F][H][W] = the live region at (r0, c0) of the Hp x Wp canvas (zero elsewhere, never stored)
+ *                   -> u complex64 [F][Pr Pc][Hp/Pr][Wp/Pc],  times `scale`;
+ *   thz_split_post: v complex64 [F][Pr Pc][Hp/Pr][Wp/Pc] -> y complex64 [F][H][W] = the region at (r0, c0) of
+ *                   sum_ab conj(w^{a i}) conj(w^{b j}) v_ab[i mod Mr][j mod Mc],  times `scale` (pass 1 / (Pr Pc));
+ * post is the adjoint of pre, so the adjoint propagation is the same chain with the two regions swapped.  tw_r / tw_c:
+ * complex64 [Hp] / [Wp] = w^j; conj_tw = 1 uses the conjugate twiddles in both (inverse transforms).
+ * ------------------------------------------------------------------------------------------- */
+int thz_split_pre(const void* x, void* u, int32_t F, int32_t H, int32_t W, int32_t r0, int32_t c0, int32_t Hp, int32_t Wp,
+                  int32_t Pr, int32_t Pc, const void* tw_r, const void* tw_c, int32_t conj_tw, float scale, void* stream);
+int thz_split_post(const void* v, void* y, int32_t F, int32_t H, int32_t W, int32_t r0, int32_t c0, int32_t Hp, int32_t Wp,
+                   int32_t Pr, int32_t Pc, const void* tw_r, const void* tw_c, int32_t conj_tw, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * thz_fft2_c2c -- stand-alone batched 2-D complex FFT in natural order (tests, ft2/ift2 helpers).

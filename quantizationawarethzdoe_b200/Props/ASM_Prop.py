@@ -26,6 +26,7 @@ import torch.nn as nn
 from .. import asm_host as AH
 from .. import bluestein as BL
 from .. import functional as Fn
+from .. import longline as LL
 from ..DataType.ElectricField import DeferredElements, ElectricField
 
 
@@ -163,6 +164,38 @@ class ASM_prop(nn.Module):
                 else:
                     print("The critical distance is {} m, the TF will be fine during the sampling !".format(Zc.numpy()))
                 self.check_Zc = False
+            unpad = bool(self.do_padding and self.do_unpad_after_pad)
+            sp = None
+            if LL.needs_split(Hp, Wp):
+                try:
+                    sp = LL.split_or_none(Hp, Wp)
+                except NotImplementedError:
+                    sp = None                         # not 2 or 4 times a radix-plan length: chirp-z below (or its size error)
+            if sp is not None:
+                # an edge above 16384 points: one outer decimation step per long axis around the fused pipeline (longline.py);
+                # the transfer function of every sub-problem is the decimated one, same two modes as below
+                rowvec, colvec, scal = AH.tf_vectors(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
+                mode_ = self.kernel_mode
+                if mode_ == 'auto':
+                    self.inregister_estimate = AH.inregister_estimate_for(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel,
+                                                                          self.bandlimit_type)
+                    mode_ = 'inregister' if self.inregister_estimate <= AH.INREGISTER_BUDGET else 'cached'
+                sv = LL.split_tf_vectors(rowvec, colvec, scal, *sp) if mode_ == 'inregister' else None
+                if sv is not None:
+                    self._plan = LL.SplitAsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, sp[0], sp[1], vectors=sv)
+                elif device.type == "cuda":
+                    table = LL.split_tf_table_device(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type,
+                                                     device, *sp)
+                    self._plan = LL.SplitAsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, sp[0], sp[1], table=table)
+                else:
+                    Hc = AH.tf_centred_reference_order(Hp, Wp, spacing, wavelengths, z, self.bandlimit_kernel, self.bandlimit_type)
+                    table = LL.split_tables_from_natural(torch.fft.ifftshift(Hc, dim=(-2, -1)), *sp)
+                    self._plan = LL.SplitAsmPlan(B, C, H, W, pad_h, pad_w, Hp, Wp, unpad, device, sp[0], sp[1], table=table)
+                self.resolved_kernel_mode = '%s (split %d x %d)' % ('inregister' if sv is not None else 'cached', sp[0], sp[1])
+                self._plan_key = key
+                self._fast_key = fast
+                self._fast_refs = (spacing, wavelengths)
+                return self._plan
             if not (BL.length_supported(Hp) and BL.length_supported(Wp)):
                 # an edge length with a prime factor > 7 (the reference's torch.fft takes any size): chirp-z on the fused
                 # pipeline, transfer function = the reference's own (host-built, as in 'cached')
@@ -221,6 +254,9 @@ class ASM_prop(nn.Module):
         plan = self._get_plan(B, C, H, W, field.spacing, wavelengths, dev)
         if isinstance(plan, BL.BluesteinAsmPlan):      # DOE modulation (if any) is materialised by its own kernel first
             out = BL.BluesteinAsmFn.apply(field.data, plan)
+            return ElectricField(data=out, wavelengths=wavelengths, spacing=field.spacing, device=dev)
+        if isinstance(plan, LL.SplitAsmPlan):          # likewise on canvases above 16384 points per edge
+            out = Fn.AsmPropagateFn.apply(field.data, plan)
             return ElectricField(data=out, wavelengths=wavelengths, spacing=field.spacing, device=dev)
         if deferred is not None and getattr(deferred, "is_elements", False):        # aperture / lens only: fused on load
             out = Fn.AsmPropagateFn.apply(deferred.x, plan, deferred.mask, deferred.mul)

@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from .. import _native as N
 from .. import functional as Fn
+from .. import longline as LL
 from ..DataType.ElectricField import ElectricField
 
 mm = 1e-3
@@ -118,9 +119,7 @@ class RSC_prop(nn.Module):
                 self.check_Zc = False
             K = self._kernel_host(Hp, Wp, dx, dy, wavelengths.detach().cpu().float(), z).to(device)
             spec = Fn.fft2_c2c(K) * (dx * dy).to(device)                     # fft2(K_rs) dx dy, natural bin order (our FFT kernels)
-            pr, pc = N.slot_to_bin(Hp).to(device), N.slot_to_bin(Wp).to(device)
-            table = spec[:, pr][:, :, pc].transpose(1, 2).contiguous()       # table[c][slot_c][slot_r]
-            plan = Fn.AsmPlan(B, C, H, W, 0, 0, Hp, Wp, True, device, None, None, None, table, 1)
+            plan = LL.table_plan(B, C, H, W, 0, 0, Hp, Wp, True, device, spec)   # cached table[c][slot_c][slot_r] (split above 16384)
             plan.out_r0, plan.out_c0 = H, W                                  # lower-right submatrix (:207); input sits at (0, 0) (:199)
             self._plan, self._plan_key = plan, key
         self._plan.B = B

@@ -105,6 +105,8 @@ def _declare(l):
     l.thz_field_mul.argtypes = [vp, vp, vp, i32, i32, u64, i32, i32, i32, vp]
     l.thz_normmse_loss.argtypes = [vp, vp, i32, u64, vp, vp, vp, vp]
     l.thz_tf_table_from_angles.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp]
+    l.thz_split_pre.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, f32, vp]
+    l.thz_split_post.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, f32, vp]
     l.thz_normmse_loss_each.argtypes = [vp, vp, i32, i32, u64, vp, vp, vp]
     l.thz_adam_step.argtypes = [vp, vp, vp, vp, vp, u64, f32, f32, f32, f32, f32, i32, i32, vp]
     l.thz_launch_count.restype = u64
@@ -127,6 +129,7 @@ EXPORTS = [
     "thz_launch_count", "thz_launch_count_class", "thz_profile_enable", "thz_profile_read", "thz_toeplitz_gemm", "thz_tf_row_thresholds",
     "thz_normmse_loss", "thz_adam_step", "thz_fft_is_static", "thz_field_mul",
     "thz_quant_softmax_fwd", "thz_quant_softmax_bwd", "thz_score_thickness", "thz_normmse_loss_each", "thz_tf_table_from_angles",
+    "thz_split_pre", "thz_split_post",
 ]
 
 

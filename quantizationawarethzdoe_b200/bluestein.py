@@ -23,15 +23,16 @@ import torch
 
 from . import _native as N
 from . import functional as Fn
+from . import longline as LL
 
-MAX_CONV = 16384          # longest line the in-shared-memory plans hold
+MAX_CONV = 16384          # longest line the in-shared-memory plans hold (longline.max_line(); longer canvases are split once)
 
 
 def length_supported(n):
     """True if the in-shared-memory plans transform length n directly (prime factors <= 7, line fits shared memory)."""
     import ctypes
     rad, ns = (ctypes.c_int32 * 16)(), ctypes.c_int32(0)
-    return int(n) <= MAX_CONV and N.lib().thz_fft_plan_info(int(n), rad, ctypes.byref(ns)) == 0
+    return int(n) <= LL.max_line() and N.lib().thz_fft_plan_info(int(n), rad, ctypes.byref(ns)) == 0
 
 
 def conv_length(n):
@@ -39,9 +40,10 @@ def conv_length(n):
     L = 16
     while L < 2 * n - 1:
         L *= 2
-    if L > MAX_CONV:
-        raise NotImplementedError("transform length %d needs a %d-point chirp convolution; the in-shared-memory plans stop at %d "
-                                  "(lengths up to %d are served)" % (n, L, MAX_CONV, (MAX_CONV + 1) // 2))
+    top = 4 * LL.max_line()                  # one outer split (longline.py) on top of the in-shared-memory plans
+    if L > top:
+        raise NotImplementedError("transform length %d needs a %d-point chirp convolution; convolutions are served up to %d points "
+                                  "(lengths up to %d)" % (n, L, top, (top + 1) // 2))
     return L
 
 
@@ -81,7 +83,7 @@ class _Conv:
         L1, L2 = conv_length(H), conv_length(W)
         spec = torch.from_numpy(kernel_spectrum(H, W, L1, L2, inverse).astype(np.complex64))[None]
         inH, inW, r0, c0 = region_in
-        self.plan = Fn.AsmPlan(1, 1, inH, inW, r0, c0, L1, L2, True, device, None, None, None, table_slot_order(spec), 1)
+        self.plan = LL.table_plan(1, 1, inH, inW, r0, c0, L1, L2, True, device, spec.to(device))
         self.plan.outH, self.plan.outW, self.plan.out_r0, self.plan.out_c0 = region_out
         self.out_shape = region_out[:2]
 

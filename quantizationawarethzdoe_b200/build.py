@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libthzdoe.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
-SOURCES = ["thz_api.cu", "thz_asm.cu", "thz_asm_p2_k1.cu", "thz_asm_p2_k2.cu", "thz_asm_p2_k3.cu", "thz_doe.cu", "thz_czt.cu", "thz_czt_tc.cu", "thz_train.cu"]
+SOURCES = ["thz_api.cu", "thz_asm.cu", "thz_asm_p2_k1.cu", "thz_asm_p2_k2.cu", "thz_asm_p2_k3.cu", "thz_doe.cu", "thz_split.cu", "thz_czt.cu", "thz_czt_tc.cu", "thz_train.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--threads", "4",

@@ -489,7 +489,7 @@ extern "C" int thz_tf_table_from_angles(const void* angq, int32_t C, int32_t Hu,
                                         const void* rabs, const void* cabs, int32_t Hp, int32_t Wp, void* table, void* stream_) {
     ThzDeviceGuard dev_guard(table);
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (C < 1 || Hp < 1 || Wp < 1 || Hu != Hp / 2 + 1 || Wu != Wp / 2 + 1) return thz_set_error(THZ_E_SHAPE, "thz_tf_table_from_angles: bad sizes");
+    if (C < 1 || Hp < 1 || Wp < 1 || Hu < 1 || Wu < 1) return thz_set_error(THZ_E_SHAPE, "thz_tf_table_from_angles: bad sizes");
     if (!angq || !rowtau || !colk2 || !rabs || !cabs || !table) return thz_set_error(THZ_E_NULL, "thz_tf_table_from_angles: null pointer");
     if (Wp > 65535 || C > 65535) return thz_set_error(THZ_E_SHAPE, "thz_tf_table_from_angles: grid too large");
     dim3 grid((Hp + 255) / 256 > 8 ? 8 : (Hp + 255) / 256, Wp, C);

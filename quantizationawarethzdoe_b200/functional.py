@@ -484,10 +484,13 @@ _bluestein_fft2 = {}
 
 def fft2_c2c(x, inverse=False, ortho=False):
     """Stand-alone natural-order batched 2-D FFT over the last two dims (thz_fft2_c2c); sizes with a prime factor > 7 go
-    through the chirp-z path (bluestein.BluesteinFft2) -- any size torch.fft.fft2 takes, up to 8192 per edge."""
+    through the chirp-z path (bluestein.BluesteinFft2), edges above 16384 points through one outer split (longline.fft2_split)."""
     x = _c64(x, "input")
     H, W = x.shape[-2], x.shape[-1]
     from . import bluestein as BL
+    from . import longline as LL
+    if LL.needs_split(H, W) and LL.split_factor(H) is not None and LL.split_factor(W) is not None:
+        return LL.fft2_split(x, inverse, ortho)       # an edge above 16384 points: one outer decimation step (longline.py)
     if not (BL.length_supported(H) and BL.length_supported(W)):
         key = (H, W, bool(inverse), bool(ortho), str(x.device))
         plan = _bluestein_fft2.get(key)

@@ -371,3 +371,45 @@ extern "C" int thz_emul_score_thickness(const float* t, const float* lut, int32_
     }
     return THZ_OK;
 }
+
+// outer decimation step for lines above 16384 points (thz_split.cuh bodies), on host pointers
+#include "../../quantizationawarethzdoe_b200/csrc/thz_split.cuh"
+template <int PR, int PC>
+static void emul_split_pre(const SplitArgs& A, const cpx* x, cpx* u, int F) {
+    for (int f = 0; f < F; ++f)
+        for (int n = 0; n < A.Hp / PR; ++n)
+            for (int m = 0; m < A.Wp / PC; ++m)
+                thz_split_pre_point<PR, PC>(A, x + (size_t)f * A.H * A.W, u + (size_t)f * A.Hp * A.Wp, n, m);
+}
+template <int PR, int PC>
+static void emul_split_post(const SplitArgs& A, const cpx* v, cpx* y, int F) {
+    for (int f = 0; f < F; ++f)
+        for (int i = 0; i < A.H; ++i)
+            for (int j = 0; j < A.W; ++j)
+                y[((size_t)f * A.H + i) * A.W + j] = thz_split_post_point<PR, PC>(A, v + (size_t)f * A.Hp * A.Wp, i, j);
+}
+#define EMUL_SPLIT_DISPATCH(FN, ...)                    \
+    switch (Pr * 8 + Pc) {                              \
+        case 1 * 8 + 1: FN<1, 1>(__VA_ARGS__); break;   \
+        case 1 * 8 + 2: FN<1, 2>(__VA_ARGS__); break;   \
+        case 1 * 8 + 4: FN<1, 4>(__VA_ARGS__); break;   \
+        case 2 * 8 + 1: FN<2, 1>(__VA_ARGS__); break;   \
+        case 2 * 8 + 2: FN<2, 2>(__VA_ARGS__); break;   \
+        case 2 * 8 + 4: FN<2, 4>(__VA_ARGS__); break;   \
+        case 4 * 8 + 1: FN<4, 1>(__VA_ARGS__); break;   \
+        case 4 * 8 + 2: FN<4, 2>(__VA_ARGS__); break;   \
+        case 4 * 8 + 4: FN<4, 4>(__VA_ARGS__); break;   \
+        default: return THZ_E_UNSUPPORTED;              \
+    }
+extern "C" int thz_emul_split_pre(const void* x, void* u, int32_t F, int32_t H, int32_t W, int32_t r0, int32_t c0, int32_t Hp,
+                                  int32_t Wp, int32_t Pr, int32_t Pc, const void* twr, const void* twc, int32_t conj_tw, float scale) {
+    const SplitArgs A = {Hp, Wp, H, W, r0, c0, (const cpx*)twr, (const cpx*)twc, conj_tw ? 1 : 0, scale};
+    EMUL_SPLIT_DISPATCH(emul_split_pre, A, (const cpx*)x, (cpx*)u, F)
+    return THZ_OK;
+}
+extern "C" int thz_emul_split_post(const void* v, void* y, int32_t F, int32_t H, int32_t W, int32_t r0, int32_t c0, int32_t Hp,
+                                   int32_t Wp, int32_t Pr, int32_t Pc, const void* twr, const void* twc, int32_t conj_tw, float scale) {
+    const SplitArgs A = {Hp, Wp, H, W, r0, c0, (const cpx*)twr, (const cpx*)twc, conj_tw ? 1 : 0, scale};
+    EMUL_SPLIT_DISPATCH(emul_split_post, A, (const cpx*)v, (cpx*)y, F)
+    return THZ_OK;
+}

@@ -85,4 +85,6 @@ def emul_lib():
     E.thz_emul_softmaxq.argtypes = [vp, vp, i32, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, u64]
     E.thz_emul_softmaxq_bwd.argtypes = [vp, vp, vp, vp, vp, vp, u64]
     E.thz_emul_score_thickness.argtypes = [vp, vp, i32, f32, i32, vp, i32, u64]
+    E.thz_emul_split_pre.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, f32]
+    E.thz_emul_split_post.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, f32]
     return E

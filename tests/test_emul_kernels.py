@@ -431,3 +431,114 @@ def test_pointwise_elements_fused_into_the_row_kernels(H, W, scale, with_doe):
     assert rel_l2(gx, gxo) < TOL_TABLE
     if with_doe:
         assert rel_l2(gh, gho) < TOL_TABLE
+
+
+# ------------------------------------------------------------------------------- lines above max_line(): the outer split
+def _install_longline_cpu(monkeypatch, max_line):
+    """Replay of thz_split_pre / thz_split_post + the fused pipeline, with the direct-transform limit lowered to `max_line` so
+    that small grids take the split path (longline.py) -- the same code that serves edges above 16384 points on the device."""
+    from quantizationawarethzdoe_b200 import functional as Fn, longline as LL
+    _install_bluestein_cpu(monkeypatch)
+    E = emul_lib()
+    monkeypatch.setitem(Fn.TUNE, "max_line", max_line)
+    monkeypatch.setattr(LL, "_plan_ok", E_plan_ok)
+
+    def pre(x, region, Hp, Wp, Pr, Pc, conj_tw=False, scale=1.0):
+        H, W, r0, c0 = region
+        x = x.contiguous()
+        u = torch.zeros(tuple(x.shape[:-2]) + (Pr * Pc, Hp // Pr, Wp // Pc), dtype=torch.complex64)
+        rc = E.thz_emul_split_pre(N.ptr(x), N.ptr(u), x.numel() // (H * W), H, W, r0, c0, Hp, Wp, Pr, Pc,
+                                  N.ptr(LL.line_twiddles(Hp, "cpu")), N.ptr(LL.line_twiddles(Wp, "cpu")), int(conj_tw), float(scale))
+        assert rc == 0
+        return u
+
+    def post(v, y, region, Hp, Wp, Pr, Pc, conj_tw=False, scale=1.0):
+        H, W, r0, c0 = region
+        v = v.contiguous()
+        out = torch.zeros(y.shape, dtype=torch.complex64)
+        rc = E.thz_emul_split_post(N.ptr(v), N.ptr(out), y.numel() // (H * W), H, W, r0, c0, Hp, Wp, Pr, Pc,
+                                   N.ptr(LL.line_twiddles(Hp, "cpu")), N.ptr(LL.line_twiddles(Wp, "cpu")), int(conj_tw), float(scale))
+        assert rc == 0
+        y.copy_(out)
+        return y
+
+    def fft2(x, inverse=False, ortho=False):
+        x = x.contiguous()
+        H, W = x.shape[-2:]
+        y, ws = torch.zeros_like(x), torch.zeros_like(x)
+        rc = E.thz_emul_fft2_c2c(N.ptr(x), N.ptr(y), x.numel() // (H * W), H, W, int(inverse), int(ortho), N.ptr(N.twiddles_host(H)),
+                                 N.ptr(N.twiddles_host(W)), N.ptr(ws))
+        assert rc == 0
+        return y
+
+    monkeypatch.setattr(LL, "split_pre", pre)
+    monkeypatch.setattr(LL, "split_post", post)
+    monkeypatch.setattr(Fn, "fft2_c2c", fft2)
+    return LL
+
+
+@pytest.mark.parametrize("H,W,scale,max_line,mode,split", [
+    (64, 64, None, 64, "inregister", "2 x 2"),          # 128 x 128 canvas, both edges split in two
+    (32, 128, None, 64, "cached", "1 x 4"),             # 64 x 256: only the long edge, in four
+    (60, 50, [3, 1], 100, "inregister", "4 x 1"),       # 240 x 100: mixed radix sub-lengths (60, 100), unpad crop off-centre
+    (96, 40, None, 48, "cached", "4 x 2")])             # 192 x 80 -> 48 x 40 sub-problems on the runtime-planned engine
+def test_long_line_asm_through_the_outer_split(H, W, scale, max_line, mode, split, monkeypatch):
+    """ASM_prop on a canvas with an edge above the direct-transform limit: split -> un-padded fused propagation of Pr Pc
+    decimated sub-problems -> merge, against the oracle, forward and adjoint, both transfer-function modes."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField
+    _install_longline_cpu(monkeypatch, max_line)
+    lams, dxy, z = [1e-3, 1.04e-3], 0.5e-3, 0.03
+    torch.manual_seed(0)
+    x = torch.randn(2, 2, H, W, dtype=torch.complex64)
+    g = torch.randn(2, 2, H, W, dtype=torch.complex64)
+    asm = ASM_prop(z_distance=z, padding_scale=scale, kernel_mode=mode, device=torch.device("cpu"))
+    asm.check_Zc = False
+    xr = x.clone().requires_grad_(True)
+    y = asm(ElectricField(xr, wavelengths=lams, spacing=dxy, device=torch.device("cpu"))).data
+    assert asm.resolved_kernel_mode == "%s (split %s)" % (mode, split)
+    (gx,) = torch.autograd.grad(y, xr, g)
+    xo = x.clone().requires_grad_(True)
+    yo = AO.asm_forward(xo, lams, dxy, z, padding_scale=scale)
+    (gxo,) = torch.autograd.grad(yo, xo, g)
+    tol = TOL if mode == "cached" else 2e-5            # in-register H: the sqrt deviation of DESIGN.md section 4, same as unsplit
+    assert rel_l2(y.detach(), yo.detach()) < tol and rel_l2(gx, gxo) < tol
+
+
+def test_long_line_split_equals_the_direct_plan(monkeypatch):
+    """The split path and the direct path are the same operator: 256 x 128 canvas run directly and as 2 x 2 / 4 x 1 splits."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, functional as Fn
+    _install_longline_cpu(monkeypatch, 16384)
+    lams, dxy, z = [1e-3], 0.5e-3, 0.02
+    torch.manual_seed(3)
+    x = torch.randn(1, 1, 128, 64, dtype=torch.complex64)
+    outs = []
+    for ml in (16384, 128, 64):
+        monkeypatch.setitem(Fn.TUNE, "max_line", ml)
+        asm = ASM_prop(z_distance=z, kernel_mode="cached", do_unpad_after_pad=False, device=torch.device("cpu"))
+        asm.check_Zc = False
+        outs.append(asm(ElectricField(x, wavelengths=lams, spacing=dxy, device=torch.device("cpu"))).data)
+        assert ("split" in asm.resolved_kernel_mode) == (ml < 256)
+    assert outs[0].shape == (1, 1, 256, 128)
+    assert rel_l2(outs[1], outs[0]) < 1e-6 and rel_l2(outs[2], outs[0]) < 1e-6
+
+
+@pytest.mark.parametrize("H,W,max_line", [(128, 64, 64), (40, 256, 64), (200, 120, 60)])
+def test_long_line_fft2_through_the_outer_split(H, W, max_line, monkeypatch):
+    LL = _install_longline_cpu(monkeypatch, max_line)
+    torch.manual_seed(2)
+    x = torch.randn(2, 3, H, W, dtype=torch.complex64)
+    for inverse, ortho in ((False, False), (True, False), (False, True), (True, True)):
+        ref = (torch.fft.ifft2 if inverse else torch.fft.fft2)(x, norm="ortho" if ortho else "backward")
+        assert rel_l2(LL.fft2_split(x, inverse, ortho), ref) < 2e-6, (inverse, ortho)
+
+
+def test_long_chirp_convolution_uses_the_split(monkeypatch):
+    """Chirp-z lengths whose convolution canvas exceeds the direct limit (n > max_line / 2) go through the split plan."""
+    from quantizationawarethzdoe_b200 import bluestein as BL, longline as LL
+    _install_longline_cpu(monkeypatch, 64)
+    monkeypatch.setattr(BL, "length_supported", lambda n: n <= 64 and E_plan_ok(n))
+    torch.manual_seed(5)
+    x = torch.randn(2, 1, 13, 47, dtype=torch.complex64)            # 47 -> 128-point convolution = 2 x 64
+    plan = BL.BluesteinFft2(13, 47, False, False, torch.device("cpu"))
+    assert isinstance(plan.conv.plan, LL.SplitAsmPlan) and (plan.conv.plan.Pr, plan.conv.plan.Pc) == (1, 2)
+    assert rel_l2(plan(x), torch.fft.fft2(x)) < 3e-6
