@@ -466,12 +466,23 @@ def run_ours(args, rank, local_rank, world):
     sp_t = torch.tensor([SPACING, SPACING], dtype=torch.float32, device=dev)
     gw_host = torch.empty(1, 1, n, n, dtype=torch.float32).pin_memory()
 
+    # N > 1: the sum of the weight gradient over the ranks forms inside the adjoint's last kernel (multimem.red through the
+    # NVSwitch, parallel.FusedGradReduce) where NVLS multicast exists; otherwise one NCCL all-reduce after the backward pass
+    fused_reduce = False
+    if world > 1 and os.environ.get("THZ_BENCH_FUSED_REDUCE", "1") == "1":
+        from quantizationawarethzdoe_b200 import parallel as P
+        ok = torch.tensor([1.0 if P.FusedGradReduce.available(dev) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) > 0:
+            P.fuse_gradient_allreduce(doe)
+            fused_reduce = True
+
     def step(x):
-        """One hot-path pass; returns the gradient wrt the DOE weights (all-reduced when world > 1)."""
+        """One hot-path pass; returns the gradient wrt the DOE weights (summed over the ranks when world > 1)."""
         field = ElectricField(x, wavelengths=lam_t, spacing=sp_t, device=dev)
         y = asm(doe(field)).data
         gx, gw = torch.autograd.grad(y, (x, doe.weight_height_map), y.detach())
-        if world > 1:
+        if world > 1 and not fused_reduce:
             dist.all_reduce(gw)
         return gw
 
@@ -634,7 +645,9 @@ def run_ours(args, rank, local_rank, world):
                    "fields_per_gpu": B * C, "samples_per_step": samples_per_step, "kernel_mode": asm.kernel_mode,
                    "kernel_mode_resolved": asm.resolved_kernel_mode, "inregister_estimate": asm.inregister_estimate,
                    "l2": "inputs larger than L2 (512 MiB fields + 2 x 1 GiB intermediate spectra per step)", "tune": dict(Fn.TUNE),
-                   "parallelism": "dp%d over wavelengths, NCCL all-reduce of grad(weights)" % world if world > 1 else "single GPU"},
+                   "parallelism": ("dp%d over wavelengths, grad(weights) summed %s" % (
+                       world, "inside the adjoint's last kernel (multimem.red over NVSwitch multicast + one symmetric-memory barrier)"
+                       if fused_reduce else "by one NCCL all-reduce per step")) if world > 1 else "single GPU"},
         "e2e": {"value": e2e_val, "unit": "Msamples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_host.numel() * 8,
                 "d2h_bytes_per_step": gw_host.numel() * 4, "numa": numa_note},
         "gpu_launches": int(launches),

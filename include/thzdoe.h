@@ -152,7 +152,12 @@ typedef struct thz_asm_desc {
        the DOE phase; 2 (adjoint calls): the output is multiplied by mask * conj(mul) and, with doe_mode 2, grad_height is
        formed against xsaved * mask * mul.  Sizes follow the region they apply to (forward: inH x inW, adjoint: outH x outW). */
     int32_t elem_mode;
-    int32_t reserved3;
+    /* doe_mode 2 only.  0: doe_gh is ordinary device memory, overwritten with this call's grad_height.  1: doe_gh is an NVLS
+       MULTICAST address (cuMulticast* / torch symmetric memory `multicast_ptr`) of a float32 [outH,outW] buffer replicated on
+       every GPU of a data-parallel group: the epilogue ADDS its partial sums with multimem.red, i.e. the sum over the ranks
+       forms inside the NVSwitch while the kernel runs and replaces the all-reduce of the weight gradient.  The caller zeroes
+       the replicas beforehand and synchronises the ranks before reading them (parallel.FusedGradReduce does both). */
+    int32_t doe_gh_mode;
     const void* elem_mask;     /* float32 [H,W] or NULL      */
     const void* elem_mul;      /* complex64 [C,H,W] or NULL  */
 } thz_asm_desc;

@@ -54,8 +54,9 @@ def _default_device(device):
 class _DeferredModulation:
     """x * [mask * mul] * p(h), not yet evaluated.  ASM_prop consumes (x, height_map, coef, mask, mul) directly."""
 
-    def __init__(self, x, height_map, coef, rows=None, mask=None, mul=None):
+    def __init__(self, x, height_map, coef, rows=None, mask=None, mul=None, reducer=None):
         self.x, self.height_map, self.coef = x, height_map, coef
+        self.reducer = reducer    # parallel.FusedGradReduce: grad_height summed over the ranks inside the fused adjoint
         self.shape = x.shape
         self.device = x.device
         self.rows = rows          # (lo, hi): x holds only these rows of the grid the height map covers (slab-decomposed fields)
@@ -63,12 +64,30 @@ class _DeferredModulation:
 
     def materialise(self):
         hm = self.height_map if self.rows is None else self.height_map[self.rows[0]:self.rows[1]]
+        if self.reducer is not None:        # not fused after all (the field was read, or the propagator took another route):
+            hm = _SumGradOverRanks.apply(hm, self.reducer.group)        # keep the promise that the gradient arrives summed
         x = self.x
         if self.mask is not None:
             x = Fn.FieldMulFn.apply(x, self.mask)
         if self.mul is not None:
             x = Fn.FieldMulFn.apply(x, self.mul)
         return Fn.DoeModulateFn.apply(x, hm, self.coef)
+
+
+class _SumGradOverRanks(torch.autograd.Function):
+    """Identity whose backward all-reduces (NCCL) the gradient: the unfused twin of parallel.FusedGradReduce."""
+
+    @staticmethod
+    def forward(ctx, h, group):
+        ctx.group = group
+        return h.view_as(h)
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        g = g.contiguous().clone()
+        dist.all_reduce(g, group=ctx.group)
+        return g, None
 
 
 class DOELayer(nn.Module):
@@ -130,7 +149,8 @@ class DOELayer(nn.Module):
         N.require_cuda(x, "field.data")
         coef = self._coef(input_field.wavelengths, epsilon, tand, x.device)
         rows = (slab[0] * input_field.height, (slab[0] + 1) * input_field.height) if slab is not None else None
-        deferred = _DeferredModulation(x, self._height_map_.to(x.device), coef, rows=rows, mask=mask, mul=mul)
+        deferred = _DeferredModulation(x, self._height_map_.to(x.device), coef, rows=rows, mask=mask, mul=mul,
+                                       reducer=getattr(self, "grad_reducer", None) if slab is None else None)
         return ElectricField._from_deferred(deferred, input_field)
 
 

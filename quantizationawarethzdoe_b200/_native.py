@@ -48,7 +48,7 @@ class AsmDesc(ctypes.Structure):
         ("slab_ptrs", ctypes.c_void_p * 8),
         ("tf_row_chunked", ctypes.c_int32), ("reserved2", ctypes.c_int32),
         ("doe_hmap_bstride", ctypes.c_int64),
-        ("elem_mode", ctypes.c_int32), ("reserved3", ctypes.c_int32),
+        ("elem_mode", ctypes.c_int32), ("doe_gh_mode", ctypes.c_int32),
         ("elem_mask", ctypes.c_void_p), ("elem_mul", ctypes.c_void_p),
     ]
 
@@ -222,4 +222,7 @@ def plan_radices(n):
 
 
 def ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    """Device address of a tensor (None -> NULL); an int is taken as a raw address (multicast mappings have no tensor)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(int(t)) if isinstance(t, int) else ctypes.c_void_p(t.data_ptr())

@@ -132,8 +132,8 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
         if (rc == THZ_E_UNSUPPORTED)
             return thz_set_error(rc, "thz_asm_propagate: transform length has a prime factor > 7 (or output row too wide)");
         if (rc != THZ_OK) return thz_set_error(rc, "thz_asm_propagate: line does not fit in shared memory");
-        L.k3.gh_atomic = (d->doe_mode == 2 && (nchunks > 1 || L.k3_gridy > 1)) ? 1 : 0;
-        if ((stages & 4) && L.k3.gh_atomic && !zeroed) {
+        L.k3.gh_atomic = (d->doe_mode == 2 && d->doe_gh_mode == 1) ? 2 : (d->doe_mode == 2 && (nchunks > 1 || L.k3_gridy > 1)) ? 1 : 0;
+        if ((stages & 4) && L.k3.gh_atomic == 1 && !zeroed) {
             cudaError_t e = cudaMemsetAsync(d->doe_gh, 0, (size_t)d->outH * d->outW * sizeof(float), stream);
             if (e != cudaSuccess) return thz_set_cuda_error("cudaMemsetAsync(gh)", e);
             zeroed = true;

@@ -307,7 +307,7 @@ struct RowInvArgs {
     DoeArgs doe;
     const cpx* xsaved;        // [nbc][outH][outW] field that entered the DOE
     float* gh;                // [outH][outW]
-    int gh_atomic;            // 1: several CTAs contribute to one gh element -> atomicAdd
+    int gh_atomic;            // how partial sums reach gh (thz_gh_commit): 0 store, 1 atomicAdd, 2 multimem.red on a multicast address
     ElemArgs elem;            // adjoint passes: gx gets conj(m), the DOE's grad_height sees the saved field times m
     SlabArgs slab;            // parts > 1: gather the input rows from column slabs instead of T
     int half_out;             // 1: the output columns are exactly [Wp/4, 3Wp/4): pruned last stage
@@ -387,8 +387,7 @@ THZ_HD void k3_flush(const RowInvArgs& a, int bx, int tid, int nthreads, const f
         const int r = bx * a.lines + l;
         if (r >= a.outH) break;
         float* g = a.gh + (size_t)r * a.outW + c;
-        if (a.gh_atomic) thz_atomic_add(g, acc[k]);
-        else *g = acc[k];
+        thz_gh_commit(g, acc[k], a.gh_atomic);
     }
 }
 

@@ -42,6 +42,7 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     if ((st & 4) && d->doe_mode == 2 && (!d->doe_xsaved || !d->doe_gh)) return THZ_E_NULL;
     if (d->elem_mode < 0 || d->elem_mode > 2 || (d->elem_mode != 0 && !d->elem_mask && !d->elem_mul)) return THZ_E_SHAPE;
     if (d->elem_mode != 0 && d->slab_parts > 1) return THZ_E_UNSUPPORTED;      // the slab pipeline fuses the DOE only
+    if (d->doe_gh_mode < 0 || d->doe_gh_mode > 1) return THZ_E_SHAPE;
     if (d->doe_hmap_bstride < 0 || (d->doe_hmap_bstride != 0 && d->doe_mode != 1)) return THZ_E_SHAPE;   // per-entry maps: forward only
     if ((st & 4) && d->doe_mode != 2 && !d->y) return THZ_E_NULL;
     if (d->slab_parts > 1) {

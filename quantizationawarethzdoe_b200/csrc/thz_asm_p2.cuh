@@ -745,8 +745,7 @@ THZ_HD void p2k3_flush(const RowInvArgs& a, int bx, int tid, int nt, const float
             const int c = j + t * M - a.out_c0;
             if ((unsigned)c >= (unsigned)a.outW) continue;
             float* g = a.gh + (size_t)r * a.outW + c;
-            if (a.gh_atomic) thz_atomic_add(g, acc[k * R + t]);
-            else *g = acc[k * R + t];
+            thz_gh_commit(g, acc[k * R + t], a.gh_atomic);
         }
     }
 }

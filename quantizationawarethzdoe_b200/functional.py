@@ -80,7 +80,7 @@ class AsmPlan:
         self.tw_w = N.twiddles(Wp, device)
         self._descs = {}
 
-    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None, hmap_bstride=0, elem=None):
+    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None, hmap_bstride=0, elem=None, gh_mode=0):
         """One thz_asm_propagate call.  Forward: x [B,C,H,W] -> y [B,C,outH,outW].
         Adjoint (conj=1): x = grad [B,C,outH,outW] -> y [B,C,H,W] (regions swapped)."""
         B, C = self.B, self.C
@@ -106,6 +106,7 @@ class AsmPlan:
         d.x, d.y, d.ws, d.ws_bytes = N.ptr(x), N.ptr(y), N.ptr(ws), ws.numel() * 8
         d.doe_hmap, d.doe_coef, d.doe_xsaved, d.doe_gh = N.ptr(hmap), N.ptr(coef), N.ptr(xsaved), N.ptr(gh)
         d.doe_hmap_bstride = int(hmap_bstride)
+        d.doe_gh_mode = int(gh_mode)           # 1: gh is an NVLS multicast address, partial sums are added (parallel.FusedGradReduce)
         # pointwise elements in front of the propagation (aperture mask, lens kernel): on load in a forward pass, conjugated in
         # the epilogue of an adjoint pass (thz_asm_desc.elem_*)
         mask, mul = elem if elem is not None else (None, None)
@@ -140,13 +141,14 @@ class DoeAsmFn(torch.autograd.Function):
     """y = ASM(x * p(h)) in one fused pipeline; backward returns grad wrt x (if needed) and wrt h."""
 
     @staticmethod
-    def forward(ctx, x, hmap, plan, coef, mask=None, mul=None):
+    def forward(ctx, x, hmap, plan, coef, mask=None, mul=None, reducer=None):
+        """reducer (parallel.FusedGradReduce or None): grad_height is summed over the data-parallel ranks inside the adjoint."""
         x = _c64(x, "field.data")
         N.require_cuda(hmap, "height_map")
         hmap = hmap.to(torch.float32).contiguous()
         y = torch.empty(x.shape[0], plan.C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
         plan.run(x, y, conj=0, doe_mode=1, hmap=hmap, coef=coef, elem=(mask, mul))
-        ctx.plan, ctx.coef, ctx.elem = plan, coef, (mask, mul)
+        ctx.plan, ctx.coef, ctx.elem, ctx.reducer = plan, coef, (mask, mul), reducer
         ctx.save_for_backward(x, hmap)
         return y
 
@@ -157,7 +159,13 @@ class DoeAsmFn(torch.autograd.Function):
         g = _c64(g, "grad_output")
         need_x, need_h = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gx = torch.empty_like(x) if need_x else None
-        if need_h:
+        if need_h and ctx.reducer is not None:
+            red = ctx.reducer
+            if (red.H, red.W) != (plan.H, plan.W):
+                raise ValueError("FusedGradReduce was built for a %d x %d height map, the DOE is %d x %d" % (red.H, red.W, plan.H, plan.W))
+            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=red.target(), elem=ctx.elem, gh_mode=1)
+            gh = red.finish().clone()       # the replica is recycled two passes later; autograd may keep what it is handed
+        elif need_h:
             gh = torch.empty(plan.H, plan.W, dtype=torch.float32, device=g.device)
             plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=gh, elem=ctx.elem)
         else:
@@ -168,7 +176,7 @@ class DoeAsmFn(torch.autograd.Function):
             N.check(N.lib().thz_doe_modulate_bwd(N.ptr(gtmp), None, N.ptr(hmap), N.ptr(coef), BASE_PLANE_THICKNESS,
                                                  N.ptr(gx), None, x.shape[0], x.shape[1], x.shape[2], x.shape[3],
                                                  N.current_stream_ptr(g.device)), "thz_doe_modulate_bwd")
-        return gx, gh, None, None, None, None
+        return gx, gh, None, None, None, None, None
 
 
 def doe_asm_sweep(x, hmaps, prop, coef, spacing, wavelengths, mask=None, mul=None):

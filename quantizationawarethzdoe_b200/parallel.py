@@ -64,7 +64,7 @@ def shard_rows(field, rank, world):
 def allreduce_gradients(params, group=None, average=False):
     """Sum (or average) .grad of the given parameters over the process group with ONE all-reduce of a
     flat fp32 bucket.  Parameters without a gradient contribute zeros (ranks must agree on the list)."""
-    params = [p for p in params if p.requires_grad]
+    params = [p for p in params if p.requires_grad and not getattr(p, "_thz_grad_is_reduced", False)]
     if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in params])
@@ -80,6 +80,74 @@ def allreduce_gradients(params, group=None, average=False):
         else:
             p.grad.copy_(g)
         off += n
+
+
+class FusedGradReduce:
+    """The data-parallel sum of a DOE's grad_height formed INSIDE the adjoint's last kernel instead of by an all-reduce after it.
+
+    grad_height [H,W] float32 lives in symmetric memory with an NVLS multicast mapping; the row-iFFT epilogue of every rank adds
+    its partial sums to the multicast address (multimem.red, thz_asm_desc.doe_gh_mode = 1), the NVSwitch applies each add to
+    all replicas, and when the kernels of all ranks have finished every rank holds the complete sum -- the transfer rides under
+    the kernel, what remains of the collective is ONE symmetric-memory barrier (~10 us against ~60-100 us for the 16 MiB NCCL
+    all-reduce at 2048^2).  Two buffers alternate: the idle one is zeroed before the barrier of the current step, so a rank
+    that runs ahead into the next step finds every replica clean.
+
+        red = parallel.fuse_gradient_allreduce(doe)        # once; afterwards doe's weight gradient is already the SUM over ranks
+        loss.backward()                                    # no allreduce_gradients for that parameter
+
+    Needs NVLS multicast (NVSwitch systems; `FusedGradReduce.available()`); all ranks must run the same sequence of backward
+    passes.  The weights must be replicated (plain data parallelism): grad_weight = grad_height . dh/dw is then linear in the
+    summed grad_height."""
+
+    @staticmethod
+    def available(device=None):
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            probe = symm.empty(64, dtype=torch.float32, device=dev)
+            return bool(symm.rendezvous(probe, dist.group.WORLD.group_name).multicast_ptr)
+        except Exception:
+            return False
+
+    def __init__(self, H, W, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.H, self.W = int(H), int(W)
+        n = self.H * self.W
+        self.buf = symm.empty(2 * n, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        if not self.hdl.multicast_ptr:
+            raise RuntimeError("FusedGradReduce needs NVLS multicast support (symmetric memory has no multicast mapping here)")
+        self.buf.zero_()
+        self.hdl.barrier()
+        self.views = [self.buf[:n].view(self.H, self.W), self.buf[n:].view(self.H, self.W)]
+        self.mc = [int(self.hdl.multicast_ptr), int(self.hdl.multicast_ptr) + 4 * n]
+        self.cur = 0
+
+    def target(self):
+        """Multicast address the adjoint kernel of THIS backward pass adds into."""
+        return self.mc[self.cur]
+
+    def finish(self):
+        """After the adjoint kernel was enqueued: zero the idle buffer, barrier, return this rank's replica (= the sum)."""
+        out = self.views[self.cur]
+        self.cur ^= 1
+        self.views[self.cur].zero_()
+        self.hdl.barrier()
+        return out
+
+
+def fuse_gradient_allreduce(doe_layer, group=None):
+    """Attach a FusedGradReduce to a DOE layer whose modulation is fused into ASM_prop: its height-map gradient (hence the weight
+    gradient) comes out of backward already summed over the ranks.  `allreduce_gradients` skips such parameters."""
+    H, W = doe_layer.doe_size
+    red = FusedGradReduce(H, W, doe_layer.device, group)
+    doe_layer.grad_reducer = red
+    for p in doe_layer.parameters():
+        p._thz_grad_is_reduced = True
+    return red
 
 
 # ----------------------------------------------------------------------------- slab-decomposed ASM

@@ -136,5 +136,32 @@ dist.all_reduce(e, op=dist.ReduceOp.MAX)
 if rank == 0:
     print("data-parallel grad over %d GPUs vs full batch: %.2e" % (world, e[0]))
 ok &= bool(e.max() < 1e-5)
+
+# ---- the same sum formed inside the adjoint's last kernel (multimem.red over the NVSwitch, parallel.FusedGradReduce) instead of
+# by the NCCL all-reduce after it; also through the unfused fall-back (modulation materialised by reading .data)
+if P.FusedGradReduce.available(dev):
+    g_full = doe.weight_height_map.grad.clone()
+    P.fuse_gradient_allreduce(doe)
+    errs = []
+    for it in range(3):                                   # three passes: both buffers of the double buffer get re-used
+        doe.weight_height_map.grad = None
+        y = asm(doe(P.shard_field(full, rank, world))).data
+        (0.5 * (y.real ** 2 + y.imag ** 2).sum()).backward()
+        P.allreduce_gradients(doe.parameters())           # must be a no-op for the fused parameter
+        errs.append(rel(doe.weight_height_map.grad, g_full))
+    doe.weight_height_map.grad = None
+    f = doe(P.shard_field(full, rank, world))
+    _ = f.data                                            # evaluates the modulation: the propagation can no longer fuse it
+    y = asm(f).data
+    (0.5 * (y.real ** 2 + y.imag ** 2).sum()).backward()
+    errs.append(rel(doe.weight_height_map.grad, g_full))
+    e = torch.tensor(errs, device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("in-kernel gradient sum (multimem.red) over %d GPUs vs full batch: %s; unfused fall-back %.2e"
+              % (world, " ".join("%.2e" % v for v in e[:3].tolist()), e[3]))
+    ok &= bool(e.max() < 1e-5)
+elif rank == 0:
+    print("in-kernel gradient sum: NVLS multicast not available here, skipped")
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
