@@ -160,6 +160,17 @@ typedef struct thz_asm_desc {
     int32_t doe_gh_mode;
     const void* elem_mask;     /* float32 [H,W] or NULL      */
     const void* elem_mul;      /* complex64 [C,H,W] or NULL  */
+    /* Quantised DOEs (level selection fused into the propagation): when the height map takes only `doe_levels` distinct values,
+       h[i,j] = lut[idx[i,j]] (STE / nearest-level / hard Gumbel layers without tolerance noise, Components/QuantizedDOE.py:
+       1239-1253), pass the int32 level map the quantiser kernels emit and the transmission of every level for every wavelength,
+       doe_level_phase[c][l] = p_c(lut[l]) (thz_doe_modulate_fwd on a unit field over the LUT evaluates exactly that).  The
+       static row kernels then LOOK the transmission UP instead of evaluating exp / sincos per pixel and wavelength, forward
+       (doe_mode 1) and adjoint (doe_mode 2); results are bit-identical to the height-map path.  doe_hmap must still be
+       given: every other code path (run-time planned lengths, pointwise elements, per-entry maps, slabs) uses it. */
+    const void* doe_level_idx;     /* int32 [H,W] or NULL */
+    const void* doe_level_phase;   /* complex64 [C][doe_levels] or NULL */
+    int32_t doe_levels;
+    int32_t reserved4;
 } thz_asm_desc;
 
 /* Bytes of `ws` a call with this descriptor needs (uses B, C, inH, outH, Hp, Wp, bc_chunk, stages, slab_parts): one

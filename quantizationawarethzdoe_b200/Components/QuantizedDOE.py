@@ -54,8 +54,10 @@ def _default_device(device):
 class _DeferredModulation:
     """x * [mask * mul] * p(h), not yet evaluated.  ASM_prop consumes (x, height_map, coef, mask, mul) directly."""
 
-    def __init__(self, x, height_map, coef, rows=None, mask=None, mul=None, reducer=None):
+    def __init__(self, x, height_map, coef, rows=None, mask=None, mul=None, reducer=None, levels=None):
         self.x, self.height_map, self.coef = x, height_map, coef
+        self.levels = levels      # (int32 level map, [C,L] level transmissions) of a quantised map: the propagation's row kernels
+                                  # then consume the quantiser's level indices directly (functional.level_phase_table)
         self.reducer = reducer    # parallel.FusedGradReduce: grad_height summed over the ranks inside the fused adjoint
         self.shape = x.shape
         self.device = x.device
@@ -129,8 +131,19 @@ class DOELayer(nn.Module):
         cache["refs"] = (wavelengths, epsilon, tand)
         return cache["coef"]
 
-    def modulate(self, input_field, preprocessed_height_map, height_tolerance, epsilon, tand):
-        """Components/QuantizedDOE.py:92-126, deferred (see module docstring)."""
+    def _level_phase(self, lut, coef):
+        """[C,L] transmissions of the LUT levels for the wavelengths behind `coef`, cached per (coef, lut) object / version."""
+        tok = (id(coef), id(lut), lut._version)
+        cache = self.__dict__.setdefault("_lphase_cache", {})
+        if cache.get("tok") != tok:
+            cache["table"] = Fn.level_phase_table(lut.to(coef.device), coef)
+            cache["tok"] = tok
+            cache["refs"] = (coef, lut)
+        return cache["table"]
+
+    def modulate(self, input_field, preprocessed_height_map, height_tolerance, epsilon, tand, level_index=None, lut=None):
+        """Components/QuantizedDOE.py:92-126, deferred (see module docstring).  level_index / lut: the map is quantised,
+        preprocessed_height_map == lut[level_index] -- handed on so that the fused propagation can look transmissions up."""
         hm = self.add_height_map_noise(preprocessed_height_map, tolerance=height_tolerance)
         # a row slab of a grid distributed over several GPUs (parallel.shard_rows): the map covers the WHOLE grid
         slab = getattr(input_field, "_row_slab", None)
@@ -149,8 +162,12 @@ class DOELayer(nn.Module):
         N.require_cuda(x, "field.data")
         coef = self._coef(input_field.wavelengths, epsilon, tand, x.device)
         rows = (slab[0] * input_field.height, (slab[0] + 1) * input_field.height) if slab is not None else None
+        levels = None
+        if (level_index is not None and lut is not None and height_tolerance is None and slab is None and
+                tuple(level_index.shape) == tuple(self._height_map_.shape) and level_index.dtype == torch.int32):
+            levels = (level_index.to(x.device).contiguous(), self._level_phase(lut, coef))
         deferred = _DeferredModulation(x, self._height_map_.to(x.device), coef, rows=rows, mask=mask, mul=mul,
-                                       reducer=getattr(self, "grad_reducer", None) if slab is None else None)
+                                       reducer=getattr(self, "grad_reducer", None) if slab is None else None, levels=levels)
         return ElectricField._from_deferred(deferred, input_field)
 
 
@@ -270,8 +287,9 @@ class STEQuantizedDOELayer(DOELayer):
         return self.height_map
 
     def forward(self, field, iter_frac=None):
-        return self.modulate(input_field=field, preprocessed_height_map=self.preprocessed_height_map(),
-                             height_tolerance=self.tolerance, epsilon=self.epsilon, tand=self.tand)
+        hm = self.preprocessed_height_map()
+        return self.modulate(input_field=field, preprocessed_height_map=hm, height_tolerance=self.tolerance, epsilon=self.epsilon,
+                             tand=self.tand, level_index=self.level_index, lut=self.lut)
 
 
 class PSQuantizedDOELayer(DOELayer):

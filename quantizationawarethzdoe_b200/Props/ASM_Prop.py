@@ -262,7 +262,7 @@ class ASM_prop(nn.Module):
             out = Fn.AsmPropagateFn.apply(deferred.x, plan, deferred.mask, deferred.mul)
         elif deferred is not None:                                                  # [aperture / lens +] DOE: fused on load
             out = Fn.DoeAsmFn.apply(deferred.x, deferred.height_map, plan, deferred.coef, deferred.mask, deferred.mul,
-                                    getattr(deferred, "reducer", None))
+                                    getattr(deferred, "reducer", None), getattr(deferred, "levels", None))
         else:
             out = Fn.AsmPropagateFn.apply(data, plan)
         return ElectricField(data=out, wavelengths=wavelengths, spacing=field.spacing, device=dev)

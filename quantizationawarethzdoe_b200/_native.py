@@ -50,6 +50,8 @@ class AsmDesc(ctypes.Structure):
         ("doe_hmap_bstride", ctypes.c_int64),
         ("elem_mode", ctypes.c_int32), ("doe_gh_mode", ctypes.c_int32),
         ("elem_mask", ctypes.c_void_p), ("elem_mul", ctypes.c_void_p),
+        ("doe_level_idx", ctypes.c_void_p), ("doe_level_phase", ctypes.c_void_p),
+        ("doe_levels", ctypes.c_int32), ("reserved4", ctypes.c_int32),
     ]
 
 

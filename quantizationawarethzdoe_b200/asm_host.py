@@ -355,7 +355,8 @@ def doe_coefficients(wavelengths, epsilon, tand):
 
 def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, out_c0, tf_mode, tf_conj,
                rowvec, colvec, scal, table, doe_mode, doe_base, hmap, coef, xsaved, gh, tw_h, tw_w, ws,
-               bc_chunk=0, tune_k2_cols=0, tune_lines=0, stages=0, slab=None, tf_row_chunked=0, elem_mode=0, elem_mask=None, elem_mul=None):
+               bc_chunk=0, tune_k2_cols=0, tune_lines=0, stages=0, slab=None, tf_row_chunked=0, elem_mode=0, elem_mask=None, elem_mul=None,
+               level_idx=None, level_phase=None):
     """Fill a thz_asm_desc from tensors (device or, in the CPU replay tests, host tensors)."""
     d = N.AsmDesc()
     d.B, d.C, d.inH, d.inW, d.Hp, d.Wp = B, C, inH, inW, Hp, Wp
@@ -370,6 +371,8 @@ def build_desc(x, y, B, C, inH, inW, Hp, Wp, in_r0, in_c0, outH, outW, out_r0, o
     d.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
     d.tf_row_chunked = int(tf_row_chunked)
     d.elem_mode, d.elem_mask, d.elem_mul = int(elem_mode), N.ptr(elem_mask), N.ptr(elem_mul)
+    d.doe_level_idx, d.doe_level_phase = N.ptr(level_idx), N.ptr(level_phase)
+    d.doe_levels = int(level_phase.shape[-1]) if level_phase is not None else 0
     if slab is not None:          # (parts, row0, rows, [pointer of every rank's column slab][, blocked]); see thz_asm_desc.slab_*
         d.slab_parts, d.slab_row0, d.slab_rows = int(slab[0]), int(slab[1]), int(slab[2])
         d.slab_blocked = int(slab[4]) if len(slab) > 4 else 0

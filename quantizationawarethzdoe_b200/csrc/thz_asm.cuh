@@ -32,6 +32,8 @@ struct DoeArgs {
     int b0;                   // batch entry of the chunk's first field (f0 / C)
     long long hstride;        // 0: one map for every batch entry; else floats between the maps of consecutive batch entries
                               // (forward only: a sweep of DOE candidates over one input field)
+    const cpx* lphase;        // quantised DOE, static row kernels: [C][nlev] transmission of every level; hmap then points at the
+    int nlev;                 //   int32 LEVEL INDEX map (same 4-byte elements) and the kernels look p up instead of evaluating it
 };
 // Fixed pointwise optical elements in front of the (DOE +) propagation -- aperture masks and thin-lens kernels
 // (Components/Aperture.py:105-135, Components/Thin_Lens.py:31-85) -- folded into the row-FFT prologue (forward:

@@ -43,6 +43,7 @@ static inline int thz_asm_validate(const thz_asm_desc* d) {
     if (d->elem_mode < 0 || d->elem_mode > 2 || (d->elem_mode != 0 && !d->elem_mask && !d->elem_mul)) return THZ_E_SHAPE;
     if (d->elem_mode != 0 && d->slab_parts > 1) return THZ_E_UNSUPPORTED;      // the slab pipeline fuses the DOE only
     if (d->doe_gh_mode < 0 || d->doe_gh_mode > 1) return THZ_E_SHAPE;
+    if (d->doe_levels < 0 || (d->doe_levels > 0 && (!d->doe_level_idx) != (!d->doe_level_phase))) return THZ_E_SHAPE;
     if (d->doe_hmap_bstride < 0 || (d->doe_hmap_bstride != 0 && d->doe_mode != 1)) return THZ_E_SHAPE;   // per-entry maps: forward only
     if ((st & 4) && d->doe_mode != 2 && !d->y) return THZ_E_NULL;
     if (d->slab_parts > 1) {
@@ -189,6 +190,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a1.doe.base = d->doe_base;
     a1.doe.b0 = f0 / d->C;
     a1.doe.hstride = d->doe_mode == 1 ? d->doe_hmap_bstride : 0;
+    a1.doe.lphase = nullptr;
+    a1.doe.nlev = 0;
     a1.elem.mask = d->elem_mode == 1 ? (const float*)d->elem_mask : nullptr;
     a1.elem.mul = d->elem_mode == 1 ? (const cpx*)d->elem_mul : nullptr;
     a1.conj_in = 0;
@@ -277,6 +280,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     a3.doe.base = d->doe_base;
     a3.doe.b0 = 0;
     a3.doe.hstride = 0;
+    a3.doe.lphase = nullptr;
+    a3.doe.nlev = 0;
     a3.elem.mask = d->elem_mode == 2 ? (const float*)d->elem_mask : nullptr;
     a3.elem.mul = d->elem_mode == 2 ? (const cpx*)d->elem_mul : nullptr;
     a3.xsaved = d->doe_mode == 2 ? (const cpx*)d->doe_xsaved + (size_t)f0 * d->outH * d->outW : nullptr;
@@ -305,6 +310,15 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k3_smem = lines * line_bytes_w;
     }
     thz_asm_apply_p2(d, nbc, sm_count, L);
+    // quantised DOE through the static row kernels: the level-index map takes the place of the height map and the transmission
+    // of every level comes from a [C][levels] table (thz_asm_desc.doe_level_*; THZ_NO_DOE_LUT=1: evaluate per pixel as before)
+    if (L->p2_w && d->doe_mode != 0 && d->doe_level_idx && d->doe_level_phase && d->doe_levels > 0 && d->elem_mode == 0 &&
+        d->doe_hmap_bstride == 0 && d->slab_parts <= 1 && !thz_env_is_1("THZ_NO_DOE_LUT")) {
+        DoeArgs& dd = d->doe_mode == 1 ? L->k1.doe : L->k3.doe;
+        dd.hmap = (const float*)d->doe_level_idx;
+        dd.lphase = (const cpx*)d->doe_level_phase;
+        dd.nlev = d->doe_levels;
+    }
     {
         // blocked intermediate between the static kernels of a whole-pipeline run (THZ_NO_TILED=1 keeps row-major T)
         int tiled = thz_asm_two_buffers(d) ? 2 : 0, tiled2 = 0;

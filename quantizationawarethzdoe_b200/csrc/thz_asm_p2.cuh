@@ -50,58 +50,65 @@ THZ_HD constexpr int p2_pitch(int N) { return N + (N >> 4); }
 THZ_HD constexpr bool p2_row_pipelined(int N) { return N <= 8192; }
 
 // =============================================================================== K1<N>
-template <bool ELEM>    // ELEM: pointwise elements in front (separate kernel instantiation: the common case pays nothing)
+// MODE of the row kernels (separate instantiations: the common case pays nothing for the others):
+//   0 plain / DOE transmission evaluated per pixel;  1 pointwise elements in front (aperture mask, lens kernel);
+//   2 quantised DOE: the staged "height" row holds int32 level indices and the transmission comes from a [C][levels] table
+template <int MODE>
 struct K1Loader {
     const cpx* xr;      // row of x (NULL: line beyond the end of the batch)
     const float* hr;    // row of the height map (NULL: no DOE)
     const float* mr;    // row of the aperture mask (NULL: none)
     const cpx* kr;      // row of this wavelength's lens kernel (NULL: none)
+    const cpx* lut;     // MODE 2: this wavelength's level transmissions
     float4 cf;
     float base;
     int in_c0, inW, conj_in;
     THZ_HD cpx elem(cpx v, int c) const {
-        if constexpr (ELEM) {
+        if constexpr (MODE == 1) {
             if (mr) v = cscale(v, thz_ldg(mr + c));
             if (kr) v = cmul(v, thz_ldg(kr + c));
         }
         return v;
+    }
+    THZ_HD cpx doe(cpx v, int c) const {
+        if (!hr) return v;
+        if constexpr (MODE == 2) return cmul(v, thz_ldg(lut + thz_float_bits(hr[c])));
+        else return cmul(v, thz_doe_phase(hr[c], cf, base));
     }
     THZ_HD cpx operator()(int pos) const {
         const int c = pos - in_c0;
         if (xr == nullptr || (unsigned)c >= (unsigned)inW) return cmake(0.f, 0.f);   // one compare: c < 0 wraps
         cpx v = xr[c];
         if (conj_in) v.y = -v.y;
-        v = elem(v, c);
-        if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
-        return v;
+        return doe(elem(v, c), c);
     }
     THZ_HD cpx live(int pos) const {             // pos known to be inside [in_c0, in_c0 + inW)
         if (xr == nullptr) return cmake(0.f, 0.f);
         const int c = pos - in_c0;
         cpx v = xr[c];
         if (conj_in) v.y = -v.y;
-        v = elem(v, c);
-        if (hr) v = cmul(v, thz_doe_phase(hr[c], cf, base));
-        return v;
+        return doe(elem(v, c), c);
     }
 };
 // rows of the pointwise elements for line gl of a row kernel's chunk (field f = gl / inH, row r)
-template <bool ELEM>
-THZ_HD void p2k1_elem_rows(const RowFwdArgs& a, K1Loader<ELEM>& ld, int f, int r) {
-    if constexpr (ELEM) {
+template <int MODE>
+THZ_HD void p2k1_elem_rows(const RowFwdArgs& a, K1Loader<MODE>& ld, int f, int r) {
+    if constexpr (MODE == 2) ld.lut = a.doe.lphase + (size_t)((a.c0 + f) % a.C) * a.doe.nlev;
+    if constexpr (MODE == 1) {
         ld.mr = a.elem.mask ? a.elem.mask + (size_t)r * a.inW : nullptr;
         ld.kr = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.inH + r) * a.inW : nullptr;
     }
 }
 
-template <int N, bool ELEM = false>
+template <int N, int MODE = 0>
 THZ_HD void p2k1_first(const RowFwdArgs& a, cpx* s, int bx, int tid, int nt) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N);
     const int total_lines = a.nbc * a.inH;
     for (int w = tid; w < LINES * NB; w += nt) {
         const int line = w / NB, j = w % NB;
         const int gl = bx * LINES + line;
-        K1Loader<ELEM> ld;
+        K1Loader<MODE> ld;
+        ld.lut = nullptr;
         ld.xr = nullptr;
         ld.hr = nullptr;
         ld.mr = nullptr;
@@ -154,14 +161,15 @@ THZ_HD void p2k1_prefetch(const RowFwdArgs& a, cpx* xs, float* hs, int grp, int 
     }
 }
 
-template <int N, bool ELEM = false>
+template <int N, int MODE = 0>
 THZ_HD void p2k1_first_staged(const RowFwdArgs& a, cpx* s, const cpx* xs, const float* hs, int grp, int tid, int nt) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N);
     const int total_lines = a.nbc * a.inH;
     for (int w = tid; w < LINES * NB; w += nt) {
         const int line = w / NB, j = w % NB;
         const int gl = grp * LINES + line;
-        K1Loader<ELEM> ld;
+        K1Loader<MODE> ld;
+        ld.lut = nullptr;
         ld.xr = nullptr;
         ld.hr = nullptr;
         ld.mr = nullptr;
@@ -596,7 +604,7 @@ THZ_HD constexpr int p2k3_acc() {
     return ((p2_row_lines(N) * P2Stage<N, 0>::NB + p2_row_threads(N) - 1) / p2_row_threads(N)) * P2Stage<N, 0>::R;
 }
 
-template <int PF_, bool ELEM = false>
+template <int PF_, int MODE = 0>
 struct K3Storer {
     static constexpr int PF = PF_;   // epilogue loads (saved field, height map) run this many outputs ahead
     cpx* yrow;            // output row (forward output or grad wrt field; may be NULL in DOE mode)
@@ -604,6 +612,7 @@ struct K3Storer {
     const float* hrow;    // height-map row (DOE mode; NULL = plain forward)
     const float* mrow;    // aperture-mask row (adjoint of pointwise elements; NULL: none)
     const cpx* krow;      // lens-kernel row of this wavelength (NULL: none)
+    const cpx* lut;       // MODE 2: this wavelength's level transmissions (hrow then holds int32 level indices)
     float4 cf;
     cpx gamma;
     float base, scale;
@@ -632,7 +641,7 @@ struct K3Storer {
         emit(c, t, t, v);
     }
     THZ_HD cpx elem(cpx v, int c, bool conj) const {     // pointwise elements in front of the DOE (thz_elem_apply per row)
-        if constexpr (ELEM) {
+        if constexpr (MODE == 1) {
             if (mrow) v = cscale(v, thz_ldg(mrow + c));
             if (krow) {
                 const cpx m = thz_ldg(krow + c);
@@ -647,7 +656,9 @@ struct K3Storer {
             yrow[c] = elem(v, c, true);            // plain output, or the adjoint of pointwise elements alone
             return;
         }
-        const cpx p = thz_doe_phase(hq[slot % PF], cf, base);
+        cpx p;
+        if constexpr (MODE == 2) p = thz_ldg(lut + thz_float_bits(hq[slot % PF]));
+        else p = thz_doe_phase(hq[slot % PF], cf, base);
         const cpx q = cmulc(v, p);                 // grad wrt the field that entered the DOE (= x m)
         if (yrow) yrow[c] = elem(q, c, true);      // grad wrt x: conj(m) on top
         // gh += Re(conj(v) (x m) p gamma) = Re(conj(q) (x m) gamma)
@@ -692,12 +703,14 @@ THZ_HD void p2k3_prefetch_epilogue(const RowInvArgs& a, int bx, int f, int tid, 
 }
 
 // inverse stage 0 + crop + scale + epilogue for field f; acc has p2k3_acc<N>() entries
-template <int N, int NACC, bool ELEM = false>
+template <int N, int NACC, int MODE = 0>
 THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, int f, int tid, int nt, float (&acc)[NACC]) {
     constexpr int LINES = p2_row_lines(N), NB = P2Stage<N, 0>::NB, PITCH = p2_pitch(N), R = P2Stage<N, 0>::R;
-    K3Storer<(R <= 16 ? 4 : 1), ELEM> st;     // radix-25 butterflies have no registers to spare for a deeper ring
+    K3Storer<(R <= 16 ? 4 : 1), MODE> st;     // radix-25 butterflies have no registers to spare for a deeper ring
     st.cf = cmake4(0.f);
     st.gamma = cmake(0.f, 0.f);
+    st.lut = nullptr;
+    if constexpr (MODE == 2) st.lut = a.doe.lphase + (size_t)((a.c0 + f) % a.C) * a.doe.nlev;
     if (a.doe.hmap) {
         st.cf = thz_ldg(a.doe.coef + (a.c0 + f) % a.C);
         st.gamma = cmake(-st.cf.x * (0.5f * st.cf.y * st.cf.z), -st.cf.x * st.cf.w);
@@ -718,7 +731,7 @@ THZ_HD void p2k3_last(const RowInvArgs& a, const cpx* s, const cpx* tw, int bx, 
         st.yrow = a.y ? a.y + o : nullptr;
         st.xrow = a.xsaved ? a.xsaved + o : nullptr;
         st.hrow = a.doe.hmap ? a.doe.hmap + (size_t)r * a.outW : nullptr;
-        if constexpr (ELEM) {
+        if constexpr (MODE == 1) {
             st.mrow = a.elem.mask ? a.elem.mask + (size_t)r * a.outW : nullptr;
             st.krow = a.elem.mul ? a.elem.mul + ((size_t)((a.c0 + f) % a.C) * a.outH + r) * a.outW : nullptr;
         }

@@ -80,7 +80,8 @@ class AsmPlan:
         self.tw_w = N.twiddles(Wp, device)
         self._descs = {}
 
-    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None, hmap_bstride=0, elem=None, gh_mode=0):
+    def run(self, x, y, conj, doe_mode=0, hmap=None, coef=None, xsaved=None, gh=None, hmap_bstride=0, elem=None, gh_mode=0,
+            levels=None):
         """One thz_asm_propagate call.  Forward: x [B,C,H,W] -> y [B,C,outH,outW].
         Adjoint (conj=1): x = grad [B,C,outH,outW] -> y [B,C,H,W] (regions swapped)."""
         B, C = self.B, self.C
@@ -107,6 +108,11 @@ class AsmPlan:
         d.doe_hmap, d.doe_coef, d.doe_xsaved, d.doe_gh = N.ptr(hmap), N.ptr(coef), N.ptr(xsaved), N.ptr(gh)
         d.doe_hmap_bstride = int(hmap_bstride)
         d.doe_gh_mode = int(gh_mode)           # 1: gh is an NVLS multicast address, partial sums are added (parallel.FusedGradReduce)
+        # quantised DOE: (int32 level map [H,W], complex64 per-level transmissions [C,L]) -- the static row kernels look the
+        # transmission up instead of evaluating it per pixel and wavelength (thz_asm_desc.doe_level_*); same results
+        lidx, lphase = levels if levels is not None else (None, None)
+        d.doe_level_idx, d.doe_level_phase = N.ptr(lidx), N.ptr(lphase)
+        d.doe_levels = int(lphase.shape[-1]) if lphase is not None else 0
         # pointwise elements in front of the propagation (aperture mask, lens kernel): on load in a forward pass, conjugated in
         # the epilogue of an adjoint pass (thz_asm_desc.elem_*)
         mask, mul = elem if elem is not None else (None, None)
@@ -141,14 +147,16 @@ class DoeAsmFn(torch.autograd.Function):
     """y = ASM(x * p(h)) in one fused pipeline; backward returns grad wrt x (if needed) and wrt h."""
 
     @staticmethod
-    def forward(ctx, x, hmap, plan, coef, mask=None, mul=None, reducer=None):
-        """reducer (parallel.FusedGradReduce or None): grad_height is summed over the data-parallel ranks inside the adjoint."""
+    def forward(ctx, x, hmap, plan, coef, mask=None, mul=None, reducer=None, levels=None):
+        """reducer (parallel.FusedGradReduce or None): grad_height is summed over the data-parallel ranks inside the adjoint.
+        levels (level map int32 [H,W], per-level transmissions complex64 [C,L]) or None: the height map is quantised, hmap =
+        lut[level map] -- the row kernels then consume the quantiser's level indices directly (level_phase_table)."""
         x = _c64(x, "field.data")
         N.require_cuda(hmap, "height_map")
         hmap = hmap.to(torch.float32).contiguous()
         y = torch.empty(x.shape[0], plan.C, plan.outH, plan.outW, dtype=torch.complex64, device=x.device)
-        plan.run(x, y, conj=0, doe_mode=1, hmap=hmap, coef=coef, elem=(mask, mul))
-        ctx.plan, ctx.coef, ctx.elem, ctx.reducer = plan, coef, (mask, mul), reducer
+        plan.run(x, y, conj=0, doe_mode=1, hmap=hmap, coef=coef, elem=(mask, mul), levels=levels)
+        ctx.plan, ctx.coef, ctx.elem, ctx.reducer, ctx.levels = plan, coef, (mask, mul), reducer, levels
         ctx.save_for_backward(x, hmap)
         return y
 
@@ -163,11 +171,12 @@ class DoeAsmFn(torch.autograd.Function):
             red = ctx.reducer
             if (red.H, red.W) != (plan.H, plan.W):
                 raise ValueError("FusedGradReduce was built for a %d x %d height map, the DOE is %d x %d" % (red.H, red.W, plan.H, plan.W))
-            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=red.target(), elem=ctx.elem, gh_mode=1)
+            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=red.target(), elem=ctx.elem, gh_mode=1,
+                     levels=ctx.levels)
             gh = red.finish().clone()       # the replica is recycled two passes later; autograd may keep what it is handed
         elif need_h:
             gh = torch.empty(plan.H, plan.W, dtype=torch.float32, device=g.device)
-            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=gh, elem=ctx.elem)
+            plan.run(g, gx, conj=1, doe_mode=2, hmap=hmap, coef=coef, xsaved=x, gh=gh, elem=ctx.elem, levels=ctx.levels)
         else:
             gh = None
             # grad wrt x only: adjoint ASM (conj(m) of the pointwise elements in its epilogue), then the conj(p) multiply
@@ -176,7 +185,19 @@ class DoeAsmFn(torch.autograd.Function):
             N.check(N.lib().thz_doe_modulate_bwd(N.ptr(gtmp), None, N.ptr(hmap), N.ptr(coef), BASE_PLANE_THICKNESS,
                                                  N.ptr(gx), None, x.shape[0], x.shape[1], x.shape[2], x.shape[3],
                                                  N.current_stream_ptr(g.device)), "thz_doe_modulate_bwd")
-        return gx, gh, None, None, None, None, None
+        return gx, gh, None, None, None, None, None, None
+
+
+def level_phase_table(lut, coef):
+    """Transmission of every level for every wavelength, complex64 [C, L] = p_c(lut[l]): the modulation kernel itself on a unit
+    field over the LUT, hence bit-identical to what the fused prologue evaluates per pixel."""
+    lut = lut.detach().to(torch.float32).reshape(1, -1).contiguous()
+    C, L = coef.shape[0], lut.shape[1]
+    ones = torch.ones(1, C, 1, L, dtype=torch.complex64, device=lut.device)
+    out = torch.empty_like(ones)
+    N.check(N.lib().thz_doe_modulate_fwd(N.ptr(ones), N.ptr(out), N.ptr(lut), N.ptr(coef), BASE_PLANE_THICKNESS, 1, C, 1, L,
+                                         N.current_stream_ptr(lut.device)), "thz_doe_modulate_fwd")
+    return out.reshape(C, L)
 
 
 def doe_asm_sweep(x, hmaps, prop, coef, spacing, wavelengths, mask=None, mul=None):

@@ -128,7 +128,8 @@ static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
         int grp = bx;
         if constexpr (!p2_row_pipelined(N)) {
             for (; grp < ngroups; grp += g) {
-                for_threads(nt, [&](int t) { p2k1_first<N, true>(a, s, grp, t, nt); });
+                if (a.doe.lphase) for_threads(nt, [&](int t) { p2k1_first<N, 2>(a, s, grp, t, nt); });
+                else for_threads(nt, [&](int t) { p2k1_first<N, 1>(a, s, grp, t, nt); });
                 e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, tws.data());
                 for_threads(nt, [&](int t) { p2k1_store<N>(a, s, grp, t, nt); });
             }
@@ -137,7 +138,8 @@ static void run_p2_k1(const RowFwdArgs& a, int grid, int nt, size_t smem) {
         if (grp < ngroups) for_threads(nt, [&](int t) { p2k1_prefetch<N>(a, xs, hs, grp, t, nt); });
         for (; grp < ngroups; grp += g) {
             // the replay copies synchronously, so the "next" prefetch must not clobber the staging buffer before it is consumed
-            for_threads(nt, [&](int t) { p2k1_first_staged<N, true>(a, s, xs, hs, grp, t, nt); });
+            if (a.doe.lphase) for_threads(nt, [&](int t) { p2k1_first_staged<N, 2>(a, s, xs, hs, grp, t, nt); });
+            else for_threads(nt, [&](int t) { p2k1_first_staged<N, 1>(a, s, xs, hs, grp, t, nt); });
             if (grp + g < ngroups) for_threads(nt, [&](int t) { p2k1_prefetch<N>(a, xs, hs, grp + g, t, nt); });
             e_fwd_rows<N, 1, p2_stages(N), LINES>(s, nt, tws.data());
             for_threads(nt, [&](int t) { p2k1_store<N>(a, s, grp, t, nt); });
@@ -191,7 +193,8 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
                 for (int f = f_lo; f < f_hi; ++f) {
                     for_threads(nt, [&](int t) { p2k3_load<N>(a, s, bx, f, t, nt); });
                     e_inv_rows<N, p2_stages(N) - 1, 1, LINES>(s, nt, tws.data());
-                    for_threads(nt, [&](int t) { p2k3_last<N, NACC, true>(a, s, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                    if (a.doe.lphase) for_threads(nt, [&](int t) { p2k3_last<N, NACC, 2>(a, s, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                    else for_threads(nt, [&](int t) { p2k3_last<N, NACC, 1>(a, s, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
                 }
                 for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
                 continue;
@@ -204,7 +207,8 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
                 e_inv_rows<N, p2_stages(N) - 1, p2_stages(N) - 1, LINES>(sc, nt, tws.data());
                 if (f + 1 < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s + (cur ^ 1) * BUF, bx, f + 1, t, nt, 1, 2); });
                 e_inv_rows<N, p2_stages(N) - 2, 1, LINES>(sc, nt, tws.data());
-                for_threads(nt, [&](int t) { p2k3_last<N, NACC, true>(a, sc, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                if (a.doe.lphase) for_threads(nt, [&](int t) { p2k3_last<N, NACC, 2>(a, sc, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                else for_threads(nt, [&](int t) { p2k3_last<N, NACC, 1>(a, sc, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
             }
             for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
         }

@@ -37,8 +37,8 @@ def test_library_exports_every_declared_symbol(lib):
 def test_descriptor_layout_matches_header(tmp_path):
     """ctypes mirrors vs the C header: sizes and field offsets as gcc lays the structs out."""
     # thz_asm_desc: 12 int32, 2 ptr, 2 int32, 4 ptr, int32+float, 4 ptr, 2 ptr, ptr, u64, 4 int32, 4 int32, 8 ptr
-    assert ctypes.sizeof(N.AsmDesc) == 12 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 4 * 4 + 4 * 4 + 8 * 8 + 2 * 4 + 8 + 2 * 4 + 2 * 8
-    fields = ["x", "tf_mode", "tf_table", "doe_base", "doe_gh", "ws_bytes", "stages", "slab_parts", "slab_ptrs", "tf_row_chunked", "doe_hmap_bstride", "elem_mode", "elem_mul"]
+    assert ctypes.sizeof(N.AsmDesc) == 12 * 4 + 2 * 8 + 2 * 4 + 4 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 4 * 4 + 4 * 4 + 8 * 8 + 2 * 4 + 8 + 2 * 4 + 2 * 8 + 2 * 8 + 2 * 4
+    fields = ["x", "tf_mode", "tf_table", "doe_base", "doe_gh", "ws_bytes", "stages", "slab_parts", "slab_ptrs", "tf_row_chunked", "doe_hmap_bstride", "elem_mode", "elem_mul", "doe_level_idx", "doe_levels"]
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "thzdoe.h"\nint main(void) {\n'
                    '  printf("%zu %zu", sizeof(thz_asm_desc), sizeof(thz_toeplitz_gemm_desc));\n' +

@@ -542,3 +542,38 @@ def test_long_chirp_convolution_uses_the_split(monkeypatch):
     plan = BL.BluesteinFft2(13, 47, False, False, torch.device("cpu"))
     assert isinstance(plan.conv.plan, LL.SplitAsmPlan) and (plan.conv.plan.Pr, plan.conv.plan.Pc) == (1, 2)
     assert rel_l2(plan(x), torch.fft.fft2(x)) < 3e-6
+
+
+@pytest.mark.parametrize("B,C,H,W,sm,chunk", [(2, 3, 128, 256, 148, 0),      # static row kernels, 256 x 512 canvas
+                                              (3, 2, 128, 256, 2, 4),        # few SMs + chunks (atomic grad_height)
+                                              (3, 1, 200, 200, 148, 0),      # 400-point lines, several per CTA
+                                              (2, 2, 48, 40, 148, 0)])       # run-time planned lengths: the tables are ignored
+def test_quantised_doe_level_tables_equal_per_pixel_evaluation(B, C, H, W, sm, chunk):
+    """Quantised height map h = lut[idx]: handing the row kernels the level map + per-level transmissions (thz_asm_desc.doe_level_*)
+    gives what evaluating the transmission per pixel gives, forward and adjoint (replayed kernel bodies)."""
+    lams = [1e-3, 1.02e-3, 1.05e-3][:C]
+    dxy, z, eps, tand = 0.5e-3, 0.1, 2.66, 0.003
+    torch.manual_seed(0)
+    x = torch.randn(B, C, H, W, dtype=torch.complex64)
+    g = torch.randn(B, C, H, W, dtype=torch.complex64)
+    lut = torch.linspace(0, 1e-3, 5)[:-1].contiguous()
+    idx = torch.randint(0, 4, (H, W), dtype=torch.int32)
+    h = lut[idx.long()].contiguous()
+    coef = AH.doe_coefficients(lams, eps, tand)
+    # per-level transmissions through the replayed fused prologue itself: a 1 x 4 "field" of ones over the LUT as height map
+    lphase = DO.modulate(torch.ones(1, C, 1, 4, dtype=torch.complex64), lut.reshape(1, 4), lams, eps, tand).reshape(C, 4).contiguous()
+    base, _ = _setup(B, C, H, W, None, lams, dxy, z, mode=1, chunk=chunk)
+    outs = []
+    for lev in (False, True):
+        kw = dict(level_idx=idx, level_phase=lphase) if lev else {}
+        y = torch.zeros_like(x)
+        _run(x, dict(base, x=x, y=y, doe_mode=1, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef, **kw), sm)
+        gx, gh = torch.zeros_like(x), torch.full((H, W), 7.0)
+        _run(g, dict(base, x=g, y=gx, tf_conj=1, doe_mode=2, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef, xsaved=x, gh=gh, **kw), sm)
+        outs.append((y, gx, gh))
+    for a, b in zip(*outs):
+        assert rel_l2(b, a) < 1e-6            # the oracle's torch exp / sincos vs the kernels' own: a few 1e-7
+    if H == 48:
+        assert all(torch.equal(a, b) for a, b in zip(*outs))      # tables not used off the static path: identical
+    else:
+        assert not torch.equal(outs[0][0], outs[1][0])            # ... and used on it (the table came from another evaluation)

@@ -412,6 +412,37 @@ def test_level_indices_bit_exact_given_identical_inputs(dev):
     assert nearest_idx(n["kat_x"].to(dev), n["mid"]).tolist() == [0, 0, 0, 1, 1, 1, 2, 3, 0, 0, 0, 0]
 
 
+@pytest.mark.parametrize("n,C,levels", [(512, 3, 4), (2048, 2, 4), (200, 1, 8), (1000, 1, 8)])
+def test_level_tables_are_bit_identical_to_per_pixel_transmission(n, C, levels, dev):
+    """Level selection fused into the propagation (north_star (3)): an STE layer hands ASM_prop its int32 level map and the
+    [C, L] transmissions of the levels; the static row kernels look p up instead of evaluating exp / sincos per pixel and
+    wavelength.  Same numbers, bit for bit, for the field and the input gradient; the weight gradient to summation order."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, STEQuantizedDOELayer
+    lams = [1 * mm * (1 + 0.02 * c) for c in range(C)]
+    torch.manual_seed(0)
+    x = torch.randn(2, C, n, n, dtype=torch.complex64, device=dev)
+    torch.manual_seed(1)
+    doe = STEQuantizedDOELayer(dict(doe_size=[n, n], doe_dxy=0.5 * mm, doe_level=levels, height_constraint_max=1 * mm, tolerance=None,
+                                    material=[2.66, 0.003]), {}, device=dev)
+    asm = ASM_prop(z_distance=0.1, device=dev)
+    asm.check_Zc = False
+    res = []
+    for use_tables in (True, False):
+        xd = x.clone().requires_grad_(True)
+        f = doe(ElectricField(xd, wavelengths=lams, spacing=0.5 * mm, device=dev))
+        lev = f._deferred.levels
+        assert lev is not None and lev[0].dtype == torch.int32 and tuple(lev[1].shape) == (C, levels)
+        assert torch.equal(doe.lut[lev[0].long()], doe.height_map)            # the map IS lut[level map]
+        if not use_tables:
+            f._deferred.levels = None
+        y = asm(f).data
+        gx, gw = torch.autograd.grad(y, (xd, doe.weight_height_map), y.detach())
+        res.append((y.detach(), gx, gw))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    # grad_height is accumulated with atomics when the fields of a row are split over several CTAs: same terms, any order
+    assert rel_l2(res[0][2], res[1][2]) < 1e-6
+
+
 @pytest.mark.parametrize("name", ["gumbel_hard", "gumbel_soft", "plain_hard", "plain_soft"])
 def test_softmax_quantization_matches_reference(name, dev):
     """Quantization(method='*softmax*' | '*gumbel*') -> SoftmaxBasedQuantization + score_thickness
