@@ -7,9 +7,9 @@ grep "^{" $S/final_bench_reference.json > profiles/r02_bench_reference.json
 cp $S/final_launches.csv profiles/r02_final_launches.csv
 cp $S/final_parity_errors.jsonl profiles/r02_parity_errors.jsonl
 cp $S/final_pytest_gpu.log profiles/r02_pytest_gpu.log
-ncu -i $S/prof_r02_final.ncu-rep --page raw --csv > /tmp/r02_final_raw.csv 2>/dev/null
+cp $S/final_ncu_raw.csv /tmp/r02_final_raw.csv
 python tools/ncu_summary.py /tmp/r02_final_raw.csv > profiles/r02_final_ncu_summary.txt
-ncu -i $S/prof_r02_final.ncu-rep --page source --csv > /tmp/r02_final_src.csv 2>/dev/null || true
+gunzip -c $S/final_ncu_source.csv.gz > /tmp/r02_final_src.csv
 python tools/sass_mix.py /tmp/r02_final_src.csv thz_p2_k2f > profiles/r02_final_k2f_sass_mix.txt 2>/dev/null || true
 (python tools/sass_mix.py /tmp/r02_final_src.csv thz_p2_k1; python tools/sass_mix.py /tmp/r02_final_src.csv thz_p2_k3) > profiles/r02_final_k1_k3_sass_mix.txt 2>/dev/null || true
 python - <<'PY'
@@ -23,7 +23,7 @@ for r in rows[2:]:
             return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[u]
         json.dump({"kernel": "thz_p2_k2f<4096,0>", "fields_per_launch": 16, "dram_bytes_read": gb('dram__bytes_read.sum'),
                    "dram_bytes_write": gb('dram__bytes_write.sum'),
-                   "source": "gpurun_out/r02/prof_r02_final.ncu-rep (ncu --set full --clock-control none, tools/profile_step.py --c 16)"},
+                   "source": "ncu --set full --clock-control none --import-source on, tools/profile_step.py --c 16 (tools/gpu_r02_final.sh; raw page exported on the GPU box)"},
                   open('profiles/r02_k2_dram_traffic.json', 'w'), indent=1)
         break
 PY

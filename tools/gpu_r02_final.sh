@@ -14,3 +14,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 python tools/profile_step.py --c 16 --steps 1 > gpurun_out/r02/final_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:thz_p2_k -c 6 -o gpurun_out/r02/prof_r02_final python tools/profile_step.py --c 16 --steps 1 > gpurun_out/r02/final_ncu_full.log 2>&1
 tail -2 gpurun_out/r02/final_ncu_full.log
+# the report itself can exceed what gpurun brings back (64 MiB): export the two pages that are read afterwards, drop the report
+ncu -i gpurun_out/r02/prof_r02_final.ncu-rep --page raw --csv > gpurun_out/r02/final_ncu_raw.csv 2>/dev/null
+ncu -i gpurun_out/r02/prof_r02_final.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/r02/final_ncu_source.csv.gz
+ls -la gpurun_out/r02/prof_r02_final.ncu-rep gpurun_out/r02/final_ncu_raw.csv gpurun_out/r02/final_ncu_source.csv.gz
+rm -f gpurun_out/r02/prof_r02_final.ncu-rep
