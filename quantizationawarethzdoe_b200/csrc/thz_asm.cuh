@@ -193,6 +193,8 @@ struct ColArgs {
     cpx* Tout;                // separate output buffer (NULL: in place in T)
     int half_in, half_out;    // 1: input / output rows are exactly [Hp/4, 3Hp/4): pruned first / last stage
     int tout_tiled;           // k > 0: Tout is blocked as well (experiment), 0: row-major
+    int pf_blocks;            // > 0 (static kernels, blocked input): every CTA asks the L2 for the 4-column blocks that lie this
+                              //    many blocks ahead of its own -- the tile of the CTA that will take its place on the SM
     int fast;                 // 1: the configuration the specialised column kernel serves (thz_p2_k2f): centred 2x padding on
                               //    the column axis (half_in && half_out), 4-column blocked input, row-major output in Tout,
                               //    whole column tiles, first radix 16 -- every address offset is then a compile-time constant
