@@ -316,6 +316,8 @@ struct RowInvArgs {
     SlabArgs slab;            // parts > 1: gather the input rows from column slabs instead of T
     int half_out;             // 1: the output columns are exactly [Wp/4, 3Wp/4): pruned last stage
     int t_tiled;              // k > 0: T is stored in 2^k-column blocks (experiment)
+    int pf_groups;            // > 0 (static kernel, row-major T): every CTA asks the L2 for the first rows of the CTA that will
+                              //    take its place -- the row group this many groups further on (same field range)
 };
 
 THZ_HD void k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nthreads) {

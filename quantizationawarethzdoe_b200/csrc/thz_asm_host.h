@@ -363,6 +363,13 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         const long blocks = (resident * L->k2.cols * pct) / 400;
         L->k2.pf_blocks = (int)(pct <= 0 ? 0 : (blocks < 1 ? 1 : blocks));
     }
+    L->k3.pf_groups = 0;
+    if (L->p2_w && L->k3.t_tiled == 0 && d->slab_parts <= 1) {
+        const char* e = getenv("THZ_K3_PF");
+        const long pct = e ? atol(e) : 100;
+        const long resident = (long)sm_count * thz_p2_min_blocks_rt(d->Wp);
+        L->k3.pf_groups = (int)(pct <= 0 ? 0 : (resident * pct / 100 < 1 ? 1 : resident * pct / 100));
+    }
     L->k2.fast = (L->p2_h && L->k2.half_in && L->k2.half_out && L->k2.t_tiled == 2 && L->k2.tout_tiled == 0 && L->k2.Tout &&
                   p2_k2_fast_ok_rt(d->Hp) && d->Wp % L->k2.cols == 0 && d->Wp % 4 == 0 &&
                   (d->tf_mode != 0 || d->tf_row_chunked) && L->k2_threads == thz_p2_col_threads_rt(d->Hp) &&
