@@ -101,6 +101,10 @@ void thz_launch_begin(cudaStream_t stream, int kernel_class) {
     g_open_event = a;
 }
 
+void thz_launch_note(int kernel_class) {
+    if (kernel_class >= 0 && kernel_class < THZ_KC_COUNT) g_launches_cls[kernel_class].fetch_add(1, std::memory_order_relaxed);
+}
+
 void thz_launch_end(cudaStream_t stream, int kernel_class) {
     if (!g_prof_on.load(std::memory_order_relaxed) || !g_open_event) return;
     ProfRec r;

@@ -261,6 +261,40 @@ def test_full_size_properties(dev):
     assert Ax.detach().norm() <= x1.norm() * (1 + 1e-5)
 
 
+@pytest.mark.parametrize("n,modes", [(1024, ("inregister", "cached")), (2048, ("inregister", "cached")), (4096, ("inregister",))])
+def test_column_pass_tma_store_is_bit_identical(dev, monkeypatch, n, modes):
+    """Column lengths 2048 / 4096 / 8192 under centred 2x padding: the column kernel hands its output to the TMA
+    (cp.async.bulk.tensor stores, thz_p2_k2ft; launch class 9 counts them).  Forward field and adjoint must equal the
+    plain-store kernel (THZ_NO_K2TMA=1) bit for bit, for every transfer-function mode, and the TMA kernel must be the one
+    that ran."""
+    from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, _native as N
+    lib = N.lib()
+    torch.manual_seed(11)
+    x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+    gy = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+    for mode in modes:
+        out = {}
+        for tma in (True, False):
+            if tma:
+                monkeypatch.delenv("THZ_NO_K2TMA", raising=False)
+            else:
+                monkeypatch.setenv("THZ_NO_K2TMA", "1")
+            a = ASM_prop(z_distance=0.1, device=dev, kernel_mode=mode)
+            a.check_Zc = False
+            xg = x.clone().requires_grad_(True)
+            c9, c1 = lib.thz_launch_count_class(9), lib.thz_launch_count_class(1)
+            y = a(ElectricField(xg, wavelengths=[1 * mm], spacing=0.5 * mm, device=dev)).data
+            (gx,) = torch.autograd.grad(y, xg, gy)
+            torch.cuda.synchronize()
+            d9, d1 = lib.thz_launch_count_class(9) - c9, lib.thz_launch_count_class(1) - c1
+            assert d1 == 2 and d9 == (2 if tma else 0), (n, mode, tma, d1, d9)
+            out[tma] = (y.detach().clone(), gx.clone())
+        assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1]), (n, mode)
+        assert float(out[True][0].abs().max()) > 0
+        del out
+    monkeypatch.delenv("THZ_NO_K2TMA", raising=False)
+
+
 def _doe_layer(name, g, dev):
     import quantizationawarethzdoe_b200 as Q
     N_ = g["x"].shape[-1]
