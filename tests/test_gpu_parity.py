@@ -262,23 +262,25 @@ def test_full_size_properties(dev):
 
 
 @pytest.mark.parametrize("n,modes", [(1024, ("inregister", "cached")), (2048, ("inregister", "cached")), (4096, ("inregister",))])
-def test_column_pass_tma_store_is_bit_identical(dev, monkeypatch, n, modes):
-    """Column lengths 2048 / 4096 / 8192 under centred 2x padding: the column kernel hands its output to the TMA
-    (cp.async.bulk.tensor stores, thz_p2_k2ft; launch class 9 counts them).  Forward field and adjoint must equal the
-    plain-store kernel (THZ_NO_K2TMA=1) bit for bit, for every transfer-function mode, and the TMA kernel must be the one
-    that ran."""
+def test_tma_stores_are_bit_identical(dev, monkeypatch, n, modes):
+    """Transform lengths 2048 / 4096 / 8192 under centred 2x padding: the row-FFT kernel and the column kernel hand their
+    output to the TMA (cp.async.bulk.tensor stores: thz_p2_k1t into the blocked intermediate, thz_p2_k2ft into the row-major
+    one; launch class 9 counts them).  Forward field and adjoint must equal the plain-store kernels (THZ_NO_K1TMA=1,
+    THZ_NO_K2TMA=1) bit for bit, for both transfer-function modes, and the TMA kernels must be the ones that ran."""
     from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, _native as N
     lib = N.lib()
     torch.manual_seed(11)
     x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
     gy = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
+    variants = (("both", (), 4), ("k1_only", ("THZ_NO_K2TMA",), 2), ("k2_only", ("THZ_NO_K1TMA",), 2), ("plain", ("THZ_NO_K1TMA", "THZ_NO_K2TMA"), 0))
     for mode in modes:
         out = {}
-        for tma in (True, False):
-            if tma:
-                monkeypatch.delenv("THZ_NO_K2TMA", raising=False)
-            else:
-                monkeypatch.setenv("THZ_NO_K2TMA", "1")
+        for name, off, expect in variants:
+            for v in ("THZ_NO_K1TMA", "THZ_NO_K2TMA"):
+                if v in off:
+                    monkeypatch.setenv(v, "1")
+                else:
+                    monkeypatch.delenv(v, raising=False)
             a = ASM_prop(z_distance=0.1, device=dev, kernel_mode=mode)
             a.check_Zc = False
             xg = x.clone().requires_grad_(True)
@@ -287,12 +289,14 @@ def test_column_pass_tma_store_is_bit_identical(dev, monkeypatch, n, modes):
             (gx,) = torch.autograd.grad(y, xg, gy)
             torch.cuda.synchronize()
             d9, d1 = lib.thz_launch_count_class(9) - c9, lib.thz_launch_count_class(1) - c1
-            assert d1 == 2 and d9 == (2 if tma else 0), (n, mode, tma, d1, d9)
-            out[tma] = (y.detach().clone(), gx.clone())
-        assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1]), (n, mode)
-        assert float(out[True][0].abs().max()) > 0
+            assert d1 == 2 and d9 == expect, (n, mode, name, d1, d9)
+            out[name] = (y.detach().clone(), gx.clone())
+        for name in ("both", "k1_only", "k2_only"):
+            assert torch.equal(out[name][0], out["plain"][0]) and torch.equal(out[name][1], out["plain"][1]), (n, mode, name)
+        assert float(out["both"][0].abs().max()) > 0
         del out
-    monkeypatch.delenv("THZ_NO_K2TMA", raising=False)
+    for v in ("THZ_NO_K1TMA", "THZ_NO_K2TMA"):
+        monkeypatch.delenv(v, raising=False)
 
 
 def _doe_layer(name, g, dev):

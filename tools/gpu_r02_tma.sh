@@ -1,4 +1,4 @@
-# column pass with TMA tensor stores (thz_p2_k2ft): parity vs the plain-store kernel, full GPU suite, A/B bench
+# row-FFT and column kernels with TMA tensor stores (thz_p2_k1t, thz_p2_k2ft): parity vs the plain-store kernels, full GPU suite, A/B bench
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out/r02
 rm -f gpurun_out/parity_errors.jsonl
@@ -16,7 +16,7 @@ except Exception as e:
     print(name,"FAILED",e, open('gpurun_out/r02/tma_%s.err'%name).read()[-800:])
 PY
 }
-run tma
-run plain THZ_NO_K2TMA=1
-run tma2
+run both
+run k2only THZ_NO_K1TMA=1
+run both2
 timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
