@@ -299,7 +299,8 @@ int thz_score_thickness(const void* thickness, const void* lut, int32_t L, float
 uint64_t thz_launch_count(void);
 /* launches of one kernel class so far: 0 row FFT, 1 column pass, 2 row iFFT, 3 fft2 column pass, 4 DOE modulation / field
  * multiply, 5 quantizers, 6 CUDA-core Toeplitz GEMM, 7 loss / optimizer, 8 tcgen05 Toeplitz GEMM (+ its prologue
- * multiply), 9 those of the column passes (also counted under 1) whose output left through TMA tensor stores. */
+ * multiply), 9 those launches of classes 0 / 1 / 2 (counted there as well) that ran the TMA variants of the kernels:
+ * tensor stores of the row-FFT and column kernels, bulk-copy staging of the row-iFFT kernel. */
 uint64_t thz_launch_count_class(int32_t kernel_class);
 int thz_profile_enable(int32_t on);
 int thz_profile_read(int32_t nclasses, float* ms_sum, int32_t* count);

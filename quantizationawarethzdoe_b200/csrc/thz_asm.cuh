@@ -195,6 +195,8 @@ struct ColArgs {
     int tout_tiled;           // k > 0: Tout is blocked as well (experiment), 0: row-major
     int pf_blocks;            // > 0 (static kernels, blocked input): every CTA asks the L2 for the 4-column blocks that lie this
                               //    many blocks ahead of its own -- the tile of the CTA that will take its place on the SM
+    int t2_perm;              // R > 0 (fast kernel, 2 columns per CTA, set by thz_asm_propagate): the columns of Tout are stored in the
+                              //    order the TMA-staged row-iFFT kernel reads them, thz_t2_perm_col below (0: natural order)
     int fast;                 // 1: the configuration the specialised column kernel serves (thz_p2_k2f): centred 2x padding on
                               //    the column axis (half_in && half_out), 4-column blocked input, row-major output in Tout,
                               //    whole column tiles, first radix 16 -- every address offset is then a compile-time constant
@@ -318,7 +320,18 @@ struct RowInvArgs {
     int t_tiled;              // k > 0: T is stored in 2^k-column blocks (experiment)
     int pf_groups;            // > 0 (static kernel, row-major T): every CTA asks the L2 for the first rows of the CTA that will
                               //    take its place -- the row group this many groups further on (same field range)
+    int t2_perm;              // R > 0: the columns of T are permuted (thz_t2_perm_col) and the kernel is thz_p2_k3t
 };
+
+// Column order of the K2 -> K3 intermediate when the row-iFFT kernel stages its rows with one TMA bulk copy (thz_p2_k3t).
+// That kernel's first butterfly (last FFT stage, radix R, unit sub-block length) owns the R consecutive slots R u .. R u + R - 1
+// of a line; reading them from a DENSE copy of the row would put all threads of a warp on one bank.  With slot p = R u + t
+// stored at column  (t / 2) (2 W / R) + 2 u + (t % 2)  thread u reads 16 bytes at [t / 2][u]: consecutive threads, consecutive
+// addresses.  Even / odd slot pairs stay adjacent, which is what the column kernel's 2-column tiles write.
+THZ_HD int thz_t2_perm_col(int p, int R, int W) {
+    const int t = p % R, u = p / R;
+    return (t >> 1) * (2 * (W / R)) + 2 * u + (t & 1);
+}
 
 THZ_HD void k3_load(const RowInvArgs& a, cpx* s, int bx, int f, int tid, int nthreads) {
     const int pitch = thz_padded_len(a.Wp);

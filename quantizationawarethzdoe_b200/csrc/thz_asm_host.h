@@ -364,6 +364,8 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
         L->k2.pf_blocks = (int)(pct <= 0 ? 0 : (blocks < 1 ? 1 : blocks));
     }
     L->k3.pf_groups = 0;
+    L->k2.t2_perm = 0;        // thz_asm_propagate turns the permuted intermediate on (device library only)
+    L->k3.t2_perm = 0;
     if (L->p2_w && L->k3.t_tiled == 0 && d->slab_parts <= 1) {
         const char* e = getenv("THZ_K3_PF");
         const long pct = e ? atol(e) : 100;

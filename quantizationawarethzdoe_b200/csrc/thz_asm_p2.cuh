@@ -510,7 +510,8 @@ template <int N, int COLS, int NT>
 THZ_HD void p2k2f_last(const ColArgs& a, const cpx* s, const cpx* tws, int bx, int by, int tid) {
     typedef P2Stage<N, 0> St;
     constexpr int NB = St::NB, M = St::M, ITEMS = (COLS * NB + NT - 1) / NT;
-    cpx* tile = a.Tout + (size_t)by * a.rowsT * a.Wp + (size_t)bx * COLS;       // row-major, row 0 = canvas row N / 4
+    const int c_out = a.t2_perm ? thz_t2_perm_col(bx * COLS, a.t2_perm, a.Wp) : bx * COLS;   // (permuted: COLS == 2, an even / odd pair)
+    cpx* tile = a.Tout + (size_t)by * a.rowsT * a.Wp + (size_t)c_out;           // row-major, row 0 = canvas row N / 4
     const size_t step = (size_t)M * a.Wp;
 #pragma unroll K2F_UNROLL
     for (int k = 0; k < ITEMS; ++k) {

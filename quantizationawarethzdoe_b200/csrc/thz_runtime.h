@@ -14,8 +14,9 @@ int thz_sm_count(void);
 // Kernel classes for the launch counter / optional per-kernel event timing (thz_profile_*).
 // THZ_KC_CZT = the CUDA-core Toeplitz GEMM (+ the prologue multiply), THZ_KC_CZT_TC = the tcgen05 kernel: separate classes so
 // that a caller can tell which implementation produced a result (thz_launch_count_class).
-// THZ_KC_COL_TMA is a side counter (thz_launch_note): column-pass launches whose output left through TMA tensor stores
-// (thz_p2_k2ft); those launches are counted and timed under THZ_KC_COL like every other column pass.
+// THZ_KC_COL_TMA is a side counter (thz_launch_note): launches of the kernel variants that move their output / input with the
+// TMA (thz_p2_k1t and thz_p2_k2ft: tensor stores; thz_p2_k3t: bulk-copy staging of the permuted intermediate); those
+// launches are counted and timed under their own class (0 / 1 / 2) like every other launch.
 enum { THZ_KC_ROW_FWD = 0, THZ_KC_COL = 1, THZ_KC_ROW_INV = 2, THZ_KC_FFT2_COL = 3, THZ_KC_DOE = 4, THZ_KC_QUANT = 5,
        THZ_KC_CZT = 6, THZ_KC_TRAIN = 7, THZ_KC_CZT_TC = 8, THZ_KC_COL_TMA = 9, THZ_KC_COUNT = 10 };
 // Called around every kernel launch: counts it and, when profiling is enabled, brackets it with CUDA events

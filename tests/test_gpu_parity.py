@@ -265,18 +265,23 @@ def test_full_size_properties(dev):
 def test_tma_stores_are_bit_identical(dev, monkeypatch, n, modes):
     """Transform lengths 2048 / 4096 / 8192 under centred 2x padding: the row-FFT kernel and the column kernel hand their
     output to the TMA (cp.async.bulk.tensor stores: thz_p2_k1t into the blocked intermediate, thz_p2_k2ft into the row-major
-    one; launch class 9 counts them).  Forward field and adjoint must equal the plain-store kernels (THZ_NO_K1TMA=1,
-    THZ_NO_K2TMA=1) bit for bit, for both transfer-function modes, and the TMA kernels must be the ones that ran."""
+    one), and the row-iFFT kernel stages its rows with one bulk copy per field from a column-permuted intermediate
+    (thz_p2_k3t; the permuting store is exercised with the column kernel's TMA and plain stores).  Launch class 9 counts the
+    TMA variants.  Forward field and adjoint must equal the plain kernels (THZ_NO_K1TMA=1, THZ_NO_K2TMA=1, THZ_NO_K3TMA=1)
+    bit for bit, for both transfer-function modes, and the TMA kernels must be the ones that ran."""
     from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, _native as N
     lib = N.lib()
     torch.manual_seed(11)
     x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
     gy = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
-    variants = (("both", (), 4), ("k1_only", ("THZ_NO_K2TMA",), 2), ("k2_only", ("THZ_NO_K1TMA",), 2), ("plain", ("THZ_NO_K1TMA", "THZ_NO_K2TMA"), 0))
+    full = 6 if n >= 2048 else 4        # the row-iFFT kernel's TMA staging needs 2-column tiles in the column kernel (column length >= 4096)
+    variants = (("all", (), full), ("k1_only", ("THZ_NO_K2TMA", "THZ_NO_K3TMA"), 2), ("k2_only", ("THZ_NO_K1TMA", "THZ_NO_K3TMA"), 2),
+                ("k3_plain_k2", ("THZ_NO_K1TMA", "THZ_NO_K2TMA"), full - 4), ("plain", ("THZ_NO_K1TMA", "THZ_NO_K2TMA", "THZ_NO_K3TMA"), 0))
+    switches = ("THZ_NO_K1TMA", "THZ_NO_K2TMA", "THZ_NO_K3TMA")
     for mode in modes:
         out = {}
         for name, off, expect in variants:
-            for v in ("THZ_NO_K1TMA", "THZ_NO_K2TMA"):
+            for v in switches:
                 if v in off:
                     monkeypatch.setenv(v, "1")
                 else:
@@ -291,11 +296,11 @@ def test_tma_stores_are_bit_identical(dev, monkeypatch, n, modes):
             d9, d1 = lib.thz_launch_count_class(9) - c9, lib.thz_launch_count_class(1) - c1
             assert d1 == 2 and d9 == expect, (n, mode, name, d1, d9)
             out[name] = (y.detach().clone(), gx.clone())
-        for name in ("both", "k1_only", "k2_only"):
+        for name in ("all", "k1_only", "k2_only", "k3_plain_k2"):
             assert torch.equal(out[name][0], out["plain"][0]) and torch.equal(out[name][1], out["plain"][1]), (n, mode, name)
-        assert float(out["both"][0].abs().max()) > 0
+        assert float(out["all"][0].abs().max()) > 0
         del out
-    for v in ("THZ_NO_K1TMA", "THZ_NO_K2TMA"):
+    for v in switches:
         monkeypatch.delenv(v, raising=False)
 
 

@@ -16,7 +16,7 @@ except Exception as e:
     print(name,"FAILED",e, open('gpurun_out/r02/tma_%s.err'%name).read()[-800:])
 PY
 }
-run both
-run k2only THZ_NO_K1TMA=1
-run both2
+run all
+run nok3 THZ_NO_K3TMA=1
+run all2
 timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
