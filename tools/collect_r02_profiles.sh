@@ -21,7 +21,7 @@ for r in rows[2:]:
         def gb(name):
             v, u = float(r[h[name]]), rows[1][h[name]]
             return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[u]
-        json.dump({"kernel": "thz_p2_k2f<4096,0>", "fields_per_launch": 16, "dram_bytes_read": gb('dram__bytes_read.sum'),
+        json.dump({"kernel": r[h["Kernel Name"]].replace("void ", ""), "fields_per_launch": 16, "dram_bytes_read": gb('dram__bytes_read.sum'),
                    "dram_bytes_write": gb('dram__bytes_write.sum'),
                    "source": "ncu --set full --clock-control none --import-source on, tools/profile_step.py --c 16 (tools/gpu_r02_final.sh; raw page exported on the GPU box)"},
                   open('profiles/r02_k2_dram_traffic.json', 'w'), indent=1)
