@@ -8,3 +8,5 @@ mkdir -p variants
 THZ_NVCC_EXTRA="$*" python -m quantizationawarethzdoe_b200.build --force > /dev/null
 cp quantizationawarethzdoe_b200/csrc/libthzdoe.so variants/libthzdoe_$name.so
 echo built variants/libthzdoe_$name.so with "$*"
+python -m quantizationawarethzdoe_b200.build --force > /dev/null
+echo rebuilt the default library

@@ -17,6 +17,5 @@ except Exception as e:
 PY
 }
 run all
-run nok3 THZ_NO_K3TMA=1
 run all2
 timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
