@@ -1,4 +1,4 @@
-# after the TMA kernels: re-check the tuning knobs that were set while the column kernel was bound by the L1 data pipe
+# A/B of experiment libraries (variants/) against the default library; the default run doubles as the check of the in-tree build
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out/r02
 run() {
@@ -15,9 +15,5 @@ except Exception as e:
 PY
 }
 run base
-run k2fu2 THZ_LIB=variants/libthzdoe_k2fu2.so
-run k2pf50 THZ_K2_PF=50
-run k2pf200 THZ_K2_PF=200
-run k3pf50 THZ_K3_PF=50
-run k3pf200 THZ_K3_PF=200
+for v in variants/libthzdoe_*.so; do n=$(basename $v .so); n=${n#libthzdoe_}; run $n THZ_LIB=$v; THZ_LIB=$v timeout 200 python -m pytest tests -m gpu -q -x -k "tma_store" 2>&1 | tail -1; done
 run base2
