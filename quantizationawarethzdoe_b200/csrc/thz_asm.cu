@@ -134,9 +134,8 @@ extern "C" int thz_asm_propagate(const thz_asm_desc* d, void* stream_) {
         if (rc != THZ_OK) return thz_set_error(rc, "thz_asm_propagate: line does not fit in shared memory");
         // K2 -> K3 intermediate with permuted columns + TMA-staged row-iFFT kernel (thz_p2_k3t): whole pipeline on the static
         // kernels, fast column kernel with 2-column tiles, row-major second buffer (THZ_NO_K3TMA=1: off)
-        if (stages == 7 && d->slab_parts <= 1 && L.p2_w && L.p2_h && L.k2.fast && L.k2.cols == 2 && L.k2.tout_tiled == 0 &&
-            L.k3.t_tiled == 0 && L.k3.T == L.k2.Tout && thz_p2_k3_tma_radix(d->Wp) > 0 && !thz_env_is_1("THZ_NO_K3TMA")) {
-            L.k2.t2_perm = thz_p2_k3_tma_radix(d->Wp);
+        if (!thz_env_is_1("THZ_NO_K3TMA")) {
+            L.k2.t2_perm = thz_asm_t2_perm_radix(d, &L, stages);
             L.k3.t2_perm = L.k2.t2_perm;
         }
         L.k3.gh_atomic = (d->doe_mode == 2 && d->doe_gh_mode == 1) ? 2 : (d->doe_mode == 2 && (nchunks > 1 || L.k3_gridy > 1)) ? 1 : 0;

@@ -380,3 +380,14 @@ static inline int thz_asm_plan_chunk(const thz_asm_desc* d, int f0, int nbc, int
     if (d->tf_row_chunked && d->tf_mode == 0 && !L->p2_h) return THZ_E_UNSUPPORTED;   // chunked row vectors: static column kernels only
     return THZ_OK;
 }
+
+// Radix R > 0 if this chunk can run with the column-permuted K2 -> K3 intermediate and the TMA-staged row-iFFT kernel
+// (ColArgs.t2_perm = RowInvArgs.t2_perm = R): whole pipeline on the static kernels, fast column kernel with 2-column tiles,
+// row-major second buffer, a line length thz_p2_k3t serves.  Applied by thz_asm_propagate (off: THZ_NO_K3TMA=1) and, for the
+// CPU replay of the same index arithmetic, by the test harness (on: THZ_EMUL_T2_PERM=1).
+static inline int thz_asm_t2_perm_radix(const thz_asm_desc* d, const AsmLaunch* L, int stages) {
+    if (stages != 7 || d->slab_parts > 1 || !L->p2_w || !L->p2_h || !L->k2.fast || L->k2.cols != 2 || L->k2.tout_tiled != 0 ||
+        L->k3.t_tiled != 0 || L->k3.T != L->k2.Tout)
+        return 0;
+    return p2_k3_tma_ok(d->Wp) ? p2_radix(d->Wp, p2_stages(d->Wp) - 1) : 0;
+}

@@ -599,6 +599,36 @@ THZ_HD void p2k3_prefetch(const RowInvArgs& a, cpx* s, int bx, int f, int tid, i
     }
 }
 
+// ---- TMA-staged variant (thz_p2_k3t, thz_asm_p2_kernels.inc): which lengths it serves, and its first butterfly, which reads
+// the dense staged copy of a column-permuted row (thz_t2_perm_col) and writes the padded line buffer
+THZ_HD constexpr bool p2_k3_tma_ok(int N) {
+    if (!sp_static_ok(N) || (N & (N - 1)) != 0 || N < 2048 || !p2_row_pipelined(N)) return false;
+    const int R = p2_radix(N, p2_stages(N) - 1);
+    return R % 2 == 0 && R <= 16 && (p2_row_lines(N) * (N / R)) % p2_row_threads(N) == 0;
+}
+template <int N>
+THZ_HD void p2k3_first_from_dense(cpx* line, const cpx* dense, int tid) {
+    constexpr int S = p2_stages(N) - 1, R = p2_radix(N, S), NBU = N / R, LINES = p2_row_lines(N), NT = p2_row_threads(N);
+    constexpr int ITEMS = LINES * NBU / NT, PITCH = p2_pitch(N);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int w = tid + k * NT;
+        const int l = w / NBU, u = w % NBU, p0 = u * R;
+        const float4* g = reinterpret_cast<const float4*>(dense + l * N) + u;
+        cpx v[R];
+#pragma unroll
+        for (int h = 0; h < R / 2; ++h) {
+            const float4 q = g[h * NBU];
+            v[2 * h] = cmake(q.x, q.y);
+            v[2 * h + 1] = cmake(q.z, q.w);
+        }
+        Dft<R, true>::run(v);
+        cpx* p = line + l * PITCH + p0 + (p0 >> 4);
+#pragma unroll
+        for (int t = 0; t < R; ++t) p[t] = v[t];
+    }
+}
+
 // number of register accumulators a thread needs: one per output of each of its stage-0 butterflies
 template <int N>
 THZ_HD constexpr int p2k3_acc() {

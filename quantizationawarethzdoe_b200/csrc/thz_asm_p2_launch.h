@@ -7,6 +7,3 @@
 int thz_p2_launch_k1(const RowFwdArgs& a, int grid, int threads, size_t smem, cudaStream_t stream);
 int thz_p2_launch_k2(const ColArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream);
 int thz_p2_launch_k3(const RowInvArgs& a, int gridx, int gridy, int threads, size_t smem, cudaStream_t stream);
-// last-stage radix of the row plan if the TMA-staged row-iFFT kernel (thz_p2_k3t, permuted K2 -> K3 intermediate) serves this
-// line length, else 0
-int thz_p2_k3_tma_radix(int Wp);

@@ -199,6 +199,22 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
                 for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
                 continue;
             }
+            if constexpr (p2_k3_tma_ok(N)) {
+                if (a.t2_perm) {       // thz_p2_k3t: dense staged rows (the bulk copy is a memcpy here) -> first butterfly -> padded line buffer
+                    cpx* g = s + BUF;
+                    const int r0 = bx * LINES;
+                    const int nvalid = (a.outH - r0) < LINES ? (a.outH - r0) : LINES;
+                    for (int f = f_lo; f < f_hi; ++f) {
+                        memcpy(g, a.T + ((size_t)f * a.rowsT + r0) * N, (size_t)nvalid * N * sizeof(cpx));
+                        for_threads(nt, [&](int t) { p2k3_first_from_dense<N>(s, g, t); });
+                        e_inv_rows<N, p2_stages(N) - 2, 1, LINES>(s, nt, tws.data());
+                        if (a.doe.lphase) for_threads(nt, [&](int t) { p2k3_last<N, NACC, 2>(a, s, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                        else for_threads(nt, [&](int t) { p2k3_last<N, NACC, 1>(a, s, tws.data(), bx, f, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                    }
+                    for_threads(nt, [&](int t) { p2k3_flush<N, NACC>(a, bx, t, nt, *(acc_t*)&accs[(size_t)t * NACC]); });
+                    continue;
+                }
+            }
             if (f_lo < f_hi) for_threads(nt, [&](int t) { p2k3_prefetch<N>(a, s, bx, f_lo, t, nt); });
             for (int f = f_lo; f < f_hi; ++f, cur ^= 1) {
                 cpx* sc = s + cur * BUF;
@@ -222,6 +238,10 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
     default: return THZ_E_UNSUPPORTED;               \
     }
 
+static int g_last_t2_perm = 0;
+// radix of the column permutation the last thz_emul_asm_propagate chunk ran with (0: natural column order)
+extern "C" int thz_emul_last_t2_perm(void) { return g_last_t2_perm; }
+
 extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
     int rc = thz_asm_validate(d);
     if (rc != THZ_OK) return rc;
@@ -236,6 +256,11 @@ extern "C" int thz_emul_asm_propagate(const thz_asm_desc* d, int sm_count) {
         AsmLaunch L;
         rc = thz_asm_plan_chunk(d, f0, nbc, sm_count, &L);
         if (rc != THZ_OK) return rc;
+        if (thz_env_is_1("THZ_EMUL_T2_PERM")) {      // column-permuted K2 -> K3 intermediate, as thz_asm_propagate sets it up
+            L.k2.t2_perm = thz_asm_t2_perm_radix(d, &L, stages);
+            L.k3.t2_perm = L.k2.t2_perm;
+        }
+        g_last_t2_perm = L.k3.t2_perm;
         L.k3.gh_atomic = (d->doe_mode == 2 && (nchunks > 1 || L.k3_gridy > 1)) ? 1 : 0;
         if ((stages & 4) && L.k3.gh_atomic && !zeroed) {
             memset(d->doe_gh, 0, (size_t)d->outH * d->outW * sizeof(float));

@@ -252,6 +252,39 @@ def test_layout_and_pruning_switches_do_not_change_the_result(env, monkeypatch):
         assert rel_l2(a, b) < 2e-6
 
 
+def test_column_permuted_intermediate_replay(monkeypatch):
+    """The TMA-staged row-iFFT kernel (thz_p2_k3t) reads a K2 -> K3 intermediate whose columns the column kernel permutes
+    (thz_t2_perm_col; it needs 2-column tiles, i.e. 4096-point columns).  CPU replay of exactly that index arithmetic --
+    permuting store of thz_p2_k2f, dense staged rows, first butterfly from the dense copy -- against the default path:
+    forward and DOE adjoint must be bit-identical (same values, same operations, another place in memory)."""
+    B, C, H, W = 1, 1, 2048, 1024                    # 4096 x 2048 padded
+    lams, dxy, z = [1.03e-3], 0.5e-3, 0.1
+    torch.manual_seed(5)
+    x = torch.randn(B, C, H, W, dtype=torch.complex64)
+    g = torch.randn(B, C, H, W, dtype=torch.complex64)
+    h = torch.rand(H, W) * 1e-3
+    coef = AH.doe_coefficients(lams, 2.66, 0.003)
+
+    def run():
+        base, _ = _setup(B, C, H, W, None, lams, dxy, z, mode=0)
+        y = torch.zeros_like(x)
+        _run(x, dict(base, x=x, y=y, doe_mode=1, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef))
+        gx, gh = torch.zeros_like(x), torch.zeros(H, W)
+        adj = dict(base, x=g, y=gx, tf_conj=1, doe_mode=2, doe_base=DO.BASE_PLANE_THICKNESS, hmap=h, coef=coef, xsaved=x, gh=gh,
+                   inH=base["outH"], inW=base["outW"], in_r0=base["out_r0"], in_c0=base["out_c0"],
+                   outH=base["inH"], outW=base["inW"], out_r0=base["in_r0"], out_c0=base["in_c0"])
+        _run(g, adj)
+        return y, gx, gh
+
+    ref = run()
+    assert float(ref[0].abs().max()) > 0 and float(ref[2].abs().max()) > 0 and E.thz_emul_last_t2_perm() == 0
+    monkeypatch.setenv("THZ_EMUL_T2_PERM", "1")
+    got = run()
+    assert E.thz_emul_last_t2_perm() == 8            # 2048-point rows: 16 x 16 x 8, last radix 8 -- the permuted path really ran
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+
+
 SOFTMAX_CASES = ("gumbel_hard", "gumbel_soft", "plain_hard", "plain_soft")
 
 
