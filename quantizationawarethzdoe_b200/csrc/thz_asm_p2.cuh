@@ -53,6 +53,8 @@ THZ_HD constexpr bool p2_row_pipelined(int N) { return N <= 8192; }
 // MODE of the row kernels (separate instantiations: the common case pays nothing for the others):
 //   0 plain / DOE transmission evaluated per pixel;  1 pointwise elements in front (aperture mask, lens kernel);
 //   2 quantised DOE: the staged "height" row holds int32 level indices and the transmission comes from a [C][levels] table
+//   3 (row-iFFT kernels only) plain output -- no DOE adjoint, no elements: the gradient accumulators, the epilogue's prefetch ring
+//     and its code are compiled out (forward passes and plain adjoints; the radix-25 lengths spill 300 bytes less)
 template <int MODE>
 struct K1Loader {
     const cpx* xr;      // row of x (NULL: line beyond the end of the batch)
@@ -652,12 +654,14 @@ struct K3Storer {
     cpx xq[PF];           // prefetch ring (registers after unrolling)
     float hq[PF];
     THZ_HD void prefetch(int pos, int t) {
+        if constexpr (MODE == 3) return;
         const int c = pos - out_c0;
         if (hrow == nullptr || (unsigned)c >= (unsigned)outW) return;
         hq[t % PF] = thz_ldg(hrow + c);
         xq[t % PF] = thz_ldg(xrow + c);
     }
     THZ_HD void prefetch_live(int pos, int slot) {      // pos known to be inside the crop
+        if constexpr (MODE == 3) return;
         if (hrow == nullptr) return;
         const int c = pos - out_c0;
         hq[slot % PF] = thz_ldg(hrow + c);
@@ -683,6 +687,10 @@ struct K3Storer {
     }
     THZ_HD void emit(int c, int slot, int t, cpx v) {
         v = cscale(v, scale);
+        if constexpr (MODE == 3) {                 // plain output known at compile time: no epilogue state is kept alive
+            yrow[c] = v;
+            return;
+        }
         if (hrow == nullptr) {
             yrow[c] = elem(v, c, true);            // plain output, or the adjoint of pointwise elements alone
             return;
