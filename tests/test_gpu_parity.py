@@ -261,23 +261,30 @@ def test_full_size_properties(dev):
     assert Ax.detach().norm() <= x1.norm() * (1 + 1e-5)
 
 
-@pytest.mark.parametrize("n,modes", [(1024, ("inregister", "cached")), (2048, ("inregister", "cached")), (4096, ("inregister",))])
-def test_tma_stores_are_bit_identical(dev, monkeypatch, n, modes):
-    """Transform lengths 2048 / 4096 / 8192 under centred 2x padding: the row-FFT kernel and the column kernel hand their
-    output to the TMA (cp.async.bulk.tensor stores: thz_p2_k1t into the blocked intermediate, thz_p2_k2ft into the row-major
-    one), and the row-iFFT kernel stages its rows with one bulk copy per field from a column-permuted intermediate
-    (thz_p2_k3t; the permuting store is exercised with the column kernel's TMA and plain stores).  Launch class 9 counts the
-    TMA variants.  Forward field and adjoint must equal the plain kernels (THZ_NO_K1TMA=1, THZ_NO_K2TMA=1, THZ_NO_K3TMA=1)
-    bit for bit, for both transfer-function modes, and the TMA kernels must be the ones that ran."""
+@pytest.mark.parametrize("shape,modes", [((1024, 1024), ("inregister", "cached")), ((2048, 2048), ("inregister", "cached")),
+                                         ((4096, 4096), ("inregister",)), ((2048, 1024), ("inregister",)), ((1024, 4096), ("inregister",))],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v[0], int) else None)
+def test_tma_stores_are_bit_identical(dev, monkeypatch, shape, modes):
+    """Transform lengths 2048 / 4096 / 8192 under centred 2x padding (square and non-square canvases): the row-FFT kernel and
+    the column kernel hand their output to the TMA (cp.async.bulk.tensor stores: thz_p2_k1t into the blocked intermediate,
+    thz_p2_k2ft into the row-major one), and the row-iFFT kernel stages its rows with one bulk copy per field from a
+    column-permuted intermediate (thz_p2_k3t; the permuting store is exercised with the column kernel's TMA and plain stores).
+    Launch class 9 counts the TMA variants.  Forward field and adjoint must equal the plain kernels (THZ_NO_K1TMA=1,
+    THZ_NO_K2TMA=1, THZ_NO_K3TMA=1) bit for bit, for both transfer-function modes, and the TMA kernels must be the ones that ran."""
     from quantizationawarethzdoe_b200 import ASM_prop, ElectricField, _native as N
     lib = N.lib()
+    h, w = shape
     torch.manual_seed(11)
-    x = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
-    gy = torch.randn(1, 1, n, n, dtype=torch.complex64, device=dev)
-    full = 6 if n >= 2048 else 4        # the row-iFFT kernel's TMA staging needs 2-column tiles in the column kernel (column length >= 4096)
-    variants = (("all", (), full), ("k1_only", ("THZ_NO_K2TMA", "THZ_NO_K3TMA"), 2), ("k2_only", ("THZ_NO_K1TMA", "THZ_NO_K3TMA"), 2),
-                ("k3_plain_k2", ("THZ_NO_K1TMA", "THZ_NO_K2TMA"), full - 4), ("plain", ("THZ_NO_K1TMA", "THZ_NO_K2TMA", "THZ_NO_K3TMA"), 0))
+    x = torch.randn(1, 1, h, w, dtype=torch.complex64, device=dev)
+    gy = torch.randn(1, 1, h, w, dtype=torch.complex64, device=dev)
+    served = (2048, 4096, 8192)
+    k1 = 2 if 2 * w in served else 0                                      # row lines
+    k2 = 2 if 2 * h in served else 0                                      # column lines
+    k3 = 2 if (2 * h in (4096, 8192) and 2 * w in served) else 0          # needs the column kernel's 2-column tiles
     switches = ("THZ_NO_K1TMA", "THZ_NO_K2TMA", "THZ_NO_K3TMA")
+    variants = (("all", (), k1 + k2 + k3), ("k1_only", ("THZ_NO_K2TMA", "THZ_NO_K3TMA"), k1), ("k2_only", ("THZ_NO_K1TMA", "THZ_NO_K3TMA"), k2),
+                ("k3_plain_k2", ("THZ_NO_K1TMA", "THZ_NO_K2TMA"), k3), ("plain", switches, 0))
+    assert k1 + k2 + k3 >= 4
     for mode in modes:
         out = {}
         for name, off, expect in variants:
@@ -294,10 +301,10 @@ def test_tma_stores_are_bit_identical(dev, monkeypatch, n, modes):
             (gx,) = torch.autograd.grad(y, xg, gy)
             torch.cuda.synchronize()
             d9, d1 = lib.thz_launch_count_class(9) - c9, lib.thz_launch_count_class(1) - c1
-            assert d1 == 2 and d9 == expect, (n, mode, name, d1, d9)
+            assert d1 == 2 and d9 == expect, (shape, mode, name, d1, d9)
             out[name] = (y.detach().clone(), gx.clone())
         for name in ("all", "k1_only", "k2_only", "k3_plain_k2"):
-            assert torch.equal(out[name][0], out["plain"][0]) and torch.equal(out[name][1], out["plain"][1]), (n, mode, name)
+            assert torch.equal(out[name][0], out["plain"][0]) and torch.equal(out[name][1], out["plain"][1]), (shape, mode, name)
         assert float(out["all"][0].abs().max()) > 0
         del out
     for v in switches:
