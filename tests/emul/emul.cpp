@@ -238,6 +238,16 @@ static void run_p2_k3(const RowInvArgs& a, int gx, int gy, int nt, size_t smem) 
     default: return THZ_E_UNSUPPORTED;               \
     }
 
+// column of slot p in the column-permuted K2 -> K3 intermediate (thz_asm.cuh) and the radix the library would permute with
+extern "C" int thz_emul_t2_perm_col(int p, int R, int W) { return thz_t2_perm_col(p, R, W); }
+extern "C" int thz_emul_k3_tma_radix(int W) {
+    if (!thz_sp_instantiated(W)) return 0;
+    int r = 0;
+#define THZ_EMUL_R_X(NN) if (W == NN) r = p2_k3_tma_ok(NN) ? p2_radix(NN, p2_stages(NN) - 1) : 0;
+    THZ_SP_SIZES(THZ_EMUL_R_X)
+#undef THZ_EMUL_R_X
+    return r;
+}
 static int g_last_t2_perm = 0;
 // radix of the column permutation the last thz_emul_asm_propagate chunk ran with (0: natural column order)
 extern "C" int thz_emul_last_t2_perm(void) { return g_last_t2_perm; }

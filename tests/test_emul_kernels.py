@@ -252,6 +252,27 @@ def test_layout_and_pruning_switches_do_not_change_the_result(env, monkeypatch):
         assert rel_l2(a, b) < 2e-6
 
 
+def test_column_permutation_is_a_pair_preserving_bijection():
+    """thz_t2_perm_col: for every line length the TMA-staged row-iFFT kernel serves, the slot -> column map of the permuted
+    intermediate is a bijection, keeps even / odd slot pairs adjacent on an even column (the column kernel's 2-column tiles write
+    them as one 16-byte piece), and puts the slots of one butterfly where its thread reads them: [t / 2][u][t % 2]."""
+    served = {}
+    for W in (256, 400, 1024, 2000, 2048, 4096, 8192, 16384):
+        R = E.thz_emul_k3_tma_radix(W)
+        if R:
+            served[W] = R
+    assert served == {2048: 8, 4096: 16, 8192: 4}
+    for W, R in served.items():
+        cols = [E.thz_emul_t2_perm_col(p, R, W) for p in range(W)]
+        assert sorted(cols) == list(range(W))
+        for p in range(0, W, 2):
+            assert cols[p] % 2 == 0 and cols[p + 1] == cols[p] + 1
+        nbu = W // R
+        for u in (0, 1, nbu // 2 + 3, nbu - 1):
+            for t in range(R):
+                assert cols[R * u + t] == (t // 2) * (2 * nbu) + 2 * u + t % 2
+
+
 def test_column_permuted_intermediate_replay(monkeypatch):
     """The TMA-staged row-iFFT kernel (thz_p2_k3t) reads a K2 -> K3 intermediate whose columns the column kernel permutes
     (thz_t2_perm_col; it needs 2-column tiles, i.e. 4096-point columns).  CPU replay of exactly that index arithmetic --
